@@ -1,0 +1,426 @@
+// Hot path (A): fused Tool–Narayanaswamy / Prony viscoelastic update.
+//
+// One launch replaces the 17 Function.interpolate(Expression) passes and 7 array
+// copies that ThermoViscoProblem.solve_timestep makes per step (TVP:370-373, the
+// expressions are VM:111-228, the Taylor stand-in for exp is VM:233-242).
+//
+// COMPILED WITH -fmad=false: the reference's pointwise kernels are FMA-free (FFCx
+// default cffi flags, no -march=native), and lambda*(1 - taylor)/xi cancels
+// catastrophically, so the IEEE operation sequence is mirrored exactly.  Every
+// product/sum below is written in the association order of the Python source.
+//
+// Data movement per CTA tile of VTILE nodes:
+//   * the two fat history tensors s_tilde / sigma_tilde ([node, N, d, d], 432 B per
+//     node each at d=3, N=6) are contiguous per tile, so they are staged into shared
+//     memory with one 1-D TMA bulk copy each (cp.async.bulk -> UBLKCP) signalled on
+//     an mbarrier, updated in place in shared memory and written back with a bulk
+//     store.  No register staging, full-line HBM transactions in both directions.
+//   * while the bulk loads are in flight the CTA evaluates the per-node scalars
+//     (2 exp, the N fictive-temperature relaxations, the 2N Taylor factors and 3N
+//     division chains) spread over (node, term) pairs.
+//   * thin arrays (T, phi, xi, Tf, Tf_partial, sigma) are read/written with plain
+//     coalesced accesses: the flat index of the tile is the thread index.
+#include "sg_common.cuh"
+
+namespace {
+
+constexpr int VTILE = 32;      // nodes per CTA
+constexpr int VTHREADS = 256;  // threads per CTA
+
+struct VKParams {
+    int N;
+    double c_HRg;    // H / Rg            (VM:158)
+    double inv_Tb;   // 1 / Tb
+    double dt;
+    double half_dt;  // dt / 2            (VM:171)
+    double inv_d;    // 1 / dim           (VM:144)
+    double alpha_s;
+    double d_alpha;  // alpha_liquid - alpha_solid (VM:130)
+    double m[SG_MAX_TERMS], lm[SG_MAX_TERMS];
+    double g2[SG_MAX_TERMS], lg[SG_MAX_TERMS];  // g2 = 2.0 * g_n (VM:178)
+    double k[SG_MAX_TERMS], lk[SG_MAX_TERMS];
+};
+
+struct VGather {
+    int n_ld;
+    const int32_t *dofs;
+    const uint8_t *local_point;
+    const double *weights;
+};
+
+// VM:233-242   (1.0 + a) + 0.5*a^2,  a = (-xi)/lambda
+__device__ __forceinline__ double taylor3(double xi, double lambda) {
+    const double a = (-1.0 * xi) / lambda;
+    return (1.0 + a) + 0.5 * (a * a);
+}
+
+// VM:156-161 / VM:162-167
+__device__ __forceinline__ double shift_phi(const VKParams &P, double T) {
+    return exp(P.c_HRg * (P.inv_Tb - 1.0 / T));
+}
+
+__device__ __forceinline__ double gather_eval(const VGather &G, const double *__restrict__ arr, long node) {
+    const double *w = G.weights + (int)G.local_point[node] * G.n_ld;
+    const int32_t *dj = G.dofs + node * G.n_ld;
+    double acc = 0.0;
+    for (int j = 0; j < G.n_ld; ++j) {
+        const double wj = w[j];
+        if (wj != 0.0) acc = acc + wj * arr[dj[j]];
+    }
+    return acc;
+}
+
+__host__ __device__ inline size_t visco_smem_bytes(int N, int DD, bool tensor) {
+    size_t doubles = 6 * (size_t)VTILE * N  // tfp, tg, tk, ds_d, ds_o, dk_d
+                     + 5 * (size_t)VTILE;   // dT, xi, tf, Tc, phi
+    if (tensor) doubles += 2 * (size_t)VTILE * N * DD;
+    return 128 + doubles * sizeof(double);
+}
+
+template <int D, bool SCALAR, bool TENSOR>
+__global__ void __launch_bounds__(VTHREADS)
+visco_kernel(const VKParams P, const sg_visco_fields f, const VGather G, const long n_nodes,
+             const unsigned phases, const int bulk_ok) {
+    constexpr int DD = D * D;
+    constexpr bool GATHER = TENSOR && !SCALAR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *sm = reinterpret_cast<double *>(smem_raw + 128);
+
+    const int N = P.N;
+    const int tid = threadIdx.x;
+    const long tile0 = (long)blockIdx.x * VTILE;
+    const int nn = (int)min((long)VTILE, n_nodes - tile0);
+
+    // shared-memory carve-up
+    double *buf_s = sm;                                   // [nn, N, DD]   s_tilde tile
+    double *buf_k = buf_s + (TENSOR ? VTILE * N * DD : 0);  // [nn, N, DD]   sigma_tilde tile
+    double *s_tfp = buf_k + (TENSOR ? VTILE * N * DD : 0);  // [nn*N]
+    double *s_tg = s_tfp + VTILE * N;
+    double *s_tk = s_tg + VTILE * N;
+    double *s_dsd = s_tk + VTILE * N;
+    double *s_dso = s_dsd + VTILE * N;
+    double *s_dkd = s_dso + VTILE * N;
+    double *s_dT = s_dkd + VTILE * N;  // [nn]
+    double *s_xi = s_dT + VTILE;
+    double *s_tf = s_xi + VTILE;
+    double *s_Tc = s_tf + VTILE;
+    double *s_phi = s_Tc + VTILE;
+
+    const bool ph_tf = SCALAR && (phases & SG_PHASE_TF);
+    const bool ph_shift = SCALAR && (phases & SG_PHASE_SHIFT);
+    const bool ph_strain = TENSOR && (phases & SG_PHASE_STRAIN);
+    const bool ph_stress = TENSOR && (phases & SG_PHASE_STRESS);
+
+    const int tile_elems = nn * N * DD;
+    const uint32_t tile_bytes = (uint32_t)tile_elems * 8u;
+    const bool use_bulk = ph_stress && bulk_ok && (tile_bytes % 16u == 0);
+    const long gbase = tile0 * N * DD;
+
+    // ---- stage 0: start the TMA bulk loads of the two history tiles -------------------
+    if (ph_stress) {
+        if (use_bulk) {
+            if (tid == 0) {
+                sgptx::mbar_init(bar, 1);
+                sgptx::fence_mbar_init();
+            }
+            __syncthreads();
+            if (tid == 0) {
+                sgptx::mbar_expect_tx(bar, 2u * tile_bytes);
+                sgptx::bulk_g2s(buf_s, f.s_tilde + gbase, tile_bytes, bar);
+                sgptx::bulk_g2s(buf_k, f.sigma_tilde + gbase, tile_bytes, bar);
+            }
+        } else {
+            for (int e = tid; e < tile_elems; e += VTHREADS) {
+                buf_s[e] = f.s_tilde[gbase + e];
+                buf_k[e] = f.sigma_tilde[gbase + e];
+            }
+        }
+    }
+
+    // ---- stage 1a: per-node scalars (thread per node) ---------------------------------
+    if (tid < nn) {
+        const long node = tile0 + tid;
+        double Tc, Tp, xi, phi = 0.0;
+        if constexpr (GATHER) {
+            Tc = gather_eval(G, f.T_cur, node);
+            Tp = gather_eval(G, f.T_prev, node);
+            xi = gather_eval(G, f.xi, node);
+            s_tf[tid] = gather_eval(G, f.Tf, node);
+        } else {
+            Tc = f.T_cur[node];
+            Tp = f.T_prev[node];
+            phi = shift_phi(P, Tc);                     // VM:156
+            const double Tn = Tc + (Tc - Tp);           // VM:151
+            const double phin = shift_phi(P, Tn);       // VM:162
+            xi = P.half_dt * (phin - phi);              // VM:171
+            if (ph_tf || ph_shift) f.phi[node] = phi;   // TVP:456, TVP:531
+            if (ph_shift) {
+                f.xi[node] = xi;                        // TVP:541
+                if (f.T_next) f.T_next[node] = Tn;      // TVP:524
+                if (f.phi_next) f.phi_next[node] = phin;  // TVP:533
+            }
+            if (!ph_tf) s_tf[tid] = f.Tf[node];
+        }
+        s_Tc[tid] = Tc;
+        s_dT[tid] = Tc - Tp;
+        s_xi[tid] = xi;
+        s_phi[tid] = phi;
+    }
+    __syncthreads();
+
+    // ---- stage 1b: (node, term) pairs: fictive-temperature relaxation + Taylor factors -
+    const int n_pairs = nn * N;
+    for (int it = tid; it < n_pairs; it += VTHREADS) {
+        const int t = it / N, i = it - t * N;
+        if (ph_tf) {
+            // VM:111-119  (lambda_m*Tfp_prev + T*dt*phi) / (lambda_m + dt*phi)
+            const double Tc = s_Tc[t], phi = s_phi[t];
+            const double num = P.lm[i] * f.Tf_partial[tile0 * N + it] + (Tc * P.dt) * phi;
+            const double den = P.lm[i] + P.dt * phi;
+            const double v = num / den;
+            f.Tf_partial[tile0 * N + it] = v;  // TVP:466 + copy TVP:469
+            s_tfp[it] = v;
+        }
+        if (ph_stress) {
+            const double xi = s_xi[t];
+            s_tg[it] = taylor3(xi, P.lg[i]);
+            s_tk[it] = taylor3(xi, P.lk[i]);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 1c: Tf, strains, Prony increment coefficients ---------------------------
+    for (int it = tid; it < n_pairs; it += VTHREADS) {
+        const int t = it / N, i = it - t * N;
+        const long node = tile0 + t;
+        double tf;
+        if (ph_tf) {
+            // VM:122-125  inner(m, Tf_partial), left-to-right
+            tf = P.m[0] * s_tfp[t * N];
+            for (int j = 1; j < N; ++j) tf = tf + P.m[j] * s_tfp[t * N + j];
+            if (i == 0) f.Tf[node] = tf;  // TVP:480 + copy TVP:481
+        } else {
+            tf = s_tf[t];
+        }
+        if constexpr (TENSOR) {
+            // VM:128-133; Tf_cur == Tf_prev bitwise after TVP:481, so the structural term is 0 (or NaN)
+            const double eth = P.alpha_s * s_dT[t] + P.d_alpha * (tf - tf);
+            const double tot_d = -1.0 * eth;   // VM:137
+            const double tot_o = -1.0 * 0.0;
+            double tr = tot_d;
+#pragma unroll
+            for (int a = 1; a < D; ++a) tr = tr + tot_d;
+            const double dev_d = tot_d - P.inv_d * tr;  // VM:144
+            const double dev_o = tot_o;
+            if (ph_strain && i == 0) {
+#pragma unroll
+                for (int c = 0; c < DD; ++c) {
+                    const bool diag = (c % (D + 1)) == 0;
+                    if (f.thermal_strain) f.thermal_strain[node * DD + c] = diag ? eth : 0.0;  // TVP:492
+                    if (f.total_strain) f.total_strain[node * DD + c] = diag ? tot_d : tot_o;  // TVP:504
+                    if (f.deviatoric_strain) f.deviatoric_strain[node * DD + c] = diag ? dev_d : dev_o;  // TVP:516
+                }
+            }
+            if (ph_stress) {
+                const double xi = s_xi[t];
+                const double one_g = 1.0 - s_tg[it], one_k = 1.0 - s_tk[it];
+                // VM:176-182   2.0*g_n*dev/xi*lambda_g_n*(1.0 - taylor)
+                s_dsd[it] = ((P.g2[i] * dev_d) / xi) * P.lg[i] * one_g;
+                s_dso[it] = ((P.g2[i] * dev_o) / xi) * P.lg[i] * one_g;
+                // VM:185-191   k_n*(tr*I)/xi*lambda_k_n*(1.0 - taylor)
+                s_dkd[it] = ((P.k[i] * tr) / xi) * P.lk[i] * one_k;
+            }
+        }
+    }
+    if constexpr (TENSOR) {
+        if (!ph_stress) return;
+        if (use_bulk) sgptx::mbar_wait(bar, 0);
+        __syncthreads();
+
+        // ---- stage 2: (node, component) pairs sweep the N terms in shared memory -------
+        const int n_items = nn * DD;
+        for (int it = tid; it < n_items; it += VTHREADS) {
+            const int t = it / DD, c = it - t * DD;
+            const bool diag = (c % (D + 1)) == 0;
+            double acc = 0.0;
+            for (int n = 0; n < N; ++n) {
+                const int e = (t * N + n) * DD + c;
+                const int q = t * N + n;
+                const double st = buf_s[e] * s_tg[q];    // VM:194-200
+                const double sg = buf_k[e] * s_tk[q];    // VM:203-209
+                buf_s[e] = st;                           // TVP:552 + copy TVP:559
+                buf_k[e] = sg;                           // TVP:571 + copy TVP:578
+                const double ds = diag ? s_dsd[q] : s_dso[q];
+                const double dk = diag ? s_dkd[q] : 0.0;
+                const double sp = ds + st;               // VM:212-215
+                const double kp = dk + sg;               // VM:218-221
+                const double pn = sp + kp;               // VM:224-228
+                acc = (n == 0) ? pn : acc + pn;
+                if (f.ds_partial) f.ds_partial[gbase + e] = ds;          // TVP:549
+                if (f.dsigma_partial) f.dsigma_partial[gbase + e] = dk;  // TVP:568
+                if (f.s_partial) f.s_partial[gbase + e] = sp;            // TVP:555 (+561)
+                if (f.sigma_partial) f.sigma_partial[gbase + e] = kp;    // TVP:574 (+582)
+            }
+            f.sigma[tile0 * DD + it] = acc;  // TVP:591
+        }
+
+        // ---- stage 3: write the updated history tiles back --------------------------------
+        if (use_bulk) {
+            sgptx::fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                sgptx::bulk_s2g(f.s_tilde + gbase, buf_s, tile_bytes);
+                sgptx::bulk_s2g(f.sigma_tilde + gbase, buf_k, tile_bytes);
+                sgptx::bulk_commit();
+                sgptx::bulk_wait_read0();
+            }
+        } else {
+            __syncthreads();
+            for (int e = tid; e < tile_elems; e += VTHREADS) {
+                f.s_tilde[gbase + e] = buf_s[e];
+                f.sigma_tilde[gbase + e] = buf_k[e];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+struct sg_visco_plan {
+    sg_ctx *ctx;
+    sg_visco_params p;
+    VKParams k;
+};
+
+namespace {
+
+template <int D, bool SCALAR, bool TENSOR>
+int launch_visco_d(const sg_visco_plan *plan, int64_t n, const sg_visco_fields &f, const VGather &G,
+                   uint32_t phases, cudaStream_t st) {
+    const size_t smem = visco_smem_bytes(plan->k.N, D * D, TENSOR);
+    auto kern = visco_kernel<D, SCALAR, TENSOR>;
+    SG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (n + VTILE - 1) / VTILE;
+    SG_REQUIRE(grid < (int64_t)2147483647, "sg_visco_update: too many nodes for one launch");
+    int bulk_ok = 0;
+    if (TENSOR) {
+        bulk_ok = ((reinterpret_cast<uintptr_t>(f.s_tilde) | reinterpret_cast<uintptr_t>(f.sigma_tilde)) % 16 == 0) &&
+                  ((VTILE * plan->k.N * D * D) % 2 == 0);
+    }
+    kern<<<(unsigned)grid, VTHREADS, smem, st>>>(plan->k, f, G, (long)n, phases, bulk_ok);
+    SG_CHECK_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+template <bool SCALAR, bool TENSOR>
+int launch_visco(const sg_visco_plan *plan, int64_t n, const sg_visco_fields &f, const VGather &G,
+                 uint32_t phases, cudaStream_t st) {
+    if (n == 0) return SG_OK;
+    switch (plan->p.dim) {
+        case 1: return launch_visco_d<1, SCALAR, TENSOR>(plan, n, f, G, phases, st);
+        case 2: return launch_visco_d<2, SCALAR, TENSOR>(plan, n, f, G, phases, st);
+        case 3: return launch_visco_d<3, SCALAR, TENSOR>(plan, n, f, G, phases, st);
+    }
+    sg_set_error("sg_visco: dim must be 1, 2 or 3 (got %d)", plan->p.dim);
+    return SG_E_INVALID;
+}
+
+int check_fields(const sg_visco_fields *f, uint32_t phases, bool scalar, bool tensor, int64_t n) {
+    SG_REQUIRE(f != nullptr, "sg_visco: fields is NULL");
+    SG_REQUIRE(n >= 0, "sg_visco: negative node count");
+    SG_REQUIRE((phases & ~SG_PHASE_ALL) == 0 && phases != 0, "sg_visco: bad phase mask 0x%x", phases);
+    SG_REQUIRE(f->T_cur && f->T_prev, "sg_visco: T_cur/T_prev are required");
+    SG_REQUIRE(f->Tf, "sg_visco: Tf is required");
+    if (scalar) {
+        SG_REQUIRE(f->phi && f->xi && f->Tf_partial, "sg_visco: phi, xi and Tf_partial are required");
+    }
+    if (tensor && (phases & SG_PHASE_STRESS)) {
+        SG_REQUIRE(f->s_tilde && f->sigma_tilde && f->sigma, "sg_visco: s_tilde, sigma_tilde, sigma are required");
+    }
+    if (tensor && !scalar) SG_REQUIRE(f->xi, "sg_visco: xi is required by the tensor phase");
+    return SG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sg_visco_plan_create(sg_ctx *ctx, const sg_visco_params *p, sg_visco_plan **out) {
+    SG_REQUIRE(ctx && p && out, "sg_visco_plan_create: NULL argument");
+    SG_REQUIRE(p->dim >= 1 && p->dim <= 3, "sg_visco_plan_create: dim must be 1..3 (got %d)", p->dim);
+    SG_REQUIRE(p->n_terms >= 1 && p->n_terms <= SG_MAX_TERMS, "sg_visco_plan_create: n_terms must be 1..%d (got %d)",
+               SG_MAX_TERMS, p->n_terms);
+    sg_visco_plan *pl = new sg_visco_plan();
+    pl->ctx = ctx;
+    pl->p = *p;
+    VKParams &k = pl->k;
+    memset(&k, 0, sizeof(k));
+    k.N = p->n_terms;
+    k.c_HRg = p->H / p->Rg;
+    k.inv_Tb = 1.0 / p->Tb;
+    k.dt = p->dt;
+    k.half_dt = p->dt / 2;
+    k.inv_d = 1.0 / (double)p->dim;
+    k.alpha_s = p->alpha_solid;
+    k.d_alpha = p->alpha_liquid - p->alpha_solid;
+    for (int i = 0; i < p->n_terms; ++i) {
+        k.m[i] = p->m[i];
+        k.lm[i] = p->lambda_m[i];
+        k.g2[i] = 2.0 * p->g[i];
+        k.lg[i] = p->lambda_g[i];
+        k.k[i] = p->k[i];
+        k.lk[i] = p->lambda_k[i];
+    }
+    *out = pl;
+    return SG_OK;
+}
+
+int sg_visco_plan_destroy(sg_visco_plan *plan) {
+    delete plan;
+    return SG_OK;
+}
+
+int sg_visco_update(sg_visco_plan *plan, int64_t n_nodes, const sg_visco_fields *f, uint32_t phases, void *stream) {
+    SG_REQUIRE(plan, "sg_visco_update: plan is NULL");
+    int rc = check_fields(f, phases, true, true, n_nodes);
+    if (rc) return rc;
+    VGather G{0, nullptr, nullptr, nullptr};
+    return launch_visco<true, true>(plan, n_nodes, *f, G, phases, (cudaStream_t)stream);
+}
+
+int sg_visco_update_scalar(sg_visco_plan *plan, int64_t n, const sg_visco_fields *f, uint32_t phases, void *stream) {
+    SG_REQUIRE(plan, "sg_visco_update_scalar: plan is NULL");
+    int rc = check_fields(f, phases, true, false, n);
+    if (rc) return rc;
+    VGather G{0, nullptr, nullptr, nullptr};
+    return launch_visco<true, false>(plan, n, *f, G, phases, (cudaStream_t)stream);
+}
+
+int sg_visco_update_tensor(sg_visco_plan *plan, int64_t n, const sg_visco_fields *f, const sg_visco_gather *g,
+                           uint32_t phases, void *stream) {
+    SG_REQUIRE(plan, "sg_visco_update_tensor: plan is NULL");
+    SG_REQUIRE(g && g->dofs && g->local_point && g->weights && g->n_ld > 0, "sg_visco_update_tensor: bad gather map");
+    int rc = check_fields(f, phases, false, true, n);
+    if (rc) return rc;
+    VGather G{g->n_ld, g->dofs, g->local_point, g->weights};
+    return launch_visco<false, true>(plan, n, *f, G, phases, (cudaStream_t)stream);
+}
+
+int64_t sg_visco_bytes_per_node(const sg_visco_params *p, const sg_visco_fields *f, uint32_t phases) {
+    if (!p || !f) return -1;
+    const int64_t N = p->n_terms, dd = (int64_t)p->dim * p->dim;
+    int64_t w = 2;  // read T_cur, T_prev
+    if (phases & SG_PHASE_TF) w += 2 * N + 1;                    // Tf_partial r+w, Tf w
+    if (phases & (SG_PHASE_TF | SG_PHASE_SHIFT)) w += 1;          // phi
+    if (phases & SG_PHASE_SHIFT) w += 1 + (f->T_next ? 1 : 0) + (f->phi_next ? 1 : 0);
+    if (phases & SG_PHASE_STRAIN)
+        w += dd * ((f->thermal_strain ? 1 : 0) + (f->total_strain ? 1 : 0) + (f->deviatoric_strain ? 1 : 0));
+    if (phases & SG_PHASE_STRESS)
+        w += 4 * N * dd + dd +
+             N * dd * ((f->ds_partial ? 1 : 0) + (f->dsigma_partial ? 1 : 0) + (f->s_partial ? 1 : 0) +
+                       (f->sigma_partial ? 1 : 0));
+    return 8 * w;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+/*
+ * surroglas_b200.h — C ABI of the B200-native SurroGlas per-timestep hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces a call the reference
+ * (pzimbrod/fem-glass-tempering) makes into dolfinx/PETSc; the reference site is
+ * cited on each declaration as  TVP = ThermoViscoProblem.py, VM =
+ * ViscoelasticModel.py, TM = ThermalModel.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (SG_E_*); the message is
+ *     available from sg_last_error() (thread-local).  Nothing throws across the ABI.
+ *   - every data pointer is a DEVICE pointer owned by the caller (PyTorch); the
+ *     library never frees caller memory.  float64 everywhere, int32 indices.
+ *   - arrays use the dolfinx blocked layout array[node*bs + comp] (TVP:82-101).
+ *   - `stream` is a cudaStream_t passed as void*; all compute calls are asynchronous
+ *     on it unless stated otherwise.
+ *   - plans/operators are opaque handles created/destroyed by paired calls; the
+ *     library keeps no global mutable state.
+ */
+#ifndef SURROGLAS_B200_H
+#define SURROGLAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_MAX_TERMS 16
+
+enum {
+    SG_OK = 0,
+    SG_E_INVALID = -1,   /* bad argument */
+    SG_E_CUDA = -2,      /* CUDA runtime error */
+    SG_E_NOCONV = -3,    /* solver did not converge (TVP:390 assert(converged)) */
+    SG_E_NCCL = -4,
+    SG_E_UNSUPPORTED = -5
+};
+
+int sg_version(void);
+const char *sg_last_error(void);
+
+/* ------------------------------------------------------------------ context */
+typedef struct sg_ctx sg_ctx;
+
+/* One context per process/GPU (the reference is one MPI rank per process,
+ * TVP:27-28 MPI.COMM_WORLD).  nccl_unique_id: 128-byte ncclUniqueId obtained from
+ * sg_nccl_unique_id() on rank 0 and broadcast by the host (torch.distributed), or
+ * NULL when nranks == 1. */
+int sg_nccl_unique_id(void *out128);
+int sg_ctx_create(int device, int rank, int nranks, const void *nccl_unique_id, sg_ctx **out);
+int sg_ctx_destroy(sg_ctx *ctx);
+int sg_ctx_sm_count(const sg_ctx *ctx);
+
+/* ------------------------------------------------- (A) viscoelastic update */
+
+/* VM:9-84: Prony tableaux and material constants; dt from VM:88. */
+typedef struct {
+    int32_t dim;      /* VM:17 */
+    int32_t n_terms;  /* VM:16 tableau_size (<= SG_MAX_TERMS) */
+    double H, Rg, Tb; /* VM:75-79 */
+    double alpha_solid, alpha_liquid; /* VM:81-83 */
+    double dt;
+    double m[SG_MAX_TERMS], lambda_m[SG_MAX_TERMS];   /* VM:19-34 */
+    double g[SG_MAX_TERMS], lambda_g[SG_MAX_TERMS];   /* VM:35-50 */
+    double k[SG_MAX_TERMS], lambda_k[SG_MAX_TERMS];   /* VM:51-68 */
+} sg_visco_params;
+
+/* Phases = the four reference methods; a phase only controls which outputs are
+ * WRITTEN, every input it needs is recomputed from T_cur/T_prev/Tf. */
+enum {
+    SG_PHASE_TF = 1,      /* TVP:393-407  _solve_Tf            */
+    SG_PHASE_STRAIN = 2,  /* TVP:409-423  _solve_strains       */
+    SG_PHASE_SHIFT = 4,   /* TVP:426-435  _solve_shifted_time  */
+    SG_PHASE_STRESS = 8,  /* TVP:438-452  _solve_stress        */
+    SG_PHASE_ALL = 15
+};
+
+/* The dolfinx Functions of TVP:106-173 the chain reads/writes.  Pointers in the
+ * "optional" block may be NULL: the quantity is then kept in registers/shared
+ * memory and never written to HBM. */
+typedef struct {
+    /* T space (bs 1 unless noted) */
+    const double *T_cur;    /* functions_current["T"]  */
+    const double *T_prev;   /* functions_previous["T"] */
+    double *Tf_partial;     /* bs N; in/out: previous on entry, current on exit (TVP:466-470) */
+    double *Tf;             /* functions_current["Tf"] == functions_previous["Tf"] (TVP:480-482) */
+    double *phi;            /* functions["phi"] */
+    double *xi;             /* functions["xi"]  */
+    /* sigma space */
+    double *s_tilde;        /* bs N*d*d; in/out (TVP:552,559) */
+    double *sigma_tilde;    /* bs N*d*d; in/out (TVP:571,578) */
+    double *sigma;          /* bs d*d;   functions_next["sigma"] (TVP:591) */
+    /* optional, full-materialisation mode */
+    double *T_next, *phi_next;                                   /* TVP:524,533 */
+    double *thermal_strain, *total_strain, *deviatoric_strain;   /* bs d*d; TVP:492,504,516 */
+    double *ds_partial, *dsigma_partial;                         /* bs N*d*d; TVP:549,568 */
+    double *s_partial, *sigma_partial;                           /* bs N*d*d; TVP:555,574 */
+} sg_visco_fields;
+
+/* Cross-space evaluation (fe_config["T"] != fe_config["sigma"], e.g. main.py:24-27
+ * DG1 -> CG1): value of a T-space function at sigma node s is
+ *   sum_j weights[local_point[s]*n_ld + j] * array[dofs[s*n_ld + j]]
+ * where (cell, local_point) is the LAST cell that dolfinx's interpolation visits
+ * for that node (last writer wins), and zero weights are skipped like FFCx's
+ * table compression does. */
+typedef struct {
+    int32_t n_ld;                /* dofs per cell of the T element */
+    int32_t n_points;            /* interpolation points per cell of the sigma element */
+    const int32_t *dofs;         /* [n_sigma_nodes * n_ld] T-space dof indices of the winner cell */
+    const uint8_t *local_point;  /* [n_sigma_nodes] */
+    const double *weights;       /* [n_points * n_ld] T basis at the sigma points */
+} sg_visco_gather;
+
+typedef struct sg_visco_plan sg_visco_plan;
+int sg_visco_plan_create(sg_ctx *ctx, const sg_visco_params *params, sg_visco_plan **out);
+int sg_visco_plan_destroy(sg_visco_plan *plan);
+
+/* Replaces the 17 Function.interpolate(Expression) calls + 7 copies of
+ * TVP:370-373 (definitions VM:111-228) when the T and sigma spaces share their
+ * node set: one fused pass over n_nodes. */
+int sg_visco_update(sg_visco_plan *plan, int64_t n_nodes, const sg_visco_fields *f,
+                    uint32_t phases, void *stream);
+
+/* Cross-space variants: T-space quantities (phi, Tf_partial, Tf, T_next,
+ * phi_next, xi) over the T nodes ... */
+int sg_visco_update_scalar(sg_visco_plan *plan, int64_t n_T_nodes, const sg_visco_fields *f,
+                           uint32_t phases, void *stream);
+/* ... and sigma-space quantities over the sigma nodes, reading T_cur, T_prev, Tf
+ * and xi through `gather`. */
+int sg_visco_update_tensor(sg_visco_plan *plan, int64_t n_sigma_nodes, const sg_visco_fields *f,
+                           const sg_visco_gather *gather, uint32_t phases, void *stream);
+
+/* Algorithmic HBM bytes per node of sg_visco_update for the given materialisation
+ * (used by bench.py for the roofline). */
+int64_t sg_visco_bytes_per_node(const sg_visco_params *params, const sg_visco_fields *f, uint32_t phases);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURROGLAS_B200_H */

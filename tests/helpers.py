@@ -1,0 +1,60 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def unhex(v):
+    if isinstance(v, list):
+        return [unhex(x) for x in v]
+    return float.fromhex(v)
+
+
+def load_visco_kat():
+    with open(os.path.join(GOLDEN, "visco_kat.json")) as fh:
+        data = json.load(fh)
+    cases = []
+    for c in data["cases"]:
+        cases.append(dict(name=c["name"], d=c["d"], inputs={k: unhex(v) for k, v in c["inputs"].items()},
+                          expected={k: unhex(v) for k, v in c["expected"].items()}))
+    return cases
+
+
+def assert_same(a, b, what=""):
+    """Exact float64 equality (0.0 == -0.0), NaNs must sit at the same positions."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), f"{what}: NaN positions differ"
+    ok = (a == b) | nan_a
+    if not ok.all():
+        i = int(np.argmin(ok.ravel()))
+        raise AssertionError(f"{what}: {int((~ok).sum())} of {a.size} values differ; first at flat index {i}: "
+                             f"{a.ravel()[i]!r} vs {b.ravel()[i]!r}")
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| over finite entries (NaN positions must match)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN positions differ"
+    m = ~np.isnan(b)
+    if not m.any():
+        return 0.0
+    scale = np.max(np.abs(b[m]))
+    return float(np.max(np.abs(a[m] - b[m])) / (scale if scale > 0 else 1.0))
+
+
+def random_visco_state(n, d, N=6, seed=1234):
+    """SURVEY §8(d) micro-benchmark state."""
+    rng = np.random.default_rng(seed)
+    T_cur = rng.uniform(650.0, 850.0, n)
+    T_prev = T_cur + rng.uniform(0.05, 1.0, n)
+    Tfp = np.repeat(T_prev, N) + rng.uniform(0.0, 5.0, n * N)
+    s = rng.normal(0.0, 1e-3, n * N * d * d)
+    k = rng.normal(0.0, 1e-3, n * N * d * d)
+    return T_cur, T_prev, Tfp, s, k
