@@ -285,12 +285,169 @@ visco_kernel(const VKParams P, const sg_visco_fields f, const VGather G, const l
     }
 }
 
+
+// =====================================================================================
+// Fast path: persistent, barrier-free kernel for the steady-state call
+// (phases == ALL, no optional outputs, same-space, N known at compile time).
+//
+// One WARP owns a tile of 32 nodes; lane == node.  The warp's s_tilde / sigma_tilde /
+// Tf_partial rows are contiguous in HBM, so lane 0 fetches them with three 1-D TMA bulk
+// copies onto a warp-private mbarrier while all lanes evaluate the exp()-dependent
+// scalars.  Each lane then runs the whole chain for its node out of registers, sweeping
+// its own row in shared memory with 128-bit accesses (row stride N*d*d*8 B is
+// bank-conflict-free for LDS.128), and the warp writes the four result tiles back with
+// bulk stores.  No __syncthreads, no cross-lane traffic, CTAs of a single warp so the
+// scheduler packs as many tiles per SM as shared memory allows.
+// Arithmetic (order of every operation) is identical to visco_kernel above.
+// =====================================================================================
+constexpr int WT = 32;  // nodes per warp tile
+
+template <int D, int N>
+struct FastCfg {
+    static constexpr int DD = D * D;
+    static constexpr int ROW = N * DD;             // doubles per node in a history tensor
+    static constexpr bool VEC = (ROW % 2) == 0;    // rows 16-B aligned -> LDS.128 / STS.128
+    static constexpr int G = VEC ? ((DD % 2) == 0 ? 1 : 2) : 1;  // terms per register group
+    static constexpr uint32_t S_BYTES = WT * ROW * 8;
+    static constexpr uint32_t TFP_BYTES = WT * N * 8;
+    static constexpr uint32_t SIG_BYTES = WT * DD * 8;
+    static constexpr uint32_t SMEM = 2 * S_BYTES + TFP_BYTES + SIG_BYTES + 16;
+};
+
+template <int D, int N>
+__global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const sg_visco_fields f, const long n_tiles) {
+    using C = FastCfg<D, N>;
+    constexpr int DD = C::DD, ROW = C::ROW, G = C::G;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *buf_s = reinterpret_cast<double *>(smem_raw);
+    double *buf_k = buf_s + WT * ROW;
+    double *buf_t = buf_k + WT * ROW;
+    double *buf_o = buf_t + WT * N;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(buf_o + WT * DD);
+    const int lane = threadIdx.x;
+
+    if (lane == 0) {
+        sgptx::mbar_init(bar, 1);
+        sgptx::fence_mbar_init();
+    }
+    __syncwarp();
+    uint32_t parity = 0;
+
+    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long node0 = tile * WT;
+        if (lane == 0) {
+            sgptx::mbar_expect_tx(bar, 2u * C::S_BYTES + C::TFP_BYTES);
+            sgptx::bulk_g2s(buf_s, f.s_tilde + node0 * ROW, C::S_BYTES, bar);
+            sgptx::bulk_g2s(buf_k, f.sigma_tilde + node0 * ROW, C::S_BYTES, bar);
+            sgptx::bulk_g2s(buf_t, f.Tf_partial + node0 * N, C::TFP_BYTES, bar);
+        }
+        const long node = node0 + lane;
+        const double Tc = f.T_cur[node], Tp = f.T_prev[node];
+        const double phi = shift_phi(P, Tc);               // VM:156
+        const double Tn = Tc + (Tc - Tp);                  // VM:151
+        const double phin = shift_phi(P, Tn);              // VM:162
+        const double xi = P.half_dt * (phin - phi);        // VM:171
+        f.phi[node] = phi;
+        f.xi[node] = xi;
+        const double Tdt_phi = (Tc * P.dt) * phi, dt_phi = P.dt * phi;
+
+        sgptx::mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        // ---- fictive temperatures (VM:111-125) ----
+        double tf = 0.0;
+        {
+            double *row = buf_t + lane * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double v = (P.lm[i] * row[i] + Tdt_phi) / (P.lm[i] + dt_phi);
+                row[i] = v;
+                tf = (i == 0) ? P.m[0] * v : tf + P.m[i] * v;
+            }
+        }
+        f.Tf[node] = tf;
+        // ---- strains (VM:128-146) ----
+        const double eth = P.alpha_s * (Tc - Tp) + P.d_alpha * (tf - tf);
+        const double tot_d = -1.0 * eth, tot_o = -1.0 * 0.0;
+        double tr = tot_d;
+#pragma unroll
+        for (int a = 1; a < D; ++a) tr = tr + tot_d;
+        const double dev_d = tot_d - P.inv_d * tr, dev_o = tot_o;
+
+        // ---- Prony recursions (VM:176-228), G terms at a time out of registers ----
+        double acc[DD];
+        double *rs = buf_s + lane * ROW, *rk = buf_k + lane * ROW;
+#pragma unroll
+        for (int n0 = 0; n0 < N; n0 += G) {
+            double tg[G], tk[G], dsd[G], dso[G], dkd[G];
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                const int n = n0 + u;
+                tg[u] = taylor3(xi, P.lg[n]);
+                tk[u] = taylor3(xi, P.lk[n]);
+                const double one_g = 1.0 - tg[u], one_k = 1.0 - tk[u];
+                dsd[u] = ((P.g2[n] * dev_d) / xi) * P.lg[n] * one_g;
+                dso[u] = ((P.g2[n] * dev_o) / xi) * P.lg[n] * one_g;
+                dkd[u] = ((P.k[n] * tr) / xi) * P.lk[n] * one_k;
+            }
+            auto item = [&](double &s, double &k, const int e) {  // e: element within the group
+                const int u = e / DD, c = e % DD;
+                const bool diag = (c % (D + 1)) == 0;
+                s = s * tg[u];
+                k = k * tk[u];
+                const double pn = ((diag ? dsd[u] : dso[u]) + s) + ((diag ? dkd[u] : 0.0) + k);
+                acc[c] = (n0 + u == 0) ? pn : acc[c] + pn;
+            };
+            if constexpr (C::VEC) {
+                double2 *vs = reinterpret_cast<double2 *>(rs + n0 * DD);
+                double2 *vk = reinterpret_cast<double2 *>(rk + n0 * DD);
+#pragma unroll
+                for (int j = 0; j < G * DD / 2; ++j) {
+                    double2 s = vs[j], k = vk[j];
+                    item(s.x, k.x, 2 * j);
+                    item(s.y, k.y, 2 * j + 1);
+                    vs[j] = s;
+                    vk[j] = k;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < G * DD; ++e) {
+                    double s = rs[n0 * DD + e], k = rk[n0 * DD + e];
+                    item(s, k, e);
+                    rs[n0 * DD + e] = s;
+                    rk[n0 * DD + e] = k;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < DD; ++c) buf_o[lane * DD + c] = acc[c];
+
+        // ---- write the four tiles back ----
+        sgptx::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            sgptx::bulk_s2g(f.s_tilde + node0 * ROW, buf_s, C::S_BYTES);
+            sgptx::bulk_s2g(f.sigma_tilde + node0 * ROW, buf_k, C::S_BYTES);
+            sgptx::bulk_s2g(f.Tf_partial + node0 * N, buf_t, C::TFP_BYTES);
+            sgptx::bulk_s2g(f.sigma + node0 * DD, buf_o, C::SIG_BYTES);
+            sgptx::bulk_commit();
+            sgptx::bulk_wait_read0();
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
+
+typedef void (*visco_fast_fn)(const VKParams, const sg_visco_fields, const long);
 
 struct sg_visco_plan {
     sg_ctx *ctx;
     sg_visco_params p;
     VKParams k;
+    visco_fast_fn fast;   // nullptr when (dim, n_terms) has no compiled fast path
+    uint32_t fast_smem;
+    int fast_grid;        // resident one-warp CTAs on the whole GPU
 };
 
 namespace {
@@ -324,6 +481,35 @@ int launch_visco(const sg_visco_plan *plan, int64_t n, const sg_visco_fields &f,
     }
     sg_set_error("sg_visco: dim must be 1, 2 or 3 (got %d)", plan->p.dim);
     return SG_E_INVALID;
+}
+
+template <int D, int N>
+int setup_fast(sg_visco_plan *pl) {
+    auto kern = visco_fast_kernel<D, N>;
+    const uint32_t smem = FastCfg<D, N>::SMEM;
+    if (smem > 227u * 1024u) return SG_OK;
+    SG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 0;
+    SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) return SG_OK;
+    pl->fast = kern;
+    pl->fast_smem = smem;
+    pl->fast_grid = per_sm * pl->ctx->sm_count;
+    return SG_OK;
+}
+
+template <int D>
+int setup_fast_d(sg_visco_plan *pl) {
+    switch (pl->p.n_terms) {
+        case 3: return setup_fast<D, 3>(pl);
+        case 4: return setup_fast<D, 4>(pl);
+        case 6: return setup_fast<D, 6>(pl);
+        case 8: return setup_fast<D, 8>(pl);
+        case 10: return setup_fast<D, 10>(pl);
+        case 12: return setup_fast<D, 12>(pl);
+    }
+    return SG_OK;
 }
 
 int check_fields(const sg_visco_fields *f, uint32_t phases, bool scalar, bool tensor, int64_t n) {
@@ -372,6 +558,17 @@ int sg_visco_plan_create(sg_ctx *ctx, const sg_visco_params *p, sg_visco_plan **
         k.k[i] = p->k[i];
         k.lk[i] = p->lambda_k[i];
     }
+    pl->fast = nullptr;
+    pl->fast_smem = 0;
+    pl->fast_grid = 0;
+    int rc = SG_OK;
+    if (p->dim == 1) rc = setup_fast_d<1>(pl);
+    if (p->dim == 2) rc = setup_fast_d<2>(pl);
+    if (p->dim == 3) rc = setup_fast_d<3>(pl);
+    if (rc != SG_OK) {
+        delete pl;
+        return rc;
+    }
     *out = pl;
     return SG_OK;
 }
@@ -386,7 +583,36 @@ int sg_visco_update(sg_visco_plan *plan, int64_t n_nodes, const sg_visco_fields 
     int rc = check_fields(f, phases, true, true, n_nodes);
     if (rc) return rc;
     VGather G{0, nullptr, nullptr, nullptr};
-    return launch_visco<true, true>(plan, n_nodes, *f, G, phases, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    // Steady-state call: everything but the tail (< 32 nodes) goes through the persistent fast path.
+    const bool no_optional = !f->T_next && !f->phi_next && !f->thermal_strain && !f->total_strain &&
+                             !f->deviatoric_strain && !f->ds_partial && !f->dsigma_partial && !f->s_partial &&
+                             !f->sigma_partial;
+    const uintptr_t align_or = reinterpret_cast<uintptr_t>(f->s_tilde) | reinterpret_cast<uintptr_t>(f->sigma_tilde) |
+                               reinterpret_cast<uintptr_t>(f->Tf_partial) | reinterpret_cast<uintptr_t>(f->sigma);
+    int64_t done = 0;
+    if (plan->fast && phases == SG_PHASE_ALL && no_optional && (align_or % 16) == 0 && n_nodes >= WT) {
+        const int64_t n_tiles = n_nodes / WT;
+        const int grid = (int)(n_tiles < plan->fast_grid ? n_tiles : plan->fast_grid);
+        plan->fast<<<grid, 32, plan->fast_smem, st>>>(plan->k, *f, (long)n_tiles);
+        SG_CHECK_CUDA(cudaGetLastError());
+        done = n_tiles * WT;
+        if (done == n_nodes) return SG_OK;
+    }
+    sg_visco_fields t = *f;
+    if (done) {
+        const int64_t N = plan->k.N, dd = (int64_t)plan->p.dim * plan->p.dim;
+        t.T_cur += done;
+        t.T_prev += done;
+        t.Tf_partial += done * N;
+        t.Tf += done;
+        t.phi += done;
+        t.xi += done;
+        t.s_tilde += done * N * dd;
+        t.sigma_tilde += done * N * dd;
+        t.sigma += done * dd;
+    }
+    return launch_visco<true, true>(plan, n_nodes - done, t, G, phases, st);
 }
 
 int sg_visco_update_scalar(sg_visco_plan *plan, int64_t n, const sg_visco_fields *f, uint32_t phases, void *stream) {

@@ -1,0 +1,430 @@
+"""Lagrange P1/P2 finite-element tables on simplices, quadrature, dof maps and mesh topology.
+
+Host-side (numpy) counterpart of what the reference gets from basix/FFCx/dolfinx
+(ThermoViscoProblem.py:61-103: FiniteElement/VectorElement/TensorElement on CG or DG).
+Everything here is set-up: the arrays are built once, uploaded, and consumed by the CUDA
+operator (csrc/thermal.cu).
+
+Conventions (internal, documented in DESIGN.md):
+  * reference simplex: v0 = 0, v_i = e_i; barycentric l_0 = 1 - sum(x), l_i = x_i
+  * local facet f is the facet OPPOSITE local vertex f (its outward normal is -grad l_f/|grad l_f|)
+  * P2 local dof order: vertices, then edges in the order of `ref_edges(dim)`
+  * '+' side of an interior facet = the cell with the lower index
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from .mesh import Mesh
+
+# --------------------------------------------------------------------------- reference topology
+
+
+def ref_edges(dim: int):
+    return {1: [(0, 1)], 2: [(1, 2), (0, 2), (0, 1)],
+            3: [(2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1)]}[dim]
+
+
+def ref_facets(dim: int):
+    """facet f = all local vertices except f, ascending."""
+    return [tuple(v for v in range(dim + 1) if v != f) for f in range(dim + 1)]
+
+
+def ref_vertices(dim: int) -> np.ndarray:
+    v = np.zeros((dim + 1, dim))
+    for i in range(dim):
+        v[i + 1, i] = 1.0
+    return v
+
+
+# --------------------------------------------------------------------------- quadrature
+
+
+def gauss_legendre_01(n: int):
+    x, w = np.polynomial.legendre.leggauss(n)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def simplex_quadrature(dim: int, degree: int):
+    """Collapsed Gauss-Jacobi rule exact for polynomials of total degree <= `degree` on the reference
+    simplex.  Returns (points [nq, dim], weights [nq]) with sum(weights) = 1/dim!."""
+    from scipy.special import roots_jacobi
+    n = degree // 2 + 1
+    if dim == 0:
+        return np.zeros((1, 0)), np.ones(1)
+    if dim == 1:
+        x, w = gauss_legendre_01(n)
+        return x[:, None], w
+    x0, w0 = gauss_legendre_01(n)
+    x1, w1 = roots_jacobi(n, 1, 0)
+    x1, w1 = 0.5 * (x1 + 1.0), w1 / 4.0
+    if dim == 2:
+        pts = [(a1, a0 * (1.0 - a1)) for a1 in x1 for a0 in x0]
+        wts = [b1 * b0 for b1 in w1 for b0 in w0]
+        pts, wts = np.array(pts), np.array(wts)
+        return pts[:, ::-1].copy(), wts
+    x2, w2 = roots_jacobi(n, 2, 0)
+    x2, w2 = 0.5 * (x2 + 1.0), w2 / 8.0
+    pts, wts = [], []
+    for a2, b2 in zip(x2, w2):
+        for a1, b1 in zip(x1, w1):
+            for a0, b0 in zip(x0, w0):
+                pts.append((a0 * (1 - a1) * (1 - a2), a1 * (1 - a2), a2))
+                wts.append(b0 * b1 * b2)
+    return np.array(pts), np.array(wts)
+
+
+def symmetric_facet_rule(fdim: int, degree: int):
+    """Rule on the reference facet simplex that is invariant under vertex permutations, in facet
+    BARYCENTRIC coordinates [nq, fdim+1]; weights sum to 1.  Needed on interior facets, where the two
+    cells see the facet through different vertex orders (FFCx's `quadrature_permutation`)."""
+    if fdim == 0:
+        return np.ones((1, 1)), np.ones(1)
+    if fdim == 1:
+        x, w = gauss_legendre_01(degree // 2 + 1)
+        return np.stack([1.0 - x, x], axis=1), w / w.sum()
+    if fdim == 2:
+        if degree <= 2:
+            a = 1.0 / 6.0
+            orbits = [(a, 1.0 / 3.0)]
+        elif degree <= 4:  # Dunavant 6-point rule
+            orbits = [(0.44594849091596488631832925388305199, 0.22338158967801146569500700843312280),
+                      (0.09157621350977074345957146340220151, 0.10995174365532186763832632490021053)]
+        else:
+            raise NotImplementedError("symmetric triangle rule of degree > 4")
+        pts, wts = [], []
+        for a, w in orbits:
+            b = 1.0 - 2.0 * a
+            pts += [(a, a, b), (a, b, a), (b, a, a)]
+            wts += [w] * 3
+        return np.array(pts), np.array(wts)
+    raise ValueError(fdim)
+
+
+def facet_permutation_table(fdim: int, bary: np.ndarray):
+    """perms: list of all vertex permutations s of the facet; table[p][q] = index q' of the rule point
+    whose barycentric coordinates are bary[q][s] (i.e. mu'_k = mu_{s(k)})."""
+    perms = list(itertools.permutations(range(fdim + 1)))
+    table = np.zeros((len(perms), bary.shape[0]), dtype=np.int32)
+    for p, s in enumerate(perms):
+        for q in range(bary.shape[0]):
+            target = bary[q][list(s)]
+            d = np.abs(bary - target).sum(axis=1)
+            j = int(np.argmin(d))
+            assert d[j] < 1e-12, "facet rule is not symmetric"
+            table[p, q] = j
+    return perms, table
+
+
+# --------------------------------------------------------------------------- the element
+
+
+class LagrangeElement:
+    """Scalar Lagrange element of degree 1 or 2 on the reference simplex."""
+
+    def __init__(self, dim: int, degree: int):
+        if degree not in (1, 2):
+            raise NotImplementedError("Lagrange degree must be 1 or 2")
+        self.dim, self.degree = dim, degree
+        self.edges = ref_edges(dim)
+        self.n_ld = dim + 1 if degree == 1 else dim + 1 + len(self.edges)
+        v = ref_vertices(dim)
+        nodes = [v[i] for i in range(dim + 1)]
+        if degree == 2:
+            nodes += [0.5 * (v[a] + v[b]) for a, b in self.edges]
+        self.nodes = np.array(nodes)  # == basix interpolation points of the element
+
+    def interpolation_points(self) -> np.ndarray:
+        return self.nodes
+
+    def tabulate(self, pts: np.ndarray):
+        """values [npts, n_ld], reference gradients [npts, dim, n_ld]."""
+        pts = np.atleast_2d(np.asarray(pts, dtype=np.float64))
+        npts, d = pts.shape[0], self.dim
+        lam = np.empty((npts, d + 1))
+        lam[:, 0] = 1.0 - pts.sum(axis=1)
+        lam[:, 1:] = pts
+        dlam = np.zeros((d + 1, d))
+        dlam[0, :] = -1.0
+        for i in range(d):
+            dlam[i + 1, i] = 1.0
+        vals = np.empty((npts, self.n_ld))
+        grads = np.empty((npts, d, self.n_ld))
+        if self.degree == 1:
+            vals[:] = lam
+            grads[:] = dlam.T[None, :, :]
+            return vals, grads
+        for i in range(d + 1):
+            vals[:, i] = lam[:, i] * (2.0 * lam[:, i] - 1.0)
+            grads[:, :, i] = (4.0 * lam[:, i] - 1.0)[:, None] * dlam[i][None, :]
+        for e, (a, b) in enumerate(self.edges):
+            j = d + 1 + e
+            vals[:, j] = 4.0 * lam[:, a] * lam[:, b]
+            grads[:, :, j] = 4.0 * (lam[:, a][:, None] * dlam[b][None, :] + lam[:, b][:, None] * dlam[a][None, :])
+        return vals, grads
+
+    def facet_points(self, f: int, bary: np.ndarray) -> np.ndarray:
+        """Reference-cell coordinates of facet-barycentric points on local facet f."""
+        fv = ref_facets(self.dim)[f]
+        v = ref_vertices(self.dim)
+        return bary @ v[list(fv)]
+
+    def facet_dofs(self, f: int):
+        """Local dofs lying on facet f (vertices of the facet, then its edges)."""
+        fv = ref_facets(self.dim)[f]
+        dofs = list(fv)
+        if self.degree == 2:
+            for e, (a, b) in enumerate(self.edges):
+                if a in fv and b in fv:
+                    dofs.append(self.dim + 1 + e)
+        return dofs
+
+
+@dataclass
+class OperatorTables:
+    """Reference tables the CUDA thermal operator needs for one (dim, degree)."""
+    n_ld: int
+    mass: np.ndarray       # [n_ld, n_ld]  int phi_i phi_j over the reference cell
+    load: np.ndarray       # [n_ld]        int phi_i
+    cq_w: np.ndarray       # [nqc]         stiffness rule weights (sum 1/d!)
+    cq_grad: np.ndarray    # [nqc, dim, n_ld]
+    # interior facets (DG): symmetric rule, weights sum to 1
+    fq_w: np.ndarray       # [nqf]
+    fq_val: np.ndarray     # [dim+1, nqf, n_ld]
+    fq_grad: np.ndarray    # [dim+1, nqf, dim, n_ld]
+    fq_perm: np.ndarray    # [n_perms, nqf] int32
+    # exterior facets (Robin + radiation): high-degree rule, weights sum to 1
+    bq_w: np.ndarray       # [nqb]
+    bq_val: np.ndarray     # [dim+1, nqb, n_ld]
+
+
+def operator_tables(dim: int, degree: int) -> OperatorTables:
+    el = LagrangeElement(dim, degree)
+    # exact mass / load (degree 2p)
+    pts, wts = simplex_quadrature(dim, 2 * degree)
+    v, _ = el.tabulate(pts)
+    mass = np.einsum("q,qi,qj->ij", wts, v, v)
+    load = np.einsum("q,qi->i", wts, v)
+    # stiffness rule (degree 2p-2)
+    cpts, cw = simplex_quadrature(dim, max(2 * degree - 2, 0))
+    _, cg = el.tabulate(cpts)
+    # interior-facet symmetric rule (degree 2p)
+    fb, fw = symmetric_facet_rule(dim - 1, 2 * degree)
+    _, ptab = facet_permutation_table(dim - 1, fb)
+    fval = np.empty((dim + 1, fb.shape[0], el.n_ld))
+    fgrad = np.empty((dim + 1, fb.shape[0], dim, el.n_ld))
+    for f in range(dim + 1):
+        fval[f], fgrad[f] = el.tabulate(el.facet_points(f, fb))
+    # exterior-facet rule: radiation integrand T^4 v has degree 5p
+    bpts, bw = simplex_quadrature(dim - 1, 5 * degree)
+    bw = bw / bw.sum()
+    bb = np.concatenate([1.0 - bpts.sum(axis=1, keepdims=True), bpts], axis=1) if dim > 1 else np.ones((1, 1))
+    bval = np.empty((dim + 1, bb.shape[0], el.n_ld))
+    for f in range(dim + 1):
+        bval[f], _ = el.tabulate(el.facet_points(f, bb))
+    return OperatorTables(el.n_ld, mass, load, cw, cg, fw, fval, fgrad, ptab, bw, bval)
+
+
+# --------------------------------------------------------------------------- mesh topology
+
+
+def _facet_keys(mesh: Mesh):
+    """Sorted global vertex tuples of every (cell, local facet): [n_cells*(d+1), d]."""
+    d = mesh.dim
+    fac = ref_facets(d)
+    fv = np.stack([mesh.cells[:, list(f)] for f in fac], axis=1).astype(np.int64)  # [nc, d+1, d]
+    return np.sort(fv.reshape(-1, d), axis=1)
+
+
+@dataclass
+class FacetTopology:
+    neighbor: np.ndarray      # [n_cells, d+1] int32 neighbour cell across local facet f, -1 on the boundary
+    nb_facet: np.ndarray      # [n_cells, d+1] int8  the neighbour's local facet index
+    nb_perm: np.ndarray       # [n_cells, d+1] int8  vertex-permutation id (index into itertools.permutations)
+    bnd_cell: np.ndarray      # [n_bf] int32 exterior facets: owning cell
+    bnd_facet: np.ndarray     # [n_bf] int32 local facet index
+
+
+def facet_topology(mesh: Mesh, exterior_mask=None) -> FacetTopology:
+    """Facet -> cell connectivity by sorting facet vertex tuples.
+
+    exterior_mask(facet_midpoints) -> bool may be given for a partitioned mesh to tell true domain
+    boundary facets from partition cuts (facets seen once locally that are interior globally)."""
+    d, nc = mesh.dim, mesh.n_cells
+    keys = _facet_keys(mesh)
+    nf = keys.shape[0]
+    order = np.lexsort(tuple(keys[:, c] for c in range(d - 1, -1, -1)))
+    sk = keys[order]
+    same = np.all(sk[1:] == sk[:-1], axis=1) if nf > 1 else np.zeros(0, dtype=bool)
+    neighbor = np.full(nf, -1, dtype=np.int32)
+    nb_facet = np.zeros(nf, dtype=np.int8)
+    a, b = order[:-1][same], order[1:][same]
+    neighbor[a], neighbor[b] = (b // (d + 1)).astype(np.int32), (a // (d + 1)).astype(np.int32)
+    nb_facet[a], nb_facet[b] = (b % (d + 1)).astype(np.int8), (a % (d + 1)).astype(np.int8)
+    # vertex permutation between the two cells' views of the facet
+    fac = np.array(ref_facets(d), dtype=np.int64)  # [d+1, d]
+    nb_perm = np.zeros(nf, dtype=np.int8)
+    if d > 1:
+        perms = list(itertools.permutations(range(d)))
+        interior = np.nonzero(neighbor >= 0)[0]
+        ci, fi = interior // (d + 1), interior % (d + 1)
+        gv_k = mesh.cells[ci[:, None], fac[fi]].astype(np.int64)                                  # [ni, d]
+        gv_n = mesh.cells[neighbor[interior][:, None], fac[nb_facet[interior].astype(np.int64)]].astype(np.int64)
+        # s(k') = position in gv_k of gv_n[k']
+        s = np.argmax(gv_n[:, :, None] == gv_k[:, None, :], axis=2)                               # [ni, d]
+        code = np.zeros(len(interior), dtype=np.int64)
+        for c in range(d):
+            code = code * d + s[:, c]
+        lut = np.full(d ** d, -1, dtype=np.int8)
+        for pid, p in enumerate(perms):
+            cc = 0
+            for c in range(d):
+                cc = cc * d + p[c]
+            lut[cc] = pid
+        nb_perm[interior] = lut[code]
+        assert (nb_perm[interior] >= 0).all()
+    bnd = np.nonzero(neighbor < 0)[0]
+    if exterior_mask is not None and bnd.size:
+        ci, fi = bnd // (d + 1), bnd % (d + 1)
+        mid = mesh.x[mesh.cells[ci[:, None], fac[fi]]].mean(axis=1)
+        bnd = bnd[exterior_mask(mid)]
+    return FacetTopology(neighbor.reshape(nc, d + 1), nb_facet.reshape(nc, d + 1), nb_perm.reshape(nc, d + 1),
+                         (bnd // (d + 1)).astype(np.int32), (bnd % (d + 1)).astype(np.int32))
+
+
+@dataclass
+class CellGeometry:
+    detJ: np.ndarray    # [n_cells]  |det J|
+    Jinv: np.ndarray    # [n_cells, d, d]  Jinv[a, c] = d xi_a / d x_c
+    h: np.ndarray       # [n_cells]  CellDiameter: max vertex distance (TVP:314)
+
+
+def cell_geometry(mesh: Mesh) -> CellGeometry:
+    d = mesh.dim
+    xv = mesh.x[mesh.cells]                       # [nc, d+1, d]
+    J = np.transpose(xv[:, 1:, :] - xv[:, :1, :], (0, 2, 1))   # J[c, a] = d x_c / d xi_a
+    if d == 1:
+        det = J[:, 0, 0]
+        Jinv = 1.0 / J
+    else:
+        det = np.linalg.det(J)
+        Jinv = np.linalg.inv(J)
+    h = np.zeros(mesh.n_cells)
+    for a, b in itertools.combinations(range(d + 1), 2):
+        h = np.maximum(h, np.linalg.norm(xv[:, a] - xv[:, b], axis=1))
+    return CellGeometry(np.abs(det), np.ascontiguousarray(Jinv), h)
+
+
+def facet_measures(mesh: Mesh, geo: CellGeometry, cell: np.ndarray, facet: np.ndarray) -> np.ndarray:
+    """|F| = detJ * |grad l_f| / (d-1)!  for the given (cell, local facet) pairs."""
+    d = mesh.dim
+    dlam = np.zeros((d + 1, d))
+    dlam[0, :] = -1.0
+    for i in range(d):
+        dlam[i + 1, i] = 1.0
+    g = np.einsum("nac,na->nc", geo.Jinv[cell], dlam[facet])
+    return geo.detJ[cell] * np.linalg.norm(g, axis=1) / math.factorial(d - 1)
+
+
+# --------------------------------------------------------------------------- function spaces
+
+
+class ScalarSpace:
+    """CG or DG Lagrange space of degree 1/2: the node set and the cell->node map.
+
+    Every reference space (T, Tf_partial, sigma, sigma_partial; TVP:77-101) is this node set times a
+    block size."""
+
+    def __init__(self, mesh: Mesh, family: str, degree: int):
+        assert family in ("CG", "DG"), "Only CG and DG elements are supported"   # TVP:70-71
+        self.mesh, self.family, self.degree = mesh, family, degree
+        self.element = LagrangeElement(mesh.dim, degree)
+        self.n_ld = self.element.n_ld
+        nc = mesh.n_cells
+        if family == "DG":
+            self.dofmap = np.arange(nc * self.n_ld, dtype=np.int32).reshape(nc, self.n_ld)
+            self.n_nodes = nc * self.n_ld
+        elif degree == 1:
+            self.dofmap = mesh.cells.copy()
+            self.n_nodes = mesh.n_vertices
+        else:
+            self.dofmap, self.n_nodes = _p2_dofmap(mesh)
+        self.dofmap = np.ascontiguousarray(self.dofmap, dtype=np.int32)
+
+    def key(self):
+        return (self.family, self.degree)
+
+    def tabulate_dof_coordinates(self) -> np.ndarray:
+        xv = self.mesh.x[self.mesh.cells]                            # [nc, d+1, d]
+        lam = np.concatenate([1.0 - self.element.nodes.sum(axis=1, keepdims=True), self.element.nodes], axis=1)
+        xc = np.einsum("lv,cvd->cld", lam, xv)                       # [nc, n_ld, d]
+        out = np.empty((self.n_nodes, self.mesh.dim))
+        out[self.dofmap.ravel()] = xc.reshape(-1, self.mesh.dim)
+        return out
+
+
+def _p2_dofmap(mesh: Mesh):
+    """P2 numbering: on a lattice mesh every P2 node is a point of the half-step lattice, so its id is
+    pure arithmetic; otherwise edges are numbered with np.unique."""
+    d, nc = mesh.dim, mesh.n_cells
+    edges = ref_edges(d)
+    lat = mesh.lattice
+    if lat is not None and lat["kind"] in ("box", "line") and _vertex_lattice_coords(mesh) is not None:
+        vc = _vertex_lattice_coords(mesh)                # [nv, d] local integer coordinates
+        dims2 = 2 * vc.max(axis=0) + 1
+        cv = vc[mesh.cells]                              # [nc, d+1, d]
+        loc = [2 * cv[:, i] for i in range(d + 1)] + [cv[:, a] + cv[:, b] for a, b in edges]
+        loc = np.stack(loc, axis=1).astype(np.int64)     # [nc, n_ld, d] doubled-lattice coordinates
+        strides = np.ones(d, dtype=np.int64)
+        for c in range(d - 2, -1, -1):
+            strides[c] = strides[c + 1] * dims2[c + 1]
+        ids = loc @ strides
+        return ids.astype(np.int32), int(np.prod(dims2))
+    nv = mesh.n_vertices
+    ev = np.stack([np.stack([mesh.cells[:, a], mesh.cells[:, b]], axis=1) for a, b in edges], axis=1).astype(np.int64)
+    ev.sort(axis=2)
+    keys = ev[:, :, 0] * nv + ev[:, :, 1]
+    uniq, inv = np.unique(keys.ravel(), return_inverse=True)
+    dm = np.concatenate([mesh.cells.astype(np.int64), nv + inv.reshape(nc, len(edges))], axis=1)
+    return dm.astype(np.int32), nv + uniq.size
+
+
+def _vertex_lattice_coords(mesh: Mesh):
+    """Integer lattice coordinates of the vertices of a structured mesh (local to the slab)."""
+    lat = mesh.lattice
+    if lat is None:
+        return None
+    if lat["kind"] == "line":
+        return np.arange(mesh.n_vertices, dtype=np.int64)[:, None]
+    n = lat["n"]
+    i0, i1 = lat["x_range"]
+    dims = [i1 - i0 + 1] + [k + 1 for k in n[1:]]
+    if int(np.prod(dims)) != mesh.n_vertices:
+        return None
+    grids = np.meshgrid(*[np.arange(k) for k in dims], indexing="ij")
+    return np.stack([g.ravel() for g in grids], axis=1).astype(np.int64)
+
+
+def winner_map(sigma: ScalarSpace, T: ScalarSpace):
+    """Cross-space evaluation map.
+
+    dolfinx interpolates an Expression cell by cell and scatters through the sigma dofmap, later
+    cells overwriting earlier ones, so the value at sigma node s comes from the LAST cell touching
+    it.  Returns (dofs [n_sigma, n_ld_T] int32, local_point [n_sigma] uint8, weights [n_pts, n_ld_T])."""
+    nc = sigma.mesh.n_cells
+    winner = np.full(sigma.n_nodes, -1, dtype=np.int64)
+    local = np.zeros(sigma.n_nodes, dtype=np.uint8)
+    flat = sigma.dofmap.ravel()
+    cell_of = np.repeat(np.arange(nc, dtype=np.int64), sigma.n_ld)
+    lp_of = np.tile(np.arange(sigma.n_ld, dtype=np.uint8), nc)
+    winner[flat] = cell_of      # numpy fancy assignment: the last occurrence wins
+    local[flat] = lp_of
+    assert (winner >= 0).all()
+    weights, _ = T.element.tabulate(sigma.element.nodes)
+    weights = np.where(np.abs(weights) < 1e-14, 0.0, weights)
+    weights = np.where(np.abs(weights - 1.0) < 1e-14, 1.0, weights)
+    return T.dofmap[winner].astype(np.int32), local, np.ascontiguousarray(weights)
