@@ -1,0 +1,370 @@
+// Jacobi-preconditioned conjugate gradients + Newton time-step driver + ghost-dof halo for hot path (B).
+//
+// Replaces dolfinx.nls.petsc.NewtonSolver (incremental criterion, TVP:334-337) and its PETSc KSP
+// 'cg' (TVP:343) — GAMG is not reproduced: the Jacobian M + dt*(alpha*K + boundary) is mass-dominated
+// and Jacobi-PCG converges in a few tens of iterations.
+//
+// All CG scalars (r.z, p.Ap, |r|^2) live on the device: each fused vector kernel finishes its
+// reduction with warp shuffles -> per-block partials -> the last block to finish sums the partials in
+// fixed order (deterministic), and the next kernel reads alpha/beta from that device buffer.  Across
+// GPUs the 1–2 doubles are combined with an in-place ncclAllReduce on the same stream; the ghost dofs
+// of the search direction are refreshed with grouped ncclSend/ncclRecv of contiguous ranges.
+#include <math.h>
+
+#include "sg_common.cuh"
+#include "sg_nccl.h"
+
+namespace {
+
+constexpr int VB = 256;          // threads per block of the vector kernels
+constexpr int MAX_BLOCKS = 1184; // 8 * 148 resident blocks; grid-stride beyond that
+
+// Scalars: S[0..1] / S[2..3] = {r.z, r.r} ping-pong by iteration parity, S[4] = p.Ap, S[5] = |dx|^2
+struct Red {
+    double *partials;   // [MAX_BLOCKS * 2]
+    unsigned *counter;
+};
+
+// Sum NR per-thread values over the grid; the LAST block adds the per-block partials in block order and
+// stores the totals in out[0..NR).  Must be called by every thread of every block.
+template <int NR>
+__device__ __forceinline__ void grid_reduce(double (&v)[NR], const Red red, double *out) {
+    __shared__ double scratch[32];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        const double s = sg_block_sum(v[k], scratch);
+        if (threadIdx.x == 0) red.partials[blockIdx.x * NR + k] = s;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(red.counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            double s = 0.0;
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += red.partials[b * NR + k];
+            s = sg_block_sum(s, scratch);
+            if (threadIdx.x == 0) out[k] = s;
+        }
+        if (threadIdx.x == 0) *red.counter = 0u;
+    }
+}
+
+__device__ __forceinline__ bool owned(long i, long lo, long hi) { return i >= lo && i < hi; }
+
+// x = 0, r = b, p = z = dinv*r ; S[0] = r.z, S[1] = r.r
+__global__ void __launch_bounds__(VB) k_pcg_init(long n, long lo, long hi, const double *__restrict__ b,
+                                                 const double *__restrict__ dinv, double *__restrict__ x,
+                                                 double *__restrict__ r, double *__restrict__ p, Red red, double *S) {
+    double acc[2] = {0.0, 0.0};
+    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
+        const double ri = b[i], zi = dinv[i] * ri;
+        x[i] = 0.0;
+        r[i] = ri;
+        p[i] = zi;
+        if (owned(i, lo, hi)) {
+            acc[0] += ri * zi;
+            acc[1] += ri * ri;
+        }
+    }
+    grid_reduce<2>(acc, red, S);
+}
+
+__global__ void __launch_bounds__(VB) k_dot(long lo, long hi, const double *__restrict__ a, const double *__restrict__ b,
+                                            Red red, double *out) {
+    double acc[1] = {0.0};
+    for (long i = lo + (long)blockIdx.x * VB + threadIdx.x; i < hi; i += (long)gridDim.x * VB) acc[0] += a[i] * b[i];
+    grid_reduce<1>(acc, red, out);
+}
+
+// alpha = rz/pAp ; x += alpha p ; r -= alpha Ap ; Snext = {r.(dinv r), r.r}
+__global__ void __launch_bounds__(VB) k_update_xr(long n, long lo, long hi, const double *__restrict__ p,
+                                                  const double *__restrict__ Ap, const double *__restrict__ dinv,
+                                                  double *__restrict__ x, double *__restrict__ r, Red red,
+                                                  const double *Scur, const double *SpAp, double *Snext) {
+    const double alpha = Scur[0] / SpAp[0];
+    double acc[2] = {0.0, 0.0};
+    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * Ap[i];
+        r[i] = ri;
+        if (owned(i, lo, hi)) {
+            acc[0] += ri * ri * dinv[i];
+            acc[1] += ri * ri;
+        }
+    }
+    grid_reduce<2>(acc, red, Snext);
+}
+
+// beta = rz_new/rz ; p = dinv r + beta p
+__global__ void __launch_bounds__(VB) k_update_p(long n, const double *__restrict__ r, const double *__restrict__ dinv,
+                                                 double *__restrict__ p, const double *Scur, const double *Snext) {
+    const double beta = Snext[0] / Scur[0];
+    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB)
+        p[i] = dinv[i] * r[i] + beta * p[i];
+}
+
+__global__ void __launch_bounds__(VB) k_invert(long n, double *__restrict__ d) {
+    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) d[i] = 1.0 / d[i];
+}
+
+// T -= dx ; out = |dx|^2 over owned dofs
+__global__ void __launch_bounds__(VB) k_newton_update(long n, long lo, long hi, double *__restrict__ T,
+                                                      const double *__restrict__ dx, Red red, double *out) {
+    double acc[1] = {0.0};
+    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
+        const double d = dx[i];
+        T[i] -= d;
+        if (owned(i, lo, hi)) acc[0] += d * d;
+    }
+    grid_reduce<1>(acc, red, out);
+}
+
+inline unsigned vgrid(long n) {
+    long g = (n + VB - 1) / VB;
+    if (g < 1) g = 1;
+    return (unsigned)(g > MAX_BLOCKS ? MAX_BLOCKS : g);
+}
+
+}  // namespace
+
+struct sg_halo_plan {
+    sg_ctx *ctx;
+    int n;
+    sg_halo_segment *seg;
+};
+
+struct sg_thermal_solver {
+    sg_thermal_op *op;
+    sg_ctx *ctx;
+    sg_halo_plan *halo;
+    long n, lo, hi;
+    double *b, *dx, *r, *p, *Ap, *dinv;   // workspace views
+    Red red;
+    double *S;        // device scalars [8]
+    double *S_host;   // pinned mirror
+};
+
+namespace {
+
+int allreduce(sg_thermal_solver *s, double *ptr, int count, cudaStream_t st) {
+    if (s->ctx->nranks == 1) return SG_OK;
+    SG_CHECK_NCCL(sg_nccl()->AllReduce(ptr, ptr, (size_t)count, ncclDouble, ncclSum, s->ctx->comm, st));
+    return SG_OK;
+}
+
+int read_scalars(sg_thermal_solver *s, int first, int count, cudaStream_t st) {
+    SG_CHECK_CUDA(cudaMemcpyAsync(s->S_host + first, s->S + first, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    SG_CHECK_CUDA(cudaStreamSynchronize(st));
+    return SG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sg_halo_plan_create(sg_ctx *ctx, int32_t n_segments, const sg_halo_segment *segments, sg_halo_plan **out) {
+    SG_REQUIRE(ctx && out && n_segments >= 0 && (n_segments == 0 || segments), "sg_halo_plan_create: bad argument");
+    for (int i = 0; i < n_segments; ++i) {
+        SG_REQUIRE(segments[i].peer >= 0 && segments[i].peer < ctx->nranks && segments[i].peer != ctx->rank,
+                   "sg_halo_plan_create: segment %d has bad peer %d", i, segments[i].peer);
+        SG_REQUIRE(segments[i].send_count >= 0 && segments[i].recv_count >= 0, "sg_halo_plan_create: negative count");
+    }
+    sg_halo_plan *p = new sg_halo_plan();
+    p->ctx = ctx;
+    p->n = n_segments;
+    p->seg = new sg_halo_segment[n_segments > 0 ? n_segments : 1];
+    for (int i = 0; i < n_segments; ++i) p->seg[i] = segments[i];
+    *out = p;
+    return SG_OK;
+}
+
+int sg_halo_plan_destroy(sg_halo_plan *plan) {
+    if (!plan) return SG_OK;
+    delete[] plan->seg;
+    delete plan;
+    return SG_OK;
+}
+
+int sg_halo_forward(sg_halo_plan *plan, double *vec, int32_t bs, void *stream) {
+    SG_REQUIRE(plan && vec && bs >= 1, "sg_halo_forward: bad argument");
+    if (plan->n == 0) return SG_OK;
+    const SgNccl *n = sg_nccl();
+    if (!n || !plan->ctx->comm) {
+        sg_set_error("sg_halo_forward: context has no NCCL communicator");
+        return SG_E_NCCL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SG_CHECK_NCCL(n->GroupStart());
+    for (int i = 0; i < plan->n; ++i) {
+        const sg_halo_segment &g = plan->seg[i];
+        if (g.send_count > 0)
+            SG_CHECK_NCCL(n->Send(vec + g.send_offset * bs, (size_t)(g.send_count * bs), ncclDouble, g.peer, plan->ctx->comm, st));
+        if (g.recv_count > 0)
+            SG_CHECK_NCCL(n->Recv(vec + g.recv_offset * bs, (size_t)(g.recv_count * bs), ncclDouble, g.peer, plan->ctx->comm, st));
+    }
+    SG_CHECK_NCCL(n->GroupEnd());
+    return SG_OK;
+}
+
+int64_t sg_thermal_solver_workspace_doubles(const sg_thermal_op *op) {
+    if (!op) return -1;
+    return 6 * sg_op_ndofs(op);
+}
+
+int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan *halo, sg_thermal_solver **out) {
+    SG_REQUIRE(op && workspace && out, "sg_thermal_solver_create: NULL argument");
+    sg_thermal_solver *s = new sg_thermal_solver();
+    s->op = op;
+    int64_t lo, hi;
+    sg_op_ranges(op, &lo, &hi, &s->ctx);
+    s->halo = halo;
+    s->n = (long)sg_op_ndofs(op);
+    s->lo = (long)lo;
+    s->hi = (long)hi;
+    SG_REQUIRE(s->ctx->nranks == 1 || halo, "sg_thermal_solver_create: a multi-GPU context needs a halo plan");
+    double *w = workspace;
+    s->b = w;
+    s->dx = w + s->n;
+    s->r = w + 2 * s->n;
+    s->p = w + 3 * s->n;
+    s->Ap = w + 4 * s->n;
+    s->dinv = w + 5 * s->n;
+    s->red.partials = nullptr;
+    s->red.counter = nullptr;
+    s->S = nullptr;
+    s->S_host = nullptr;
+    cudaError_t e = cudaMalloc(&s->red.partials, sizeof(double) * MAX_BLOCKS * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&s->red.counter, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(s->red.counter, 0, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&s->S, sizeof(double) * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->S, 0, sizeof(double) * 8);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->S_host, sizeof(double) * 8);
+    if (e != cudaSuccess) {
+        sg_set_error("sg_thermal_solver_create: %s", cudaGetErrorString(e));
+        sg_thermal_solver_destroy(s);
+        return SG_E_CUDA;
+    }
+    *out = s;
+    return SG_OK;
+}
+
+int sg_thermal_solver_destroy(sg_thermal_solver *s) {
+    if (!s) return SG_OK;
+    if (s->red.partials) cudaFree(s->red.partials);
+    if (s->red.counter) cudaFree(s->red.counter);
+    if (s->S) cudaFree(s->S);
+    if (s->S_host) cudaFreeHost(s->S_host);
+    delete s;
+    return SG_OK;
+}
+
+int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, double *x, double rtol, double atol,
+                 int32_t max_it, int32_t *iters, double *rel_res, void *stream) {
+    SG_REQUIRE(s && T_lin && b && x, "sg_pcg_solve: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long n = s->n, lo = s->lo, hi = s->hi;
+    const unsigned g = vgrid(n), go = vgrid(hi - lo);
+    double *S = s->S;
+    int rc;
+    k_pcg_init<<<g, VB, 0, st>>>(n, lo, hi, b, s->dinv, x, s->r, s->p, s->red, S);
+    SG_CHECK_CUDA(cudaGetLastError());
+    if ((rc = allreduce(s, S, 2, st))) return rc;
+    if ((rc = read_scalars(s, 0, 2, st))) return rc;
+    const double rr0 = s->S_host[1];
+    const double tol2 = fmax(rtol * rtol * rr0, atol * atol);
+    int it = 0;
+    double rr = rr0;
+    if (!(rr0 >= 0.0) || !isfinite(rr0)) {
+        sg_set_error("sg_pcg_solve: right-hand side is not finite");
+        return SG_E_NOCONV;
+    }
+    while (rr > tol2 && it < max_it) {
+        double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
+        if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
+        if ((rc = sg_thermal_jac_apply(s->op, T_lin, s->p, s->Ap, st))) return rc;
+        k_dot<<<go, VB, 0, st>>>(lo, hi, s->p, s->Ap, s->red, S + 4);
+        SG_CHECK_CUDA(cudaGetLastError());
+        if ((rc = allreduce(s, S + 4, 1, st))) return rc;
+        k_update_xr<<<g, VB, 0, st>>>(n, lo, hi, s->p, s->Ap, s->dinv, x, s->r, s->red, Scur, S + 4, Snext);
+        SG_CHECK_CUDA(cudaGetLastError());
+        if ((rc = allreduce(s, Snext, 2, st))) return rc;
+        k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, Scur, Snext);
+        SG_CHECK_CUDA(cudaGetLastError());
+        ++it;
+        if ((rc = read_scalars(s, 2 * (it & 1), 2, st))) return rc;
+        rr = s->S_host[2 * (it & 1) + 1];
+        if (!isfinite(rr)) {
+            sg_set_error("sg_pcg_solve: residual became non-finite at iteration %d (operator not SPD?)", it);
+            return SG_E_NOCONV;
+        }
+    }
+    if (iters) *iters = it;
+    if (rel_res) *rel_res = rr0 > 0.0 ? sqrt(rr / rr0) : 0.0;
+    if (rr > tol2) {
+        sg_set_error("sg_pcg_solve: no convergence in %d iterations (relative residual %.3e)", it,
+                     rr0 > 0 ? sqrt(rr / rr0) : 0.0);
+        return SG_E_NOCONV;
+    }
+    return SG_OK;
+}
+
+int sg_thermal_timestep(sg_thermal_solver *s, double *T, const double *T_prev, const sg_newton_opts *o,
+                        sg_newton_stats *stats, void *stream) {
+    SG_REQUIRE(s && T && T_prev && o, "sg_thermal_timestep: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long n = s->n;
+    const unsigned g = vgrid(n);
+    int rc, lin_total = 0;
+    double r0 = 0.0, r = 0.0, lin_res = 0.0;
+    int it = 0, converged = 0;
+    for (it = 1; it <= o->newton_max_it; ++it) {
+        if (s->halo && (rc = sg_halo_forward(s->halo, T, 1, st))) return rc;
+        if ((rc = sg_thermal_residual(s->op, T, T_prev, s->b, st))) return rc;          // b = F(T)
+        if ((rc = sg_thermal_jac_diag(s->op, T, s->dinv, st))) return rc;               // J(T) diagonal
+        k_invert<<<g, VB, 0, st>>>(n, s->dinv);
+        SG_CHECK_CUDA(cudaGetLastError());
+        int lin_it = 0;
+        rc = sg_pcg_solve(s, T, s->b, s->dx, o->lin_rtol, o->lin_atol, o->lin_max_it, &lin_it, &lin_res, st);
+        lin_total += lin_it;
+        if (rc) return rc;
+        k_newton_update<<<g, VB, 0, st>>>(n, s->lo, s->hi, T, s->dx, s->red, s->S + 5);  // T <- T - dx
+        SG_CHECK_CUDA(cudaGetLastError());
+        if ((rc = allreduce(s, s->S + 5, 1, st))) return rc;
+        if ((rc = read_scalars(s, 5, 1, st))) return rc;
+        r = sqrt(s->S_host[5]);
+        // dolfinx NewtonSolver, convergence_criterion = "incremental": iteration 1 only records r0
+        if (it == 1) {
+            r0 = r;
+            if (r0 == 0.0) {
+                converged = 1;
+                break;
+            }
+        } else if (r / r0 < o->newton_rtol || r < o->newton_atol) {
+            converged = 1;
+            break;
+        }
+    }
+    if (s->halo && (rc = sg_halo_forward(s->halo, T, 1, st))) return rc;
+    if (stats) {
+        stats->newton_its = it > o->newton_max_it ? o->newton_max_it : it;
+        stats->lin_its = lin_total;
+        stats->converged = converged;
+        stats->dx_norm_first = r0;
+        stats->dx_norm_last = r;
+        stats->lin_rel_res_last = lin_res;
+    }
+    if (!converged) {
+        sg_set_error("sg_thermal_timestep: Newton did not converge in %d iterations (|dx| = %.3e, |dx0| = %.3e)",
+                     o->newton_max_it, r, r0);
+        return SG_E_NOCONV;
+    }
+    return SG_OK;
+}
+
+}  // extern "C"

@@ -20,6 +20,10 @@ struct sg_ctx {
 
 void sg_set_error(const char *fmt, ...);
 
+// internal accessors of sg_thermal_op (defined in thermal.cu) for the solver in pcg.cu
+int64_t sg_op_ndofs(const sg_thermal_op *op);
+void sg_op_ranges(const sg_thermal_op *op, int64_t *own_lo, int64_t *own_hi, sg_ctx **ctx);
+
 #define SG_CHECK_CUDA(expr)                                                                  \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \

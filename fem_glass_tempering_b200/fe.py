@@ -78,6 +78,20 @@ def simplex_quadrature(dim: int, degree: int):
     return np.array(pts), np.array(wts)
 
 
+def minimal_cell_rule(dim: int, degree: int):
+    """Fewest-point rules for the stiffness integrand: centroid (degree <= 1), and the classical
+    degree-2 rules with dim+1 points; otherwise the collapsed rule."""
+    if degree <= 1:
+        return np.full((1, dim), 1.0 / (dim + 1)), np.array([1.0 / math.factorial(dim)])
+    if degree == 2 and dim == 2:
+        a = 1.0 / 6.0
+        return np.array([[a, a], [1 - 2 * a, a], [a, 1 - 2 * a]]), np.full(3, 1.0 / 6.0)
+    if degree == 2 and dim == 3:
+        a, b = (5.0 - math.sqrt(5.0)) / 20.0, (5.0 + 3.0 * math.sqrt(5.0)) / 20.0
+        return np.array([[a, a, a], [b, a, a], [a, b, a], [a, a, b]]), np.full(4, 1.0 / 24.0)
+    return simplex_quadrature(dim, degree)
+
+
 def symmetric_facet_rule(fdim: int, degree: int):
     """Rule on the reference facet simplex that is invariant under vertex permutations, in facet
     BARYCENTRIC coordinates [nq, fdim+1]; weights sum to 1.  Needed on interior facets, where the two
@@ -209,8 +223,8 @@ def operator_tables(dim: int, degree: int) -> OperatorTables:
     v, _ = el.tabulate(pts)
     mass = np.einsum("q,qi,qj->ij", wts, v, v)
     load = np.einsum("q,qi->i", wts, v)
-    # stiffness rule (degree 2p-2)
-    cpts, cw = simplex_quadrature(dim, max(2 * degree - 2, 0))
+    # stiffness rule (degree 2p-2) with the minimal number of points
+    cpts, cw = minimal_cell_rule(dim, max(2 * degree - 2, 0))
     _, cg = el.tabulate(cpts)
     # interior-facet symmetric rule (degree 2p)
     fb, fw = symmetric_facet_rule(dim - 1, 2 * degree)

@@ -1,0 +1,169 @@
+"""Host-side builder of the CUDA heat-equation operator: uploads the mesh/element arrays of one
+function space and wraps sg_thermal_op / sg_thermal_solver / sg_halo_plan.
+
+This is the product's replacement for `NonlinearProblem(F, u)` + `NewtonSolver` (ThermoViscoProblem.py:
+330-346).  Set-up is numpy on the host; every operation afterwards is a CUDA call through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, fe
+from ._lib_thermal import HaloSegmentC, NewtonOptsC, NewtonStatsC, ThermalDescC
+
+PENALTY = 5.0  # ThermoViscoProblem.py:313
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ThermalOperator:
+    """Matrix-free Jacobian/residual of the heat equation on one GPU (one rank's part of the mesh).
+
+    space         fe.ScalarSpace of T
+    params        model_params dict (main.py:29-55)
+    partition     optional dict(cell_lo, cell_hi, own_lo, own_hi, exterior_mask, halo=[(peer, send_off, send_cnt,
+                  recv_off, recv_cnt), ...]) describing this rank's slab; default: everything owned.
+    """
+
+    def __init__(self, ctx: _lib.Context, space: fe.ScalarSpace, params: dict, dt: float, partition: dict | None = None):
+        import torch
+        self.ctx, self.space, self.dt = ctx, space, float(dt)
+        mesh, d = space.mesh, space.mesh.dim
+        dev = torch.device("cuda", ctx.device)
+        part = partition or {}
+        tabs = fe.operator_tables(d, space.degree)
+        geo = fe.cell_geometry(mesh)
+        topo = fe.facet_topology(mesh, part.get("exterior_mask"))
+        nc = mesh.n_cells
+        self.tabs, self.n_dofs = tabs, space.n_nodes
+        # geometry SoA [d*d + 2][nc]
+        g = np.empty((d * d + 2, nc))
+        g[: d * d] = geo.Jinv.reshape(nc, d * d).T
+        g[d * d], g[d * d + 1] = geo.detJ, geo.h
+        keep = {}
+        keep["geom"] = torch.from_numpy(np.ascontiguousarray(g)).to(dev)
+        dg = space.family == "DG"
+        if dg:
+            keep["nbr"] = torch.from_numpy(np.ascontiguousarray(topo.neighbor.T.astype(np.int32))).to(dev)
+            info = np.zeros(nc, dtype=np.int64)
+            for f in range(d + 1):
+                info |= ((topo.nb_facet[:, f].astype(np.int64) & 3) | (topo.nb_perm[:, f].astype(np.int64) << 2)) << (5 * f)
+            keep["nbinfo"] = torch.from_numpy(info.astype(np.int32)).to(dev)
+        else:
+            keep["dofmap"] = torch.from_numpy(np.ascontiguousarray(space.dofmap.T.astype(np.int32))).to(dev)
+        nbf = topo.bnd_cell.size
+        if nbf:
+            keep["bf_cell"] = torch.from_numpy(topo.bnd_cell.astype(np.int32)).to(dev)
+            keep["bf_facet"] = torch.from_numpy(topo.bnd_facet.astype(np.int32)).to(dev)
+            keep["bf_area"] = torch.from_numpy(fe.facet_measures(mesh, geo, topo.bnd_cell, topo.bnd_facet)).to(dev)
+        self._keep = keep
+        # host tables (copied by the library during create)
+        h = {k: np.ascontiguousarray(getattr(tabs, k), dtype=np.float64)
+             for k in ("mass", "load", "cq_w", "cq_grad", "fq_w", "fq_val", "fq_grad", "bq_w", "bq_val")}
+        h["fq_perm"] = np.ascontiguousarray(tabs.fq_perm, dtype=np.int32)
+        desc = ThermalDescC()
+        desc.dim, desc.degree, desc.family = d, space.degree, 1 if dg else 0
+        desc.n_cells, desc.cell_lo, desc.cell_hi = nc, part.get("cell_lo", 0), part.get("cell_hi", nc)
+        desc.n_dofs, desc.own_lo, desc.own_hi = space.n_nodes, part.get("own_lo", 0), part.get("own_hi", space.n_nodes)
+        for name in ("dofmap", "geom", "nbr", "nbinfo", "bf_cell", "bf_facet", "bf_area"):
+            setattr(desc, name, _lib.ptr(keep.get(name)))
+        desc.n_bfacets = nbf
+        desc.n_ld, desc.nqc, desc.nqf, desc.nqb = tabs.n_ld, tabs.cq_w.size, tabs.fq_w.size, tabs.bq_w.size
+        desc.n_perm = tabs.fq_perm.shape[0]
+        for name, arr in h.items():
+            setattr(desc, name, _np_ptr(arr))
+        desc.dt, desc.alpha, desc.f = self.dt, float(params["alpha"]), float(params["f"])
+        desc.sigma, desc.epsilon = float(params["sigma"]), float(params["epsilon"])
+        desc.htc, desc.T_ambient, desc.penalty = float(params["htc"]), float(params["T_ambient"]), PENALTY
+        self.own_lo, self.own_hi = desc.own_lo, desc.own_hi
+        self.cell_lo, self.cell_hi = desc.cell_lo, desc.cell_hi
+        self.n_bfacets = nbf
+        L = _lib.lib()
+        hnd = C.c_void_p()
+        _lib.check(L.sg_thermal_op_create(ctx.handle, C.byref(desc), C.byref(hnd)))
+        self.handle = hnd
+        # halo plan + solver
+        self.halo = None
+        segs = part.get("halo") or []
+        if segs:
+            arr = (HaloSegmentC * len(segs))()
+            for i, (peer, so, sc, ro, rc) in enumerate(segs):
+                arr[i].peer, arr[i].send_offset, arr[i].send_count = peer, so, sc
+                arr[i].recv_offset, arr[i].recv_count = ro, rc
+            hh = C.c_void_p()
+            _lib.check(L.sg_halo_plan_create(ctx.handle, len(segs), arr, C.byref(hh)))
+            self.halo = hh
+        nws = L.sg_thermal_solver_workspace_doubles(self.handle)
+        self.workspace = torch.zeros(max(int(nws), 1), dtype=torch.float64, device=dev)
+        sh = C.c_void_p()
+        _lib.check(L.sg_thermal_solver_create(self.handle, self.workspace.data_ptr(), self.halo, C.byref(sh)))
+        self.solver = sh
+        self.opts = NewtonOptsC(1e-12, 1e-10, 50, 1e-8, 0.0, 10000)
+        self.last_stats = None
+
+    # -- raw operator calls (asynchronous on the current stream) ---------------------------------
+    def residual(self, T, T_prev, out):
+        _lib.check(_lib.lib().sg_thermal_residual(self.handle, _lib.ptr(T), _lib.ptr(T_prev), _lib.ptr(out),
+                                                  _lib.current_stream_ptr()))
+        return out
+
+    def jac_apply(self, T_lin, x, out):
+        _lib.check(_lib.lib().sg_thermal_jac_apply(self.handle, _lib.ptr(T_lin), _lib.ptr(x), _lib.ptr(out),
+                                                   _lib.current_stream_ptr()))
+        return out
+
+    def jac_diag(self, T_lin, out):
+        _lib.check(_lib.lib().sg_thermal_jac_diag(self.handle, _lib.ptr(T_lin), _lib.ptr(out), _lib.current_stream_ptr()))
+        return out
+
+    def apply_bytes(self) -> int:
+        return int(_lib.lib().sg_thermal_apply_bytes(self.handle))
+
+    def halo_forward(self, vec, block_size: int = 1):
+        if self.halo is not None:
+            _lib.check(_lib.lib().sg_halo_forward(self.halo, _lib.ptr(vec), block_size, _lib.current_stream_ptr()))
+
+    # -- solves (synchronous) ------------------------------------------------------------------------
+    def pcg(self, T_lin, b, x, rtol=1e-10, atol=0.0, max_it=10000):
+        """Solve J(T_lin) x = b; the Jacobi diagonal must have been set by `prepare_preconditioner`."""
+        it, res = C.c_int32(0), C.c_double(0.0)
+        _lib.check(_lib.lib().sg_pcg_solve(self.solver, _lib.ptr(T_lin), _lib.ptr(b), _lib.ptr(x), rtol, atol, max_it,
+                                           C.byref(it), C.byref(res), _lib.current_stream_ptr()))
+        return it.value, res.value
+
+    def prepare_preconditioner(self, T_lin):
+        n = self.n_dofs
+        dinv = self.workspace[5 * n: 6 * n]
+        self.jac_diag(T_lin, dinv)
+        dinv.reciprocal_()
+
+    def timestep(self, T, T_prev) -> NewtonStatsC:
+        """Newton solve of F(T) = 0 in place on T (NewtonSolver.solve, ThermoViscoProblem.py:389)."""
+        st = NewtonStatsC()
+        rc = _lib.lib().sg_thermal_timestep(self.solver, _lib.ptr(T), _lib.ptr(T_prev), C.byref(self.opts), C.byref(st),
+                                            _lib.current_stream_ptr())
+        self.last_stats = st
+        _lib.check(rc)
+        return st
+
+    def close(self):
+        L = _lib.lib()
+        if getattr(self, "solver", None):
+            L.sg_thermal_solver_destroy(self.solver)
+            self.solver = None
+        if getattr(self, "halo", None):
+            L.sg_halo_plan_destroy(self.halo)
+            self.halo = None
+        if getattr(self, "handle", None):
+            L.sg_thermal_op_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

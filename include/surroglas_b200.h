@@ -135,6 +135,89 @@ int sg_visco_update_tensor(sg_visco_plan *plan, int64_t n_sigma_nodes, const sg_
  * (used by bench.py for the roofline). */
 int64_t sg_visco_bytes_per_node(const sg_visco_params *params, const sg_visco_fields *f, uint32_t phases);
 
+
+/* --------------------------------------------- (B) heat-equation operator + solve */
+
+/* Mesh, element tables and physics of the thermal problem.  Replaces
+ * NonlinearProblem(F, u) (TVP:331) built from the weak form TVP:293-325 with the
+ * constants of ThermalModel (TM:18-27).  Index/geometry arrays are DEVICE pointers
+ * that must outlive the operator; the reference tables are HOST pointers and are
+ * copied.  Local cells [cell_lo, cell_hi) are the ones this rank integrates over;
+ * dofs [own_lo, own_hi) are the ones it owns (reductions run over them). */
+typedef struct {
+    int32_t dim, degree;
+    int32_t family;                 /* 0 = CG ('Lagrange'), 1 = DG ('Discontinuous Lagrange'), TVP:284,308 */
+    int64_t n_cells, cell_lo, cell_hi;
+    int64_t n_dofs, own_lo, own_hi;
+    const int32_t *dofmap;          /* CG: [n_ld][n_cells] (SoA); DG: NULL (dof = cell*n_ld + i) */
+    const double *geom;             /* [dim*dim + 2][n_cells]: Jinv[a][c] = d xi_a/d x_c, |detJ|, CellDiameter h */
+    const int32_t *nbr;             /* DG: [dim+1][n_cells] neighbour across local facet f, -1 = none */
+    const int32_t *nbinfo;          /* DG: [n_cells], 5 bits per facet: nb_facet | perm_id << 2 */
+    int64_t n_bfacets;              /* exterior facets (ds) */
+    const int32_t *bf_cell, *bf_facet;
+    const double *bf_area;
+    /* reference tables (host), see fem_glass_tempering_b200/fe.py: operator_tables() */
+    int32_t n_ld, nqc, nqf, nqb, n_perm;
+    const double *mass, *load, *cq_w, *cq_grad;
+    const double *fq_w, *fq_val, *fq_grad;
+    const int32_t *fq_perm;
+    const double *bq_w, *bq_val;
+    /* physics: main.py:29-55 / TM:18-27; penalty = 5.0 (TVP:313) */
+    double dt, alpha, f, sigma, epsilon, htc, T_ambient, penalty;
+} sg_thermal_desc;
+
+typedef struct sg_thermal_op sg_thermal_op;
+int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *desc, sg_thermal_op **out);
+int sg_thermal_op_destroy(sg_thermal_op *op);
+
+/* F(T; v) of TVP:293-325 (what NonlinearProblem.F assembles). */
+int sg_thermal_residual(sg_thermal_op *op, const double *T, const double *T_prev, double *F, void *stream);
+/* y = J(T_lin) x, J = dF/dT (what NonlinearProblem.J assembles + PETSc MatMult). */
+int sg_thermal_jac_apply(sg_thermal_op *op, const double *T_lin, const double *x, double *y, void *stream);
+/* diag J(T_lin) (Jacobi preconditioner; the reference uses GAMG, TVP:344). */
+int sg_thermal_jac_diag(sg_thermal_op *op, const double *T_lin, double *diag, void *stream);
+/* Algorithmic HBM bytes of one sg_thermal_jac_apply (roofline numerator). */
+int64_t sg_thermal_apply_bytes(const sg_thermal_op *op);
+
+/* Ghost-dof forward scatter (TVP:351 x.scatter_forward()).  The element partition is
+ * by x-slabs with lattice numbering, so every exchange is a contiguous range. */
+typedef struct {
+    int32_t peer;
+    int64_t send_offset, send_count;   /* in nodes; multiplied by block_size */
+    int64_t recv_offset, recv_count;
+} sg_halo_segment;
+typedef struct sg_halo_plan sg_halo_plan;
+int sg_halo_plan_create(sg_ctx *ctx, int32_t n_segments, const sg_halo_segment *segments, sg_halo_plan **out);
+int sg_halo_plan_destroy(sg_halo_plan *plan);
+int sg_halo_forward(sg_halo_plan *plan, double *vec, int32_t block_size, void *stream);
+
+/* Newton + Jacobi-PCG time-step solver (NewtonSolver.solve, TVP:334-346,389). */
+typedef struct {
+    double newton_rtol;   /* 1e-12, TVP:336 */
+    double newton_atol;   /* 1e-10, dolfinx default */
+    int32_t newton_max_it;/* 50, dolfinx default */
+    double lin_rtol;      /* relative residual of each PCG solve */
+    double lin_atol;
+    int32_t lin_max_it;
+} sg_newton_opts;
+
+typedef struct {
+    int32_t newton_its, lin_its, converged;
+    double dx_norm_first, dx_norm_last, lin_rel_res_last;
+} sg_newton_stats;
+
+typedef struct sg_thermal_solver sg_thermal_solver;
+int64_t sg_thermal_solver_workspace_doubles(const sg_thermal_op *op);
+int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan *halo, sg_thermal_solver **out);
+int sg_thermal_solver_destroy(sg_thermal_solver *s);
+/* Solve J(T_lin) x = b with Jacobi-PCG from x = 0; blocks until converged (KSP 'cg', TVP:343). */
+int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, double *x, double rtol, double atol,
+                 int32_t max_it, int32_t *iters, double *rel_res, void *stream);
+/* One implicit-Euler step: Newton on F(T) = 0 starting from T (in/out), TVP:384-391.  Returns
+ * SG_E_NOCONV when the incremental criterion is not met (the reference asserts, TVP:390). */
+int sg_thermal_timestep(sg_thermal_solver *s, double *T, const double *T_prev, const sg_newton_opts *opts,
+                        sg_newton_stats *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,89 @@
+"""TEST INFRASTRUCTURE: numpy emulation of the table-driven algorithm csrc/thermal.cu implements
+(cell-centric cells + DG interior facets via permutation tables + exterior facets).  It exists so that
+the host-side tables of fem_glass_tempering_b200.fe (quadrature, facet permutations, neighbour maps) can
+be validated against the assembled oracle on the CPU, where no GPU is available.  Never used by the product."""
+import math
+
+import numpy as np
+
+from fem_glass_tempering_b200 import fe
+
+
+def _dlam(d):
+    g = np.zeros((d + 1, d))
+    g[0, :] = -1.0
+    for i in range(d):
+        g[i + 1, i] = 1.0
+    return g
+
+
+def jac_apply(space, tabs, geo, topo, params, dt, x, T_lin=None, xm=None, residual=False, T_prev=None):
+    """y = J(T_lin) x   (residual=False)   or   y = F(x; T_prev)   (residual=True)."""
+    mesh, d, nl = space.mesh, space.mesh.dim, space.n_ld
+    a = float(params["alpha"])
+    dm = space.dofmap
+    y = np.zeros(space.n_nodes)
+    xk = x[dm]                                                    # [nc, nl]
+    xmass = xk - T_prev[dm] if residual else xk
+    ym = geo.detJ[:, None] * (xmass @ tabs.mass.T)
+    gref = np.einsum("qaj,cj->cqa", tabs.cq_grad, xk)
+    gphys = np.einsum("cab,cqa->cqb", geo.Jinv, gref)
+    flux = np.einsum("cab,cqb->cqa", geo.Jinv, gphys) * (tabs.cq_w[None, :, None] * geo.detJ[:, None, None])
+    ys = np.einsum("qai,cqa->ci", tabs.cq_grad, flux)
+    yk = ym + dt * a * ys
+    if residual:
+        yk -= dt * float(params["f"]) * geo.detJ[:, None] * tabs.load[None, :]
+    if space.family == "DG":
+        dl = _dlam(d)
+        nc = mesh.n_cells
+        for f in range(d + 1):
+            nb = topo.neighbor[:, f]
+            act = np.nonzero(nb >= 0)[0]
+            if act.size == 0:
+                continue
+            nbc = nb[act]
+            g = np.einsum("cab,a->cb", geo.Jinv[act], dl[f])                  # grad lambda_f
+            gn = np.linalg.norm(g, axis=1)
+            n = -g / gn[:, None]
+            area = geo.detJ[act] * gn / math.factorial(d - 1)
+            hplus = np.where(act < nbc, geo.h[act], geo.h[nbc])
+            jn = np.einsum("cab,cb->ca", geo.Jinv[act], n)                    # (Jinv n)_a, own cell
+            jnN = np.einsum("cab,cb->ca", geo.Jinv[nbc], n)
+            nbf = topo.nb_facet[act, f].astype(int)
+            pid = topo.nb_perm[act, f].astype(int)
+            xK, xN = x[dm[act]], x[dm[nbc]]
+            for q in range(tabs.fq_w.size):
+                qn = tabs.fq_perm[pid, q]
+                vK = tabs.fq_val[f, q] @ xK.T                                  # [na]
+                phiN = tabs.fq_val[nbf, qn]                                    # [na, nl]
+                vN = np.einsum("cj,cj->c", phiN, xN)
+                dphiK = np.einsum("ca,ai->ci", jn, tabs.fq_grad[f, q])         # dn of own basis
+                dphiN = np.einsum("ca,cai->ci", jnN, tabs.fq_grad[nbf, qn])
+                dnK = np.einsum("ci,ci->c", dphiK, xK)
+                dnN = np.einsum("ci,ci->c", dphiN, xN)
+                jump = vK - vN
+                w = dt * a * tabs.fq_w[q] * area
+                contrib = w[:, None] * ((fe_penalty() / hplus * jump)[:, None] * tabs.fq_val[f, q][None, :]
+                                        - 0.5 * dphiK * jump[:, None]
+                                        - tabs.fq_val[f, q][None, :] * (0.5 * (dnK + dnN))[:, None])
+                np.add.at(yk, act, contrib)
+    np.add.at(y, dm.ravel(), yk.ravel())
+    # exterior facets
+    se, htc, Ta = float(params["sigma"]) * float(params["epsilon"]), float(params["htc"]), float(params["T_ambient"])
+    area = fe.facet_measures(mesh, geo, topo.bnd_cell, topo.bnd_facet)
+    for c, f, ar in zip(topo.bnd_cell, topo.bnd_facet, area):
+        v = tabs.bq_val[f]                                                     # [nq, nl]
+        dofs = dm[c]
+        if residual:
+            Tq = v @ x[dofs]
+            flux = 0.001 * se * (Tq ** 4 - Ta ** 4) + 0.001 * htc * (Tq - Ta)
+            y[dofs] += dt * ar * (v.T @ (tabs.bq_w * flux))
+        else:
+            Tq = v @ T_lin[dofs]
+            coef = 0.001 * (4 * se * Tq ** 3 + htc)
+            y[dofs] += dt * ar * (v.T @ (tabs.bq_w * coef * (v @ x[dofs])))
+    return y
+
+
+def fe_penalty():
+    return 5.0

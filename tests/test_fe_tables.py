@@ -1,0 +1,182 @@
+"""CPU: host-side FE tables / mesh topology of the product against the independent thermal oracle."""
+import itertools
+import math
+
+import numpy as np
+import pytest
+
+import kernel_mirror
+from fem_glass_tempering_b200 import fe
+from fem_glass_tempering_b200 import mesh as msh
+from oracle import thermal_oracle as to
+from oracle.visco_oracle import MAIN_PARAMS
+
+
+def _mesh(dim, n=None):
+    if dim == 1:
+        return msh.graded_line_mesh() if n is None else msh.interval_mesh(n)
+    if dim == 2:
+        return msh.rectangle_mesh(*(n or (5, 3)), 5.0, 2.5)
+    return msh.box_mesh(*(n or (3, 2, 2)), 1.5, 1.0, 0.8)
+
+
+def test_graded_line_matches_gmsh_counts():
+    m = msh.graded_line_mesh()
+    assert m.n_cells == 48                       # 13 + 11 + 11 + 13
+    x = m.x[:, 0]
+    assert x[0] == 0.0 and x[-1] == 50.0 and np.all(np.diff(x) > 0)
+    assert abs(x[1] - x[0] - 0.1) < 0.02 and abs(np.diff(x).max() - 3.0) < 0.5
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("degree", [0, 1, 2, 3, 4, 5, 10])
+def test_simplex_quadrature_exact(dim, degree):
+    P, W = fe.simplex_quadrature(dim, degree)
+    assert abs(W.sum() - 1 / math.factorial(dim)) < 1e-14
+    for e in itertools.product(range(degree + 1), repeat=dim):
+        if sum(e) > degree:
+            continue
+        exact = math.prod(math.factorial(k) for k in e) / math.factorial(dim + sum(e))
+        assert abs(np.sum(W * np.prod(P ** np.array(e), axis=1)) - exact) < 1e-14
+
+
+@pytest.mark.parametrize("fdim,degree", [(1, 2), (1, 4), (2, 2), (2, 4)])
+def test_symmetric_facet_rule(fdim, degree):
+    B, W = fe.symmetric_facet_rule(fdim, degree)
+    assert abs(W.sum() - 1) < 1e-15 and np.allclose(B.sum(axis=1), 1)
+    for e in itertools.product(range(degree + 1), repeat=fdim):   # monomials in the first fdim barycentrics
+        if sum(e) > degree:
+            continue
+        exact = math.factorial(fdim) * math.prod(math.factorial(k) for k in e) / math.factorial(fdim + sum(e))
+        assert abs(np.sum(W * np.prod(B[:, 1:] ** np.array(e), axis=1)) - exact) < 1e-14
+    perms, tab = fe.facet_permutation_table(fdim, B)
+    assert len(perms) == math.factorial(fdim + 1)
+    for p in range(len(perms)):
+        assert sorted(tab[p]) == list(range(B.shape[0]))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("degree", [1, 2])
+def test_basis_matches_vandermonde_oracle(dim, degree):
+    el = fe.LagrangeElement(dim, degree)
+    v, g = el.tabulate(el.nodes)
+    assert np.allclose(v, np.eye(el.n_ld), atol=1e-14)
+    rng = np.random.default_rng(0)
+    pts = rng.dirichlet(np.ones(dim + 1), 7)[:, 1:]
+    v, g = el.tabulate(pts)
+    nb = to.NodalBasis(dim, degree, el.nodes)
+    assert np.allclose(v, nb.values(pts), atol=1e-13)
+    assert np.allclose(g, nb.grads(pts), atol=1e-12)
+    assert np.allclose(v.sum(axis=1), 1) and np.allclose(g.sum(axis=2), 0, atol=1e-13)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_facet_topology(dim):
+    m = _mesh(dim)
+    t = fe.facet_topology(m)
+    nc = m.n_cells
+    for c in range(nc):
+        for f in range(dim + 1):
+            nb = t.neighbor[c, f]
+            if nb >= 0:
+                assert t.neighbor[nb, t.nb_facet[c, f]] == c and t.nb_facet[nb, t.nb_facet[c, f]] == f
+    geo = fe.cell_geometry(m)
+    area = fe.facet_measures(m, geo, t.bnd_cell, t.bnd_facet).sum()
+    if dim == 1:
+        assert len(t.bnd_cell) == 2
+    elif dim == 2:
+        assert abs(area - 2 * (5.0 + 2.5)) < 1e-12
+    else:
+        assert abs(area - 2 * (1.5 * 1.0 + 1.5 * 0.8 + 1.0 * 0.8)) < 1e-12
+    assert abs(geo.detJ.sum() / math.factorial(dim) - {1: 50.0, 2: 12.5, 3: 1.2}[dim]) < 1e-10
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_p2_lattice_numbering_equals_generic(dim):
+    m = _mesh(dim)
+    a = fe.ScalarSpace(m, "CG", 2)
+    lat, m.lattice = m.lattice, None
+    b = fe.ScalarSpace(m, "CG", 2)
+    m.lattice = lat
+    assert a.n_nodes == b.n_nodes
+    xa, xb = a.tabulate_dof_coordinates(), b.tabulate_dof_coordinates()
+    # same node set; the dofmaps agree up to the renumbering
+    ren = np.full(a.n_nodes, -1)
+    ren[a.dofmap.ravel()] = b.dofmap.ravel()
+    assert (ren >= 0).all() and np.allclose(xa, xb[ren])
+
+
+def _setup(dim, family, degree, n=None):
+    m = _mesh(dim, n)
+    space = fe.ScalarSpace(m, family, degree)
+    tabs = fe.operator_tables(dim, degree)
+    geo = fe.cell_geometry(m)
+    topo = fe.facet_topology(m)
+    orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, family, degree, MAIN_PARAMS, 0.1)
+    return m, space, tabs, geo, topo, orc
+
+
+CASES = [(1, "CG", 1), (1, "DG", 1), (1, "CG", 2), (1, "DG", 2), (2, "CG", 1), (2, "CG", 2), (2, "DG", 1),
+         (2, "DG", 2), (3, "CG", 1), (3, "CG", 2), (3, "DG", 1), (3, "DG", 2)]
+
+
+@pytest.mark.parametrize("dim,family,degree", CASES)
+def test_table_driven_operator_equals_assembled_oracle(dim, family, degree):
+    m, space, tabs, geo, topo, orc = _setup(dim, family, degree)
+    rng = np.random.default_rng(dim * 10 + degree)
+    T = 700 + 100 * rng.random(space.n_nodes)
+    Tp = T + rng.random(space.n_nodes)
+    x = rng.standard_normal(space.n_nodes)
+    J = orc.jacobian(T)
+    assert abs(J - J.T).max() < 1e-12 * abs(J).max()
+    y = kernel_mirror.jac_apply(space, tabs, geo, topo, MAIN_PARAMS, 0.1, x, T_lin=T)
+    yo = J @ x
+    assert np.max(np.abs(y - yo)) < 1e-11 * np.max(np.abs(yo))
+    r = kernel_mirror.jac_apply(space, tabs, geo, topo, MAIN_PARAMS, 0.1, T, residual=True, T_prev=Tp)
+    ro = orc.residual(T, Tp)
+    assert np.max(np.abs(r - ro)) < 1e-11 * np.max(np.abs(ro))
+
+
+@pytest.mark.parametrize("dim,family,degree", [(1, "DG", 1), (2, "CG", 2), (3, "DG", 1)])
+def test_oracle_jacobian_is_derivative_of_residual(dim, family, degree):
+    m, space, tabs, geo, topo, orc = _setup(dim, family, degree)
+    rng = np.random.default_rng(1)
+    T = 700 + 100 * rng.random(space.n_nodes)
+    Tp = T + 1.0
+    v = rng.standard_normal(space.n_nodes)
+    eps = 1e-4
+    fd = (orc.residual(T + eps * v, Tp) - orc.residual(T - eps * v, Tp)) / (2 * eps)
+    assert np.max(np.abs(fd - orc.jacobian(T) @ v)) < 1e-7 * np.max(np.abs(fd))
+
+
+def test_oracle_steady_state_and_newton():
+    """T == T_prev == T_ambient is a fixed point; from T_0 = 800 the Newton iteration converges in a few steps."""
+    m, space, tabs, geo, topo, orc = _setup(1, "DG", 1)
+    Ta = np.full(space.n_nodes, MAIN_PARAMS["T_ambient"])
+    assert np.max(np.abs(orc.residual(Ta, Ta))) < 1e-12
+    T0 = np.full(space.n_nodes, 800.0)
+    T, its, ok = orc.newton(T0, T0)
+    assert ok and 2 <= its <= 6
+    assert np.max(np.abs(orc.residual(T, T0))) < 1e-9
+    assert T.min() > 600 and T.max() < 800.01 and T[0] < 799.9   # surfaces cool first
+
+
+@pytest.mark.parametrize("dim,n", [(1, None), (2, (8, 4)), (3, (4, 4, 2))])
+def test_dg_operator_is_spd_on_the_benchmark_plates(dim, n):
+    """CG needs an SPD Jacobian (TVP:342); check the SIP-DG operator with the reference's penalty 5/h.
+
+    The reference's penalty (5.0 / CellDiameter, independent of degree and element shape, TVP:313-320) is
+    coercive on Kuhn tetrahedra only while the mass term dominates (dt*alpha/a^2 <~ 0.15 for cube edge a):
+    with a = 0.5 mm the Jacobian has negative eigenvalues.  The 3-D DG benchmark plate therefore uses
+    1 mm cubes (320 x 320 x 8 mm plate), see DESIGN.md."""
+    if dim == 3:
+        m = msh.box_mesh(*n, 4 * 1.0, 4 * 1.0, 2 * 1.0)
+    elif dim == 2:
+        m = msh.rectangle_mesh(*n, 8 * 50 / 408, 4 * 25 / 204)
+    else:
+        m = msh.graded_line_mesh()
+    space = fe.ScalarSpace(m, "DG", 1)
+    orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "DG", 1, MAIN_PARAMS, 0.1)
+    J = orc.jacobian(np.full(space.n_nodes, 800.0)).toarray()
+    ev = np.linalg.eigvalsh(0.5 * (J + J.T))
+    assert ev.min() > 0, f"indefinite: min eigenvalue {ev.min()}"

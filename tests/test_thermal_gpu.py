@@ -1,0 +1,106 @@
+"""GPU parity of hot path (B): matrix-free CUDA operator / PCG / Newton (through the C ABI) against the
+assembled scipy oracle.  Tolerances are written next to each assertion; the north_star bar is 1e-10."""
+import numpy as np
+import pytest
+import torch
+
+from fem_glass_tempering_b200 import fe
+from fem_glass_tempering_b200 import mesh as msh
+from fem_glass_tempering_b200.thermal_op import ThermalOperator
+from oracle import thermal_oracle as to
+from oracle.visco_oracle import MAIN_PARAMS
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(1, "CG", 1), (1, "DG", 1), (1, "CG", 2), (1, "DG", 2), (2, "CG", 1), (2, "CG", 2), (2, "DG", 1),
+         (2, "DG", 2), (3, "CG", 1), (3, "CG", 2), (3, "DG", 1), (3, "DG", 2)]
+
+
+def make_mesh(dim):
+    if dim == 1:
+        return msh.graded_line_mesh()
+    if dim == 2:
+        return msh.rectangle_mesh(9, 5, 9.0, 5.0)
+    return msh.box_mesh(5, 4, 3, 5.0, 4.0, 3.0)
+
+
+def setup(sg_ctx, dim, family, degree, dt=0.1, params=MAIN_PARAMS):
+    m = make_mesh(dim)
+    space = fe.ScalarSpace(m, family, degree)
+    op = ThermalOperator(sg_ctx, space, params, dt)
+    orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, family, degree, params, dt)
+    return m, space, op, orc
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0")
+
+
+@pytest.mark.parametrize("dim,family,degree", CASES)
+def test_operator_matches_assembled_oracle(sg_ctx, dim, family, degree):
+    m, space, op, orc = setup(sg_ctx, dim, family, degree)
+    rng = np.random.default_rng(dim * 10 + degree)
+    n = space.n_nodes
+    T = 700 + 100 * rng.random(n)
+    Tp = T + rng.random(n)
+    x = rng.standard_normal(n)
+    J = orc.jacobian(T)
+    out = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    y = op.jac_apply(dev(T), dev(x), out).cpu().numpy()
+    yo = J @ x
+    assert np.max(np.abs(y - yo)) <= 1e-12 * np.max(np.abs(yo))        # Jacobian apply: 1e-12 relative
+    r = op.residual(dev(T), dev(Tp), out).cpu().numpy()
+    ro = orc.residual(T, Tp)
+    assert np.max(np.abs(r - ro)) <= 1e-12 * np.max(np.abs(ro))        # residual: 1e-12 relative
+    dg = op.jac_diag(dev(T), out).cpu().numpy()
+    do = J.diagonal()
+    assert np.max(np.abs(dg - do)) <= 1e-12 * np.max(np.abs(do))       # Jacobi diagonal: 1e-12 relative
+
+
+@pytest.mark.parametrize("dim,family,degree", [(1, "DG", 1), (2, "CG", 2), (3, "DG", 1), (3, "CG", 2), (2, "DG", 2)])
+def test_pcg_solves_the_linear_system(sg_ctx, dim, family, degree):
+    import scipy.sparse.linalg as spla
+    m, space, op, orc = setup(sg_ctx, dim, family, degree)
+    n = space.n_nodes
+    rng = np.random.default_rng(3)
+    T = np.full(n, 800.0) - rng.random(n)
+    b = rng.standard_normal(n)
+    Td, bd, xd = dev(T), dev(b), torch.zeros(n, dtype=torch.float64, device="cuda:0")
+    op.prepare_preconditioner(Td)
+    its, res = op.pcg(Td, bd, xd, rtol=1e-13)
+    xo = spla.spsolve(orc.jacobian(T).tocsc(), b)
+    assert res <= 1e-13 and 1 <= its < 2000
+    assert np.max(np.abs(xd.cpu().numpy() - xo)) <= 1e-10 * np.max(np.abs(xo))   # solution: 1e-10 relative
+
+
+@pytest.mark.parametrize("dim,family,degree", [(1, "DG", 1), (1, "CG", 1), (2, "CG", 2), (3, "DG", 1), (3, "CG", 1)])
+def test_time_steps_match_oracle_newton(sg_ctx, dim, family, degree):
+    """Several implicit-Euler steps from T_0 = 800 K: temperature within 1e-10 relative of the oracle
+    (the oracle solves each Newton system directly)."""
+    m, space, op, orc = setup(sg_ctx, dim, family, degree)
+    n = space.n_nodes
+    T_o = np.full(n, 800.0)
+    T_d, Tp_d = dev(T_o), dev(T_o)
+    for step in range(4):
+        Tp_o = T_o.copy()
+        T_o, its_o, ok = orc.newton(T_o, Tp_o)
+        assert ok
+        st = op.timestep(T_d, Tp_d)
+        assert st.converged == 1 and st.newton_its <= its_o + 2
+        err = np.max(np.abs(T_d.cpu().numpy() - T_o)) / np.max(np.abs(T_o))
+        assert err <= 1e-10, f"step {step}: rel err {err}"
+        dT_o = T_o - Tp_o                                  # the increment drives the stress (H3): 1e-8 of its size
+        dT_d = T_d.cpu().numpy() - Tp_d.cpu().numpy()
+        assert np.max(np.abs(dT_d - dT_o)) <= 1e-8 * np.max(np.abs(dT_o))
+        Tp_d.copy_(T_d)
+
+
+def test_nonconvergence_is_reported(sg_ctx):
+    from fem_glass_tempering_b200 import _lib
+    m, space, op, orc = setup(sg_ctx, 2, "CG", 1)
+    n = space.n_nodes
+    T = dev(np.full(n, 800.0))
+    op.opts.newton_max_it = 1
+    with pytest.raises(_lib.SgError) as e:
+        op.timestep(T, T.clone())
+    assert e.value.code == _lib.SG_E_NOCONV          # TVP:390 assert(converged)
