@@ -60,7 +60,7 @@ def compare_step(prob, orc, tol_T, tol_inc, tol_sigma):
     assert np.isfinite(sig_g[good]).all() and np.isfinite(sig_o[good]).all()
     assert np.max(np.abs(sig_g[good] - sig_o[good])) <= tol_sigma * scale
     rest = sig_g[~good]
-    assert np.all(np.isnan(rest) | (np.abs(rest) <= 1e-6 * scale))
+    assert np.all(np.isnan(rest) | (np.abs(rest) <= 1e-9))   # |sigma| ~ sum(k) * alpha_s * |dT| < 3.2e-10 there
     return float(np.max(np.abs(sig_g[good] - sig_o[good])) / scale)
 
 
@@ -219,7 +219,8 @@ def test_minimal_materialisation_matches_full(sg_ctx):
     for step in range(3):
         a.solve_timestep(t=0.0)
         b.solve_timestep(t=0.0)
+    # the two runs differ only by the atomic summation order of the exterior-facet kernel in the thermal solve
     for k in ("sigma", "s_tilde_partial", "sigma_tilde_partial"):
-        assert_same(cpu(a.functions_next[k]), cpu(b.functions_next[k]), k)
+        assert rel_err(cpu(a.functions_next[k]), cpu(b.functions_next[k])) <= 1e-10, k
     with pytest.raises(RuntimeError):
         b.functions["ds_partial"].x.array
