@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — SurroGlas per-timestep hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the CPU restatement of the reference, timed on the host cores
+
+A "step" is ONE FULL TIMESTEP of ThermoViscoProblem.solve_timestep (TVP:367-381): the implicit-Euler heat solve
+(Newton + matrix-free Jacobi-PCG, hot path B), the fused viscoelastic update at every quadrature point (hot
+path A) and T_prev <- T_cur; file output is disabled.  Workload (config.workload): BASELINE configs[2], the
+3-D DG1 plate with radiative/convective Robin boundary, 320x320x8 hexahedra x 6 tetrahedra = 4 915 200 cells =
+19 660 800 quadrature points PER GPU (weak scaling: the plate grows along x with N; x-slab partition).
+configs[1] (~1 M points) is launch-latency bound on a B200 and configs[3] is the multi-GPU case, so configs[2]
+is the single-GPU configuration the metric is quoted on.
+
+Printed JSON (rank 0): metric = quadrature-point updates/s over all GPUs, plus timesteps/s, the e2e variant
+(host buffers: H2D of the step's temperature input, D2H of the five fields the reference writes every step,
+TVP:357-362), a roofline object for the dominant kernel (the DG Jacobian-apply cell kernel, timed live with
+CUDA events on its launch stream), the same for the fused viscoelastic kernel, and a CPU baseline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAIN_PARAMS = {  # main.py:29-55
+    "f": 0.0, "epsilon": 0.93, "sigma": 5.670e-8, "T_ambient": 600.0, "T_0": 800.0, "alpha": 1.0, "htc": 280.1,
+    "rho": 2500.0, "cp": 1433.0, "k": 1.0, "H": 627.8e3, "Tb": 869.0e0, "Rg": 8.314,
+    "alpha_solid": 9.10e-6, "alpha_liquid": 25.10e-6, "Tf_init": 873.0,
+}
+
+WORKLOADS = {
+    # name: (dim, cells per axis PER GPU, cell edge [mm], fe_config)
+    "C3_plate3d_DG1_robin_19.7M_qp": (3, (320, 320, 8), 1.0, {"T": {"element": "DG", "degree": 1},
+                                                              "sigma": {"element": "DG", "degree": 1}}),
+    "C2_plate2d_CG2_1M_qp": (2, (408, 204), 50.0 / 408, {"T": {"element": "CG", "degree": 2},
+                                                         "sigma": {"element": "CG", "degree": 2}}),
+    "C4_plate3d_CG2": (3, (96, 768, 6), 1.0, {"T": {"element": "CG", "degree": 2},
+                                              "sigma": {"element": "CG", "degree": 2}}),
+    "small_plate3d_DG1": (3, (48, 48, 8), 1.0, {"T": {"element": "DG", "degree": 1},
+                                                "sigma": {"element": "DG", "degree": 1}}),
+}
+DEFAULT_WORKLOAD = "C3_plate3d_DG1_robin_19.7M_qp"
+DT = 0.1
+METRIC, UNIT = "quadrature-point updates/s (full timestep: heat solve + viscoelastic update)", "QP-updates/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([s.strip() for s in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = float(s[1])
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_timestep_rate(workload_name: str, steps: int, warmup: int):
+    """Times the CPU restatement of the same timestep (oracle/: assembled scipy Jacobian + Jacobi-CG Newton for
+    the heat equation, OpenMP C for the 17-pass viscoelastic chain) on a BOUNDED sample of the workload: the
+    same plate cross-section cut to 48 columns (110 592 tetrahedra, 442 368 points for C3).  The reference's own
+    `mpiexec -np N python3 main.py` cannot run here (dolfinx/PETSc/MPI not installed), so this is a port."""
+    import numpy as np
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from fem_glass_tempering_b200 import fe
+    from fem_glass_tempering_b200 import mesh as msh
+    from oracle import thermal_oracle as to
+    from oracle import visco_oracle as vo
+
+    dim, n, a, cfg = WORKLOADS[workload_name]
+    if dim == 3:
+        n = (min(n[0], 48), min(n[1], 48), n[2])
+    lengths = tuple(k * a for k in n)
+    mesh = msh.plate_mesh(dim, n, lengths)
+    space = fe.ScalarSpace(mesh, cfg["T"]["element"], cfg["T"]["degree"])
+    t0 = time.time()
+    orc = to.ThermalOracle(mesh.x, mesh.cells, space.dofmap, space.element.nodes, space.family, space.degree,
+                           MAIN_PARAMS, DT)
+    setup_s = time.time() - t0
+    nn, d = space.n_nodes, dim
+    p = vo.ViscoParams(dim=d, dt=DT)
+    st = vo.new_state(p, nn, MAIN_PARAMS["T_0"])
+    omp = True
+    try:
+        vo._lib(True)
+    except OSError:
+        omp = False
+
+    def newton(T0, Tp):
+        T, r0 = T0.copy(), None
+        for it in range(1, 51):
+            b = orc.residual(T, Tp)
+            J = orc.jacobian(T)
+            dinv = 1.0 / J.diagonal()
+            dx, info = spla.cg(J, b, rtol=1e-8, atol=0.0, M=sp.diags(dinv), maxiter=10000)
+            T = T - dx
+            r = np.linalg.norm(dx)
+            if it == 1:
+                r0 = r
+                if r0 == 0.0:
+                    return T
+            elif r / r0 < 1e-12 or r < 1e-10:
+                return T
+        raise RuntimeError("CPU Newton did not converge")
+
+    def step():
+        st["T_cur"][:] = newton(st["T_cur"], st["T_prev"])
+        vo.step_passes(p, st, omp=omp)
+        st["T_prev"][:] = st["T_cur"]
+
+    for _ in range(warmup):
+        step()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt_s = (time.time() - t0) / steps
+    qp = mesh.n_cells * space.n_ld
+    cores = os.cpu_count() if omp else 1
+    sample = (f"{'x'.join(map(str, n))} cells x {6 if dim == 3 else 2} simplices = {qp} points, {steps} steps; heat solve: "
+              f"assembled scipy.sparse Jacobian + Jacobi-CG Newton (1 thread); viscoelastic chain: 17-pass C port, "
+              f"OpenMP on {cores} threads; set-up {setup_s:.1f}s not timed")
+    return qp / dt_s, dt_s, cores, sample, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    value, dt_s, cores, sample, n = cpu_timestep_rate(args.workload, steps, warmup)
+    dim, _, a, cfg = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "fe_config": cfg, "dt": DT,
+                       "note": "CPU port of the reference path on a bounded sample of the workload; throughput is per "
+                               "point so it is comparable with the GPU arm"},
+            "timesteps_per_s": 1.0 / dt_s,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from fem_glass_tempering_b200 import ThermoViscoProblem, _lib, distributed
+    from fem_glass_tempering_b200 import mesh as msh
+
+    rank, world, local = distributed.init_process_group()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = distributed.make_context(rank, world, local)
+
+    dim, n_per_gpu, a, cfg = WORKLOADS[args.workload]
+    n = (n_per_gpu[0] * world,) + tuple(n_per_gpu[1:])
+    lengths = tuple(k * a for k in n)
+    t_setup = time.time()
+    if world == 1:
+        mesh, part = msh.plate_mesh(dim, n, lengths), None
+        el = cfg["T"]
+        n_ld = {1: dim + 1, 2: (dim + 1) * (dim + 2) // 2}[el["degree"]]
+        qp_local = mesh.n_cells * n_ld
+    else:
+        mesh, part, info = distributed.slab_partition(dim, n, lengths, cfg["T"]["element"], cfg["T"]["degree"], rank, world)
+        qp_local = info["owned_cell_points"]
+    prob = ThermoViscoProblem(mesh_path="", time=(0.0, 50.0), dt=DT, config=cfg, model_parameters=MAIN_PARAMS,
+                              mesh=mesh, ctx=ctx, partition=part, materialize="minimal", verbose=False)
+    prob.setup(dirichlet_bc=False)
+    t_setup = time.time() - t_setup
+    op = prob._thermal_op
+    L = _lib.lib()
+    nT = prob.functionSpaces["T"].n_nodes
+    nS = prob.functionSpaces["sigma"].n_nodes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step():
+        prob.t += prob.dt
+        prob.solve_timestep(t=prob.t)
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    import ctypes as C
+    _lib.check(L.sg_thermal_profile(op.handle, 1, 8192))
+    launches0 = L.sg_launch_count()
+    lin_its = newton_its = 0
+    visco_ev = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            prob.t += prob.dt
+            prob._solve_T()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            prob._solve_viscoelastic()
+            a1.record()
+            visco_ev.append((a0, a1))
+            prob._update_values(current=prob.functions_current["T"], previous=prob.functions_previous["T"])
+            lin_its += prob.solver.last_stats.lin_its
+            newton_its += prob.solver.last_stats.newton_its
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = L.sg_launch_count() - launches0
+    n_apply, ms_apply = C.c_int64(0), C.c_double(0.0)
+    _lib.check(L.sg_thermal_profile_read(op.handle, C.byref(n_apply), C.byref(ms_apply)))
+    _lib.check(L.sg_thermal_profile(op.handle, 0, 0))
+    ms_visco = sum(a.elapsed_time(b) for a, b in visco_ev) / len(visco_ev)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    q = torch.tensor([float(qp_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(q, op=dist.ReduceOp.SUM)
+    ms_total, qp_total = float(t.item()), float(q.item())
+    value = qp_total * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end-to-end timing through the public API with host buffers ----------------
+    fields_out = [prob.functions_current["T"], prob.functions["phi"], prob.functions_current["Tf"],
+                  prob.functions["xi"], prob.functions_next["sigma"]]                    # TVP:249-273, 357-362
+    host_out = [torch.empty(f.x.array.shape, dtype=torch.float64, pin_memory=True) for f in fields_out]
+    host_in = torch.empty(nT, dtype=torch.float64, pin_memory=True)
+    host_in.copy_(prob.functions_previous["T"].x.array)
+    h2d = host_in.numel() * 8
+    d2h = sum(h.numel() * 8 for h in host_out)
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        prob.functions_previous["T"].x.array.copy_(host_in, non_blocking=True)          # H2D: the step's input
+        one_step()
+        for h, f in zip(host_out, fields_out):
+            h.copy_(f.x.array, non_blocking=True)                                       # D2H: what _write_output consumes
+        host_in.copy_(host_out[0])                                                      # next step's T_prev (host side)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = qp_total * e2e_steps / (float(t.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+    peak, peak_how = measured_peak()
+    apply_bytes = op.apply_bytes()
+    apply_ms = ms_apply.value / max(1, n_apply.value)
+    apply_gbs = apply_bytes / (apply_ms * 1e-3) / 1e9 if n_apply.value else None
+    visco_bytes = prob.material_model.plan.bytes_per_node(prob._visco_tensors()) * nS
+    visco_gbs = visco_bytes / (ms_visco * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "cells_per_gpu": int(mesh.n_cells if world == 1 else qp_local // (dim + 1)),
+                   "qp_per_gpu": int(qp_local), "qp_total": int(qp_total), "fe_config": cfg, "dt": DT, "prony_terms": 6,
+                   "plate_mm": list(lengths), "partition": f"x-slabs over {world} GPU(s)",
+                   "cache": "state per GPU (>17 GB) is far larger than the 126 MB L2; no L2 flush needed",
+                   "newton_its_per_step": newton_its / args.steps, "pcg_its_per_step": lin_its / args.steps,
+                   "setup_s": round(t_setup, 1)},
+        "timesteps_per_s": args.steps / (ms_total * 1e-3),
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "what": "ThermoViscoProblem.solve_timestep + pinned-host T_prev in, T/phi/Tf/xi/sigma out"},
+        "roofline": {"kernel": "thermal cell_kernel<APPLY> (matrix-free Jacobian apply incl. DG interior facets)",
+                     "bound": "hbm", "achieved": apply_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": (apply_gbs / peak) if apply_gbs else None, "traffic": None, "peak_source": peak_how,
+                     "algorithmic_bytes_per_launch": int(apply_bytes), "launches_timed": int(n_apply.value),
+                     "avg_launch_ms": apply_ms, "share_of_step": ms_apply.value / ms_total},
+        "roofline_visco": {"kernel": "visco_fast_kernel (fused viscoelastic update)", "bound": "hbm",
+                           "achieved": visco_gbs, "peak": peak, "unit": "GB/s", "frac": visco_gbs / peak,
+                           "algorithmic_bytes_per_launch": int(visco_bytes), "avg_launch_ms": ms_visco,
+                           "share_of_step": ms_visco * args.steps / ms_total, "frac_of_8TBs_spec": visco_gbs / 8000.0},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt_s, cores, sample, _ = cpu_timestep_rate(args.workload, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         L = C.CDLL(LIB_PATH)
         L.sg_last_error.restype = C.c_char_p
         L.sg_visco_bytes_per_node.restype = C.c_int64
+        L.sg_launch_count.restype = C.c_int64
         L.sg_visco_update.argtypes = [C.c_void_p, C.c_int64, C.POINTER(ViscoFieldsC), C.c_uint32, C.c_void_p]
         L.sg_visco_update_scalar.argtypes = [C.c_void_p, C.c_int64, C.POINTER(ViscoFieldsC), C.c_uint32, C.c_void_p]
         L.sg_visco_update_tensor.argtypes = [C.c_void_p, C.c_int64, C.POINTER(ViscoFieldsC), C.POINTER(ViscoGatherC),

@@ -38,6 +38,8 @@ def bind(L) -> None:
     L.sg_thermal_residual.argtypes = [vp, vp, vp, vp, vp]
     L.sg_thermal_jac_apply.argtypes = [vp, vp, vp, vp, vp]
     L.sg_thermal_jac_diag.argtypes = [vp, vp, vp, vp]
+    L.sg_thermal_profile.argtypes = [vp, C.c_int32, C.c_int32]
+    L.sg_thermal_profile_read.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.sg_thermal_apply_bytes.argtypes = [vp]
     L.sg_thermal_apply_bytes.restype = C.c_int64
     L.sg_halo_plan_create.argtypes = [vp, C.c_int32, C.POINTER(HaloSegmentC), C.POINTER(vp)]

@@ -5,7 +5,12 @@
 #include "sg_common.cuh"
 #include "sg_nccl.h"
 
+#include <atomic>
+
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void sg_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void sg_set_error(const char *fmt, ...) {
     va_list ap;
@@ -48,6 +53,8 @@ const SgNccl *sg_nccl() {
 extern "C" {
 
 int sg_version(void) { return 100; }
+
+int64_t sg_launch_count(void) { return (int64_t)g_launches.load(); }
 
 const char *sg_last_error(void) { return g_err; }
 

@@ -274,6 +274,7 @@ int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, dou
     int rc;
     k_pcg_init<<<g, VB, 0, st>>>(n, lo, hi, b, s->dinv, x, s->r, s->p, s->red, S);
     SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
     if ((rc = allreduce(s, S, 2, st))) return rc;
     if ((rc = read_scalars(s, 0, 2, st))) return rc;
     const double rr0 = s->S_host[1];
@@ -290,12 +291,15 @@ int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, dou
         if ((rc = sg_thermal_jac_apply(s->op, T_lin, s->p, s->Ap, st))) return rc;
         k_dot<<<go, VB, 0, st>>>(lo, hi, s->p, s->Ap, s->red, S + 4);
         SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
         if ((rc = allreduce(s, S + 4, 1, st))) return rc;
         k_update_xr<<<g, VB, 0, st>>>(n, lo, hi, s->p, s->Ap, s->dinv, x, s->r, s->red, Scur, S + 4, Snext);
         SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
         if ((rc = allreduce(s, Snext, 2, st))) return rc;
         k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, Scur, Snext);
         SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
         ++it;
         if ((rc = read_scalars(s, 2 * (it & 1), 2, st))) return rc;
         rr = s->S_host[2 * (it & 1) + 1];
@@ -329,6 +333,7 @@ int sg_thermal_timestep(sg_thermal_solver *s, double *T, const double *T_prev, c
         if ((rc = sg_thermal_jac_diag(s->op, T, s->dinv, st))) return rc;               // J(T) diagonal
         k_invert<<<g, VB, 0, st>>>(n, s->dinv);
         SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
         int lin_it = 0;
         rc = sg_pcg_solve(s, T, s->b, s->dx, o->lin_rtol, o->lin_atol, o->lin_max_it, &lin_it, &lin_res, st);
         lin_total += lin_it;

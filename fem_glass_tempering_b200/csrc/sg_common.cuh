@@ -20,6 +20,9 @@ struct sg_ctx {
 
 void sg_set_error(const char *fmt, ...);
 
+// number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
+void sg_count_launch(int n = 1);
+
 // internal accessors of sg_thermal_op (defined in thermal.cu) for the solver in pcg.cu
 int64_t sg_op_ndofs(const sg_thermal_op *op);
 void sg_op_ranges(const sg_thermal_op *op, int64_t *own_lo, int64_t *own_hi, sg_ctx **ctx);

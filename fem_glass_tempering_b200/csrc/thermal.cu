@@ -337,6 +337,9 @@ struct sg_thermal_op {
     void *tab_host;      // Tab<D,P,DG> instance
     size_t tab_bytes;
     double *btab_dev, *bw_dev;
+    // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
+    int prof_on, prof_n, prof_cap;
+    cudaEvent_t *prof_ev;
     int (*launch)(const sg_thermal_op *, int mode, const double *T, const double *x, const double *xprev, double *y,
                   cudaStream_t st);
 };
@@ -353,7 +356,15 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
     const unsigned gc = (unsigned)((ncell + TB - 1) / TB), gb = (unsigned)((dv.n_bf + TB - 1) / TB);
     if (!DG) SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
     if (ncell > 0) {
+        const bool prof = mode == MODE_APPLY && op->prof_on && op->prof_n < op->prof_cap;
+        sg_thermal_op *mop = const_cast<sg_thermal_op *>(op);
+        if (prof) SG_CHECK_CUDA(cudaEventRecord(op->prof_ev[2 * op->prof_n], st));
         if (mode == MODE_APPLY) cell_kernel<D, P, DG, MODE_APPLY><<<gc, TB, 0, st>>>(tab, dv, x, nullptr, y);
+        if (prof) {
+            SG_CHECK_CUDA(cudaEventRecord(op->prof_ev[2 * op->prof_n + 1], st));
+            mop->prof_n++;
+        }
+        sg_count_launch();
         if (mode == MODE_RESID) cell_kernel<D, P, DG, MODE_RESID><<<gc, TB, 0, st>>>(tab, dv, x, xprev, y);
         if (mode == MODE_DIAG) cell_kernel<D, P, DG, MODE_DIAG><<<gc, TB, 0, st>>>(tab, dv, nullptr, nullptr, y);
         SG_CHECK_CUDA(cudaGetLastError());
@@ -363,6 +374,7 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         if (mode == MODE_RESID) bfacet_kernel<D, P, DG, MODE_RESID><<<gb, TB, 0, st>>>(dv, x, nullptr, y);
         if (mode == MODE_DIAG) bfacet_kernel<D, P, DG, MODE_DIAG><<<gb, TB, 0, st>>>(dv, Tlin, nullptr, y);
         SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
     }
     return SG_OK;
 }
@@ -431,6 +443,8 @@ int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *d, sg_thermal_op **
     op->d = *d;
     op->tab_host = nullptr;
     op->btab_dev = op->bw_dev = nullptr;
+    op->prof_on = op->prof_n = op->prof_cap = 0;
+    op->prof_ev = nullptr;
     int rc = SG_E_INVALID;
     if (d->dim == 1) rc = build_tab_d<1>(op);
     if (d->dim == 2) rc = build_tab_d<2>(op);
@@ -487,6 +501,8 @@ int sg_thermal_op_destroy(sg_thermal_op *op) {
     if (!op) return SG_OK;
     if (op->btab_dev) cudaFree(op->btab_dev);
     if (op->bw_dev) cudaFree(op->bw_dev);
+    for (int i = 0; i < 2 * op->prof_cap; ++i) cudaEventDestroy(op->prof_ev[i]);
+    delete[] op->prof_ev;
     ::operator delete(op->tab_host);
     delete op;
     return SG_OK;
@@ -505,6 +521,34 @@ int sg_thermal_jac_apply(sg_thermal_op *op, const double *T_lin, const double *x
 int sg_thermal_jac_diag(sg_thermal_op *op, const double *T_lin, double *diag, void *stream) {
     SG_REQUIRE(op && T_lin && diag, "sg_thermal_jac_diag: NULL argument");
     return op->launch(op, MODE_DIAG, T_lin, nullptr, nullptr, diag, (cudaStream_t)stream);
+}
+
+int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity) {
+    SG_REQUIRE(op, "sg_thermal_profile: NULL operator");
+    if (enable && op->prof_cap < capacity) {
+        for (int i = 0; i < 2 * op->prof_cap; ++i) cudaEventDestroy(op->prof_ev[i]);
+        delete[] op->prof_ev;
+        op->prof_ev = new cudaEvent_t[2 * capacity];
+        for (int i = 0; i < 2 * capacity; ++i) SG_CHECK_CUDA(cudaEventCreate(&op->prof_ev[i]));
+        op->prof_cap = capacity;
+    }
+    op->prof_on = enable;
+    op->prof_n = 0;
+    return SG_OK;
+}
+
+int sg_thermal_profile_read(sg_thermal_op *op, int64_t *n_launches, double *ms_total) {
+    SG_REQUIRE(op && n_launches && ms_total, "sg_thermal_profile_read: NULL argument");
+    double tot = 0.0;
+    for (int i = 0; i < op->prof_n; ++i) {
+        float ms = 0.f;
+        SG_CHECK_CUDA(cudaEventSynchronize(op->prof_ev[2 * i + 1]));
+        SG_CHECK_CUDA(cudaEventElapsedTime(&ms, op->prof_ev[2 * i], op->prof_ev[2 * i + 1]));
+        tot += ms;
+    }
+    *n_launches = op->prof_n;
+    *ms_total = tot;
+    return SG_OK;
 }
 
 int64_t sg_thermal_apply_bytes(const sg_thermal_op *op) {

@@ -467,6 +467,7 @@ int launch_visco_d(const sg_visco_plan *plan, int64_t n, const sg_visco_fields &
     }
     kern<<<(unsigned)grid, VTHREADS, smem, st>>>(plan->k, f, G, (long)n, phases, bulk_ok);
     SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
     return SG_OK;
 }
 
@@ -596,6 +597,7 @@ int sg_visco_update(sg_visco_plan *plan, int64_t n_nodes, const sg_visco_fields 
         const int grid = (int)(n_tiles < plan->fast_grid ? n_tiles : plan->fast_grid);
         plan->fast<<<grid, 32, plan->fast_smem, st>>>(plan->k, *f, (long)n_tiles);
         SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
         done = n_tiles * WT;
         if (done == n_nodes) return SG_OK;
     }

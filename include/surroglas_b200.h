@@ -38,6 +38,8 @@ enum {
 };
 
 int sg_version(void);
+/* kernels launched by this library in this process so far (bench.py: gpu_launches) */
+int64_t sg_launch_count(void);
 const char *sg_last_error(void);
 
 /* ------------------------------------------------------------------ context */
@@ -176,6 +178,10 @@ int sg_thermal_residual(sg_thermal_op *op, const double *T, const double *T_prev
 int sg_thermal_jac_apply(sg_thermal_op *op, const double *T_lin, const double *x, double *y, void *stream);
 /* diag J(T_lin) (Jacobi preconditioner; the reference uses GAMG, TVP:344). */
 int sg_thermal_jac_diag(sg_thermal_op *op, const double *T_lin, double *diag, void *stream);
+/* Optional timing of the Jacobian-apply cell kernel with CUDA event pairs on its launch stream
+ * (measurement harness only; at most `capacity` launches are recorded after each enable). */
+int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity);
+int sg_thermal_profile_read(sg_thermal_op *op, int64_t *n_launches, double *ms_total);
 /* Algorithmic HBM bytes of one sg_thermal_jac_apply (roofline numerator). */
 int64_t sg_thermal_apply_bytes(const sg_thermal_op *op);
 

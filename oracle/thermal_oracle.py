@@ -146,29 +146,42 @@ class ThermalOracle:
         self.int = [tuple(sorted(v)) for v in table.values() if len(v) == 2]   # '+' = lower cell index
         assert all(len(v) <= 2 for v in table.values())
 
-    def _facet_frame(self, c, f):
-        """vertices of facet f of cell c, its measure and the unit normal pointing out of c."""
+    def _facet_frames(self, c, f):
+        """Vectorised over facets: vertices [nf, d, d], measures [nf], unit normals pointing out of cell c [nf, d]."""
         d = self.d
-        fv = self.x[self.cells[c][list(self.loc_facets[f])]]               # [d, d]
-        opp = self.x[self.cells[c][f]]
+        c, f = np.asarray(c, dtype=np.int64), np.asarray(f, dtype=np.int64)
+        loc = np.array(self.loc_facets, dtype=np.int64).reshape(d + 1, d)
+        fv = self.x[self.cells[c[:, None], loc[f]]]                        # [nf, d, d]
+        opp = self.x[self.cells[c, f]]                                     # [nf, d]
         if d == 1:
-            n = np.array([1.0 if fv[0, 0] > opp[0] else -1.0])
-            return fv, 1.0, n
+            n = np.where(fv[:, 0, :] > opp, 1.0, -1.0)
+            return fv, np.ones(len(c)), n
         if d == 2:
-            t = fv[1] - fv[0]
-            meas = np.linalg.norm(t)
-            n = np.array([t[1], -t[0]]) / meas
+            t = fv[:, 1] - fv[:, 0]
+            meas = np.linalg.norm(t, axis=1)
+            n = np.stack([t[:, 1], -t[:, 0]], axis=1) / meas[:, None]
         else:
-            cr = np.cross(fv[1] - fv[0], fv[2] - fv[0])
-            meas = 0.5 * np.linalg.norm(cr)
-            n = cr / np.linalg.norm(cr)
-        if np.dot(n, fv[0] - opp) < 0:
-            n = -n
+            cr = np.cross(fv[:, 1] - fv[:, 0], fv[:, 2] - fv[:, 0])
+            nrm = np.linalg.norm(cr, axis=1)
+            meas = 0.5 * nrm
+            n = cr / nrm[:, None]
+        flip = np.einsum("nd,nd->n", n, fv[:, 0] - opp) < 0
+        n[flip] *= -1.0
         return fv, meas, n
 
     def _ref_coords(self, c, xp):
-        """reference coordinates in cell c of physical points xp [npts, d] (inverse affine map)."""
-        return (xp - self.x[self.cells[c][0]]) @ self.Jinv[c].T
+        """reference coordinates in cells c [nf] of physical points xp [nf, nq, d] (inverse affine map)."""
+        return np.einsum("nqc,nac->nqa", xp - self.x[self.cells[c, 0]][:, None, :], self.Jinv[c])
+
+    def _tab(self, c, xq, grads=False):
+        """basis values [nf, nq, nl] (and physical gradients [nf, nq, d, nl]) at physical points xq of cells c."""
+        nf, nq, d = xq.shape
+        ref = self._ref_coords(c, xq).reshape(nf * nq, d)
+        v = self.basis.values(ref).reshape(nf, nq, -1)
+        if not grads:
+            return v
+        g = self.basis.grads(ref).reshape(nf, nq, d, -1)
+        return v, np.einsum("nab,nqai->nqbi", self.Jinv[c], g)
 
     # -- cell integrals -------------------------------------------------------------------------
     def _assemble_cells(self, mass):
@@ -197,33 +210,33 @@ class ThermalOracle:
     def _assemble_sip(self):
         d, nl = self.d, self.basis.n
         a_plus = float(self.p["alpha"])
+        if not self.int:
+            return sp.csr_matrix((self.n_dof, self.n_dof))
         FP, FW = simplex_rule(d - 1, 2 * self.degree)
         FW = FW / FW.sum()
         bary = np.concatenate([1 - FP.sum(axis=1, keepdims=True), FP], axis=1) if d > 1 else np.ones((1, 1))
+        pairs = np.array([[cp, fp, cm, fm] for (cp, fp), (cm, fm) in self.int], dtype=np.int64)
         rows, cols, vals = [], [], []
-        for (cp, fp), (cm, fm) in self.int:
-            fv, meas, n_p = self._facet_frame(cp, fp)
+        for lo in range(0, len(pairs), 20000):                              # chunks bound the temporary memory
+            cp, fp, cm = pairs[lo:lo + 20000, 0], pairs[lo:lo + 20000, 1], pairs[lo:lo + 20000, 2]
+            fv, meas, n_p = self._facet_frames(cp, fp)
             n_m = -n_p
-            xq = bary @ fv
-            out = np.zeros((2 * nl, 2 * nl))
-            vp, vm = self.basis.values(self._ref_coords(cp, xq)), self.basis.values(self._ref_coords(cm, xq))
-            gp = np.einsum("ab,qai->qbi", self.Jinv[cp], self.basis.grads(self._ref_coords(cp, xq)))
-            gm = np.einsum("ab,qai->qbi", self.Jinv[cm], self.basis.grads(self._ref_coords(cm, xq)))
-            # jump(w, n) = w+ n+ + w- n-  as a [q, d, 2nl] array over the stacked (+,-) basis
-            jump = np.concatenate([vp[:, None, :] * n_p[None, :, None], vm[:, None, :] * n_m[None, :, None]], axis=2)
-            avg_g = 0.5 * np.concatenate([gp, gm], axis=2)
+            xq = np.einsum("qk,nkd->nqd", bary, fv)
+            vp, gp = self._tab(cp, xq, grads=True)
+            vm, gm = self._tab(cm, xq, grads=True)
+            # jump(w, n) = w+ n+ + w- n-  as [nf, q, d, 2nl] over the stacked (+,-) basis
+            jump = np.concatenate([vp[:, :, None, :] * n_p[:, None, :, None], vm[:, :, None, :] * n_m[:, None, :, None]], axis=3)
+            avg_g = 0.5 * np.concatenate([gp, gm], axis=3)
             pen = self.PENALTY / self.h[cp]
-            wq = FW * meas
-            out += pen * np.einsum("q,qbi,qbj->ij", wq, jump, jump)
-            out -= np.einsum("q,qbi,qbj->ij", wq, avg_g, jump)
-            out -= np.einsum("q,qbi,qbj->ij", wq, jump, avg_g)
+            wq = FW[None, :] * meas[:, None]
+            out = pen[:, None, None] * np.einsum("nq,nqbi,nqbj->nij", wq, jump, jump)
+            out -= np.einsum("nq,nqbi,nqbj->nij", wq, avg_g, jump)
+            out -= np.einsum("nq,nqbi,nqbj->nij", wq, jump, avg_g)
             out *= self.dt * a_plus
-            dofs = np.concatenate([self.dofmap[cp], self.dofmap[cm]])
-            rows.append(np.repeat(dofs, 2 * nl))
-            cols.append(np.tile(dofs, 2 * nl))
+            dofs = np.concatenate([self.dofmap[cp], self.dofmap[cm]], axis=1)      # [nf, 2nl]
+            rows.append(np.repeat(dofs[:, :, None], 2 * nl, axis=2).ravel())
+            cols.append(np.repeat(dofs[:, None, :], 2 * nl, axis=1).ravel())
             vals.append(out.ravel())
-        if not rows:
-            return sp.csr_matrix((self.n_dof, self.n_dof))
         return sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                              shape=(self.n_dof, self.n_dof)).tocsr()
 
@@ -231,29 +244,27 @@ class ThermalOracle:
     def _boundary(self, T, want_matrix):
         d, nl, p = self.d, self.basis.n, self.p
         se, htc, Ta = float(p["sigma"]) * float(p["epsilon"]), float(p["htc"]), float(p["T_ambient"])
-        FP, FW = simplex_rule(d - 1, self.qdeg)
-        FW = FW / FW.sum()
-        bary = np.concatenate([1 - FP.sum(axis=1, keepdims=True), FP], axis=1) if d > 1 else np.ones((1, 1))
+        if not hasattr(self, "_bcache"):
+            FP, FW = simplex_rule(d - 1, self.qdeg)
+            FW = FW / FW.sum()
+            bary = np.concatenate([1 - FP.sum(axis=1, keepdims=True), FP], axis=1) if d > 1 else np.ones((1, 1))
+            c = np.array([e[0] for e in self.ext], dtype=np.int64)
+            f = np.array([e[1] for e in self.ext], dtype=np.int64)
+            fv, meas, _ = self._facet_frames(c, f)
+            v = self._tab(c, np.einsum("qk,nkd->nqd", bary, fv))                   # [nf, q, nl]
+            self._bcache = (c, v, FW[None, :] * meas[:, None], self.dofmap[c])
+        c, v, wq, dofs = self._bcache
+        Tq = np.einsum("nqj,nj->nq", v, T[dofs])
+        flux = 0.001 * se * (Tq ** 4 - Ta ** 4) + 0.001 * htc * (Tq - Ta)
         vec = np.zeros(self.n_dof)
-        rows, cols, vals = [], [], []
-        for c, f in self.ext:
-            fv, meas, _ = self._facet_frame(c, f)
-            v = self.basis.values(self._ref_coords(c, bary @ fv))          # [q, nl]
-            dofs = self.dofmap[c]
-            Tq = v @ T[dofs]
-            wq = FW * meas
-            flux = 0.001 * se * (Tq ** 4 - Ta ** 4) + 0.001 * htc * (Tq - Ta)
-            np.add.at(vec, dofs, self.dt * (v.T @ (wq * flux)))
-            if want_matrix:
-                coef = 0.001 * (4.0 * se * Tq ** 3 + htc)
-                out = self.dt * np.einsum("q,qi,qj->ij", wq * coef, v, v)
-                rows.append(np.repeat(dofs, nl))
-                cols.append(np.tile(dofs, nl))
-                vals.append(out.ravel())
+        np.add.at(vec, dofs.ravel(), (self.dt * np.einsum("nqi,nq->ni", v, wq * flux)).ravel())
         B = None
         if want_matrix:
-            B = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
-                              shape=(self.n_dof, self.n_dof)).tocsr() if rows else sp.csr_matrix((self.n_dof,) * 2)
+            coef = 0.001 * (4.0 * se * Tq ** 3 + htc)
+            out = self.dt * np.einsum("nq,nqi,nqj->nij", wq * coef, v, v)
+            rows = np.repeat(dofs[:, :, None], nl, axis=2).ravel()
+            cols = np.repeat(dofs[:, None, :], nl, axis=1).ravel()
+            B = sp.coo_matrix((out.ravel(), (rows, cols)), shape=(self.n_dof, self.n_dof)).tocsr()
         return vec, B
 
     # -- residual / Jacobian / Newton --------------------------------------------------------------
