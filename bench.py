@@ -293,6 +293,7 @@ def run_gpu(args):
         one_step()
         for h, f in zip(host_out, fields_out):
             h.copy_(f.x.array, non_blocking=True)                                       # D2H: what _write_output consumes
+        torch.cuda.current_stream().synchronize()                                       # the host consumes the outputs
         host_in.copy_(host_out[0])                                                      # next step's T_prev (host side)
     e1.record()
     barrier()

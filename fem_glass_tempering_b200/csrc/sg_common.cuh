@@ -24,8 +24,14 @@ void sg_set_error(const char *fmt, ...);
 void sg_count_launch(int n = 1);
 
 // internal accessors of sg_thermal_op (defined in thermal.cu) for the solver in pcg.cu
-int64_t sg_op_ndofs(const sg_thermal_op *op);
-void sg_op_ranges(const sg_thermal_op *op, int64_t *own_lo, int64_t *own_hi, sg_ctx **ctx);
+struct SgOpInfo {
+    sg_ctx *ctx;
+    int dim, family, n_ld;
+    int64_t n_dofs, own_lo, own_hi, n_cells, cell_lo, cell_hi;
+    const double *detJ;        // device, [n_cells]
+    const double *mass_inv;    // host, [n_ld * n_ld]: inverse of the reference mass matrix
+};
+void sg_op_info(const sg_thermal_op *op, SgOpInfo *info);
 
 #define SG_CHECK_CUDA(expr)                                                                  \
     do {                                                                                     \

@@ -15,6 +15,8 @@
 // atomics, no colouring; the neighbour's dofs/geometry come through L2).  CG: gather through an SoA
 // dofmap, scatter with native fp64 atomics (RED.ADD.F64).  Exterior (Robin + radiation) facets are a
 // small separate kernel.
+#include <math.h>
+
 #include "sg_common.cuh"
 
 namespace {
@@ -338,6 +340,7 @@ struct sg_thermal_op {
     size_t tab_bytes;
     double *btab_dev, *bw_dev;
     // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
+    double mass_inv[100];
     int prof_on, prof_n, prof_cap;
     cudaEvent_t *prof_ev;
     int (*launch)(const sg_thermal_op *, int mode, const double *T, const double *x, const double *xprev, double *y,
@@ -416,12 +419,48 @@ int build_tab_d(sg_thermal_op *op) {
 
 }  // namespace
 
-int64_t sg_op_ndofs(const sg_thermal_op *op) { return op->d.n_dofs; }
+void sg_op_info(const sg_thermal_op *op, SgOpInfo *o) {
+    o->ctx = op->ctx;
+    o->dim = op->d.dim;
+    o->family = op->d.family;
+    o->n_ld = op->d.n_ld;
+    o->n_dofs = op->d.n_dofs;
+    o->own_lo = op->d.own_lo;
+    o->own_hi = op->d.own_hi;
+    o->n_cells = op->d.n_cells;
+    o->cell_lo = op->d.cell_lo;
+    o->cell_hi = op->d.cell_hi;
+    o->detJ = op->d.geom + (int64_t)op->d.dim * op->d.dim * op->d.n_cells;
+    o->mass_inv = op->mass_inv;
+}
 
-void sg_op_ranges(const sg_thermal_op *op, int64_t *own_lo, int64_t *own_hi, sg_ctx **ctx) {
-    *own_lo = op->d.own_lo;
-    *own_hi = op->d.own_hi;
-    *ctx = op->ctx;
+// Gauss-Jordan inverse of the (SPD, n <= 10) reference mass matrix
+static void invert_small(const double *a, int n, double *inv) {
+    double m[10][20];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            m[i][j] = a[i * n + j];
+            m[i][n + j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        for (int i = k + 1; i < n; ++i)
+            if (fabs(m[i][k]) > fabs(m[piv][k])) piv = i;
+        for (int j = 0; j < 2 * n; ++j) {
+            const double tmp = m[k][j];
+            m[k][j] = m[piv][j];
+            m[piv][j] = tmp;
+        }
+        const double d = m[k][k];
+        for (int j = 0; j < 2 * n; ++j) m[k][j] /= d;
+        for (int i = 0; i < n; ++i)
+            if (i != k) {
+                const double f = m[i][k];
+                for (int j = 0; j < 2 * n; ++j) m[i][j] -= f * m[k][j];
+            }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) inv[i * n + j] = m[i][n + j];
 }
 
 extern "C" {
@@ -453,6 +492,7 @@ int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *d, sg_thermal_op **
         delete op;
         return rc;
     }
+    invert_small(d->mass, d->n_ld, op->mass_inv);
     OpDev &dv = op->dev;
     memset(&dv, 0, sizeof(dv));
     dv.n_cells = d->n_cells;

@@ -45,7 +45,7 @@ class NewtonSolverGPU:
         self.rtol, self.atol, self.max_it = 1e-12, 1e-10, 50
         self.report = False
         self.krylov_solver = _KrylovStub()
-        self.linear_rtol = 1e-8
+        self.linear_rtol = 1e-10   # PCG residual target, relative to the first Newton residual of the step
         self.last_stats = None
 
     def solve(self, u: Function):
@@ -280,7 +280,7 @@ class ThermoViscoProblem:
 
     def _solve_T(self) -> None:
         _, converged = self.solver.solve(self.functions_current["T"])                             # TVP:389
-        assert (converged)                                                                        # TVP:390
+        assert (converged), "Newton solver did not converge: " + _lib.lib().sg_last_error().decode()   # TVP:390
 
     def _run_phases(self, phases: int) -> None:
         plan, t = self.material_model.plan, self._visco_tensors()

@@ -111,7 +111,9 @@ def test_other_configs(sg_ctx, dim, config, n):
     for step in range(8):
         prob.solve_timestep(t=0.0)
         orc.step()
-        compare_step(prob, orc, 1e-11, 1e-9, 1e-9)
+        # stress bound: the reference's lambda*(1 - taylor)/xi cancels to eps_mach/|xi/lambda| ~ 1e-16/3e-7 per term
+        # (SURVEY §7 H2), so a 1e-12 relative difference in xi re-rolls that rounding noise: 5e-9, not solver error
+        compare_step(prob, orc, 1e-11, 1e-9, 5e-9)
         orc.end_step()
 
 
