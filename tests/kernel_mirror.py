@@ -17,8 +17,10 @@ def _dlam(d):
     return g
 
 
-def jac_apply(space, tabs, geo, topo, params, dt, x, T_lin=None, xm=None, residual=False, T_prev=None):
-    """y = J(T_lin) x   (residual=False)   or   y = F(x; T_prev)   (residual=True)."""
+def jac_apply(space, tabs, geo, topo, params, dt, x, T_lin=None, xm=None, residual=False, T_prev=None,
+              cell_lo=0, cell_hi=None):
+    """y = J(T_lin) x   (residual=False)   or   y = F(x; T_prev)   (residual=True).
+    Only cells [cell_lo, cell_hi) are integrated (a rank's share of a partitioned mesh)."""
     mesh, d, nl = space.mesh, space.mesh.dim, space.n_ld
     a = float(params["alpha"])
     dm = space.dofmap
@@ -67,11 +69,16 @@ def jac_apply(space, tabs, geo, topo, params, dt, x, T_lin=None, xm=None, residu
                                         - 0.5 * dphiK * jump[:, None]
                                         - tabs.fq_val[f, q][None, :] * (0.5 * (dnK + dnN))[:, None])
                 np.add.at(yk, act, contrib)
+    cell_hi = mesh.n_cells if cell_hi is None else cell_hi
+    yk[:cell_lo] = 0.0
+    yk[cell_hi:] = 0.0
     np.add.at(y, dm.ravel(), yk.ravel())
     # exterior facets
     se, htc, Ta = float(params["sigma"]) * float(params["epsilon"]), float(params["htc"]), float(params["T_ambient"])
     area = fe.facet_measures(mesh, geo, topo.bnd_cell, topo.bnd_facet)
     for c, f, ar in zip(topo.bnd_cell, topo.bnd_facet, area):
+        if c < cell_lo or c >= cell_hi:
+            continue
         v = tabs.bq_val[f]                                                     # [nq, nl]
         dofs = dm[c]
         if residual:
