@@ -308,6 +308,13 @@ def run_gpu(args):
             dist.barrier()
         return
     peak, peak_how = measured_peak()
+    cls = op.class_info()
+    fam = cfg["T"]["element"]
+    if cls["active"]:
+        kname = (f"thermal {'dg' if fam == 'DG' else 'cg'}_class_apply (matrix-free Jacobian apply from local-matrix class tables "
+                 f"in shared memory, fused x.Ax reduction; {cls['self']} cell + {cls['facet']} facet classes)")
+    else:
+        kname = "thermal cell_kernel<APPLY> (matrix-free Jacobian apply from per-cell geometry)"
     apply_bytes = op.apply_bytes()
     apply_ms = ms_apply.value / max(1, n_apply.value)
     apply_gbs = apply_bytes / (apply_ms * 1e-3) / 1e9 if n_apply.value else None
@@ -322,13 +329,13 @@ def run_gpu(args):
                    "plate_mm": list(lengths), "partition": f"x-slabs over {world} GPU(s)",
                    "cache": "state per GPU (>17 GB) is far larger than the 126 MB L2; no L2 flush needed",
                    "newton_its_per_step": newton_its / args.steps, "pcg_its_per_step": lin_its / args.steps,
-                   "setup_s": round(t_setup, 1)},
+                   "setup_s": round(t_setup, 1), "local_matrix_classes": cls},
         "timesteps_per_s": args.steps / (ms_total * 1e-3),
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "what": "ThermoViscoProblem.solve_timestep + pinned-host T_prev in, T/phi/Tf/xi/sigma out"},
-        "roofline": {"kernel": "thermal cell_kernel<APPLY> (matrix-free Jacobian apply incl. DG interior facets)",
+        "roofline": {"kernel": kname,
                      "bound": "hbm", "achieved": apply_gbs, "peak": peak, "unit": "GB/s",
                      "frac": (apply_gbs / peak) if apply_gbs else None, "traffic": None, "peak_source": peak_how,
                      "algorithmic_bytes_per_launch": int(apply_bytes), "launches_timed": int(n_apply.value),

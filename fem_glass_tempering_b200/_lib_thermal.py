@@ -13,7 +13,8 @@ class ThermalDescC(C.Structure):
                 ("fq_w", C.c_void_p), ("fq_val", C.c_void_p), ("fq_grad", C.c_void_p), ("fq_perm", C.c_void_p),
                 ("bq_w", C.c_void_p), ("bq_val", C.c_void_p),
                 ("dt", C.c_double), ("alpha", C.c_double), ("f", C.c_double), ("sigma", C.c_double),
-                ("epsilon", C.c_double), ("htc", C.c_double), ("T_ambient", C.c_double), ("penalty", C.c_double)]
+                ("epsilon", C.c_double), ("htc", C.c_double), ("T_ambient", C.c_double), ("penalty", C.c_double),
+                ("own_cell_lo", C.c_int64), ("own_cell_hi", C.c_int64), ("flags", C.c_int32)]
 
 
 class HaloSegmentC(C.Structure):
@@ -38,6 +39,7 @@ def bind(L) -> None:
     L.sg_thermal_residual.argtypes = [vp, vp, vp, vp, vp]
     L.sg_thermal_jac_apply.argtypes = [vp, vp, vp, vp, vp]
     L.sg_thermal_jac_diag.argtypes = [vp, vp, vp, vp]
+    L.sg_thermal_class_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.sg_thermal_profile.argtypes = [vp, C.c_int32, C.c_int32]
     L.sg_thermal_profile_read.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.sg_thermal_apply_bytes.argtypes = [vp]

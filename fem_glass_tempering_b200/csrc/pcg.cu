@@ -17,50 +17,37 @@
 namespace {
 
 constexpr int VB = 256;          // threads per block of the vector kernels
-constexpr int MAX_BLOCKS = 1184; // 8 * 148 resident blocks; grid-stride beyond that
+constexpr int BATCH = 8;         // PCG iterations enqueued between two host checks of the convergence flag
 
-// Scalars: S[0..1] / S[2..3] = {r.z, r.r} ping-pong by iteration parity, S[4] = p.Ap, S[5] = |dx|^2
-struct Red {
-    double *partials;   // [MAX_BLOCKS * 2]
-    unsigned *counter;
+// Device scalars S (doubles): S[0..1] / S[2..3] = {r.z, r.r} ping-pong by iteration parity,
+// S[4] + S[5] = p.Ap (cells + exterior facets), S[6] = |dx|^2.
+// Device control block: the kernels themselves detect convergence, later launches of the same solve
+// return immediately, and the host looks at the flag once per BATCH iterations.
+struct PcgCtrl {
+    int done;      // 0 running, 1 converged, 2 non-finite residual
+    int iters;     // iterations completed when `done` was set
+    double rr;     // |r|^2 at that point
 };
 
-// Sum NR per-thread values over the grid; the LAST block adds the per-block partials in block order and
-// stores the totals in out[0..NR).  Must be called by every thread of every block.
+using Red = SgRed;
+
 template <int NR>
 __device__ __forceinline__ void grid_reduce(double (&v)[NR], const Red red, double *out) {
-    __shared__ double scratch[32];
-    __shared__ bool is_last;
-#pragma unroll
-    for (int k = 0; k < NR; ++k) {
-        const double s = sg_block_sum(v[k], scratch);
-        if (threadIdx.x == 0) red.partials[blockIdx.x * NR + k] = s;
-    }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned done = atomicAdd(red.counter, 1u);
-        is_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-#pragma unroll
-        for (int k = 0; k < NR; ++k) {
-            double s = 0.0;
-            for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += red.partials[b * NR + k];
-            s = sg_block_sum(s, scratch);
-            if (threadIdx.x == 0) out[k] = s;
-        }
-        if (threadIdx.x == 0) *red.counter = 0u;
-    }
+    sg_grid_reduce<NR>(v, red, out);
 }
 
 __device__ __forceinline__ bool owned(long i, long lo, long hi) { return i >= lo && i < hi; }
 
-// x = 0, r = b, p = z = dinv*r ; S[0] = r.z, S[1] = r.r
+// x = 0, r = b, p = z = dinv*r ; S[0] = r.z, S[1] = r.r ; resets the control block
 __global__ void __launch_bounds__(VB) k_pcg_init(long n, long lo, long hi, const double *__restrict__ b,
                                                  const double *__restrict__ dinv, double *__restrict__ x,
-                                                 double *__restrict__ r, double *__restrict__ p, Red red, double *S) {
+                                                 double *__restrict__ r, double *__restrict__ p, Red red, double *S,
+                                                 PcgCtrl *ctrl) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctrl->done = 0;
+        ctrl->iters = 0;
+        ctrl->rr = 0.0;
+    }
     double acc[2] = {0.0, 0.0};
     for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
         const double ri = b[i], zi = dinv[i] * ri;
@@ -75,19 +62,14 @@ __global__ void __launch_bounds__(VB) k_pcg_init(long n, long lo, long hi, const
     grid_reduce<2>(acc, red, S);
 }
 
-__global__ void __launch_bounds__(VB) k_dot(long lo, long hi, const double *__restrict__ a, const double *__restrict__ b,
-                                            Red red, double *out) {
-    double acc[1] = {0.0};
-    for (long i = lo + (long)blockIdx.x * VB + threadIdx.x; i < hi; i += (long)gridDim.x * VB) acc[0] += a[i] * b[i];
-    grid_reduce<1>(acc, red, out);
-}
-
 // alpha = rz/pAp ; x += alpha p ; r -= alpha Ap ; Snext = {r.(dinv r), r.r}
 __global__ void __launch_bounds__(VB) k_update_xr(long n, long lo, long hi, const double *__restrict__ p,
                                                   const double *__restrict__ Ap, const double *__restrict__ dinv,
                                                   double *__restrict__ x, double *__restrict__ r, Red red,
-                                                  const double *Scur, const double *SpAp, double *Snext) {
-    const double alpha = Scur[0] / SpAp[0];
+                                                  const double *Scur, const double *SpAp, double *Snext,
+                                                  const PcgCtrl *ctrl) {
+    if (ctrl->done) return;
+    const double alpha = Scur[0] / (SpAp[0] + SpAp[1]);
     double acc[2] = {0.0, 0.0};
     for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
         x[i] += alpha * p[i];
@@ -101,12 +83,27 @@ __global__ void __launch_bounds__(VB) k_update_xr(long n, long lo, long hi, cons
     grid_reduce<2>(acc, red, Snext);
 }
 
-// beta = rz_new/rz ; p = dinv r + beta p
+// Convergence test of iteration `it` (0-based), by one thread, on the (all-reduced) new residual norm.
+__device__ __forceinline__ void pcg_check(PcgCtrl *ctrl, const double *Snext, double tol2, int it) {
+    const double rr = Snext[1];
+    if (!(rr > tol2) || !isfinite(rr)) {
+        ctrl->done = isfinite(rr) ? 1 : 2;
+        ctrl->iters = it + 1;
+        ctrl->rr = rr;
+    }
+}
+
+// beta = rz_new/rz ; p = dinv r + beta p ; flags convergence for the launches that follow
 __global__ void __launch_bounds__(VB) k_update_p(long n, const double *__restrict__ r, const double *__restrict__ dinv,
-                                                 double *__restrict__ p, const double *Scur, const double *Snext) {
+                                                 double *__restrict__ p, const double *Scur, const double *Snext,
+                                                 PcgCtrl *ctrl, double tol2, int it) {
+    if (ctrl->done) return;
     const double beta = Snext[0] / Scur[0];
     for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB)
         p[i] = dinv[i] * r[i] + beta * p[i];
+    // every block has read `done` before block 0 can change it?  No ordering is needed: a block that
+    // sees done != 0 set by THIS kernel merely skips a p update nobody will use.
+    if (blockIdx.x == 0 && threadIdx.x == 0) pcg_check(ctrl, Snext, tol2, it);
 }
 
 __global__ void __launch_bounds__(VB) k_invert(long n, double *__restrict__ d) {
@@ -128,7 +125,8 @@ __global__ void __launch_bounds__(VB) k_newton_update(long n, long lo, long hi, 
 // ---------------------------------------------------------------------------------------------
 // DG: the mass matrix is block diagonal, M_K = |detJ_K| * Mhat, so z_K = Mhat^-1 r_K / |detJ_K| is an
 // exact, set-up-free preconditioner for the mass-dominated Jacobian (about 1.7x fewer CG iterations
-// than point Jacobi).  One thread per cell; the NLD dofs of a cell are contiguous.
+// than point Jacobi).  One thread per cell; the NLD dofs of a cell are contiguous (128-bit accesses
+// when NLD is even).
 template <int NLD>
 struct MassInv {
     double a[NLD * NLD];  // Mhat^-1
@@ -146,22 +144,50 @@ __device__ __forceinline__ void mass_solve(const MassInv<NLD> &mi, double inv_de
 }
 
 template <int NLD>
+__device__ __forceinline__ void ld_row(const double *__restrict__ p, double (&v)[NLD]) {
+    if constexpr (NLD % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < NLD / 2; ++i) {
+            const double2 t = reinterpret_cast<const double2 *>(p)[i];
+            v[2 * i] = t.x;
+            v[2 * i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) v[i] = p[i];
+    }
+}
+template <int NLD>
+__device__ __forceinline__ void st_row(double *__restrict__ p, const double (&v)[NLD]) {
+    if constexpr (NLD % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < NLD / 2; ++i) reinterpret_cast<double2 *>(p)[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) p[i] = v[i];
+    }
+}
+
+template <int NLD>
 __global__ void __launch_bounds__(VB) k_pcg_init_blk(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
                                                      const double *__restrict__ detJ, const double *__restrict__ b,
                                                      double *__restrict__ x, double *__restrict__ r,
-                                                     double *__restrict__ p, Red red, double *S) {
+                                                     double *__restrict__ p, Red red, double *S, PcgCtrl *ctrl) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctrl->done = 0;
+        ctrl->iters = 0;
+        ctrl->rr = 0.0;
+    }
     double acc[2] = {0.0, 0.0};
     for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
-        double rk[NLD], zk[NLD];
-#pragma unroll
-        for (int i = 0; i < NLD; ++i) rk[i] = b[c * NLD + i];
+        double rk[NLD], zk[NLD], zero[NLD];
+        ld_row<NLD>(b + c * NLD, rk);
         mass_solve<NLD>(mi, 1.0 / detJ[c], rk, zk);
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-            x[c * NLD + i] = 0.0;
-            r[c * NLD + i] = rk[i];
-            p[c * NLD + i] = zk[i];
-        }
+        for (int i = 0; i < NLD; ++i) zero[i] = 0.0;
+        st_row<NLD>(x + c * NLD, zero);
+        st_row<NLD>(r + c * NLD, rk);
+        st_row<NLD>(p + c * NLD, zk);
         if (c >= clo && c < chi) {
 #pragma unroll
             for (int i = 0; i < NLD; ++i) {
@@ -178,19 +204,26 @@ __global__ void __launch_bounds__(VB) k_update_xr_blk(const __grid_constant__ Ma
                                                       const double *__restrict__ detJ, const double *__restrict__ p,
                                                       const double *__restrict__ Ap, double *__restrict__ x,
                                                       double *__restrict__ r, Red red, const double *Scur,
-                                                      const double *SpAp, double *Snext) {
-    const double alpha = Scur[0] / SpAp[0];
+                                                      const double *SpAp, double *Snext, const PcgCtrl *ctrl) {
+    if (ctrl->done) return;
+    const double alpha = Scur[0] / (SpAp[0] + SpAp[1]);
     double acc[2] = {0.0, 0.0};
     for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
-        double rk[NLD], zk[NLD];
+        double pk[NLD], ak[NLD], xk[NLD], rk[NLD], zk[NLD];
+        ld_row<NLD>(p + c * NLD, pk);
+        ld_row<NLD>(Ap + c * NLD, ak);
+        ld_row<NLD>(x + c * NLD, xk);
+        ld_row<NLD>(r + c * NLD, rk);
+        const double idet = 1.0 / detJ[c];
 #pragma unroll
         for (int i = 0; i < NLD; ++i) {
-            x[c * NLD + i] += alpha * p[c * NLD + i];
-            rk[i] = r[c * NLD + i] - alpha * Ap[c * NLD + i];
-            r[c * NLD + i] = rk[i];
+            xk[i] += alpha * pk[i];
+            rk[i] -= alpha * ak[i];
         }
+        st_row<NLD>(x + c * NLD, xk);
+        st_row<NLD>(r + c * NLD, rk);
         if (c >= clo && c < chi) {
-            mass_solve<NLD>(mi, 1.0 / detJ[c], rk, zk);
+            mass_solve<NLD>(mi, idet, rk, zk);
 #pragma unroll
             for (int i = 0; i < NLD; ++i) {
                 acc[0] += rk[i] * zk[i];
@@ -204,22 +237,26 @@ __global__ void __launch_bounds__(VB) k_update_xr_blk(const __grid_constant__ Ma
 template <int NLD>
 __global__ void __launch_bounds__(VB) k_update_p_blk(const __grid_constant__ MassInv<NLD> mi, long n_cells,
                                                      const double *__restrict__ detJ, const double *__restrict__ r,
-                                                     double *__restrict__ p, const double *Scur, const double *Snext) {
+                                                     double *__restrict__ p, const double *Scur, const double *Snext,
+                                                     PcgCtrl *ctrl, double tol2, int it) {
+    if (ctrl->done) return;
     const double beta = Snext[0] / Scur[0];
     for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
-        double rk[NLD], zk[NLD];
-#pragma unroll
-        for (int i = 0; i < NLD; ++i) rk[i] = r[c * NLD + i];
+        double rk[NLD], zk[NLD], pk[NLD];
+        ld_row<NLD>(r + c * NLD, rk);
+        ld_row<NLD>(p + c * NLD, pk);
         mass_solve<NLD>(mi, 1.0 / detJ[c], rk, zk);
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) p[c * NLD + i] = zk[i] + beta * p[c * NLD + i];
+        for (int i = 0; i < NLD; ++i) pk[i] = zk[i] + beta * pk[i];
+        st_row<NLD>(p + c * NLD, pk);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) pcg_check(ctrl, Snext, tol2, it);
 }
 
 inline unsigned vgrid(long n) {
     long g = (n + VB - 1) / VB;
     if (g < 1) g = 1;
-    return (unsigned)(g > MAX_BLOCKS ? MAX_BLOCKS : g);
+    return (unsigned)(g > SG_MAX_BLOCKS ? SG_MAX_BLOCKS : g);
 }
 
 }  // namespace
@@ -239,6 +276,7 @@ struct sg_thermal_solver {
     Red red;
     double *S;        // device scalars [8]
     double *S_host;   // pinned mirror
+    PcgCtrl *ctrl, *ctrl_host;            // device control block + pinned mirror
     // DG element-mass preconditioner
     int blk_nld;          // 0 = point Jacobi (CG), else dofs per cell
     long n_cells, clo, chi;
@@ -262,29 +300,32 @@ int read_scalars(sg_thermal_solver *s, int first, int count, cudaStream_t st) {
 }
 
 template <int NLD>
-int blk_init(sg_thermal_solver *s, const double *b, double *x, cudaStream_t st) {
+MassInv<NLD> mass_inv_of(const sg_thermal_solver *s) {
     MassInv<NLD> mi;
     for (int i = 0; i < NLD * NLD; ++i) mi.a[i] = s->mass_inv[i];
-    k_pcg_init_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mi, s->n_cells, s->clo, s->chi, s->detJ, b, x, s->r, s->p, s->red, s->S);
+    return mi;
+}
+
+template <int NLD>
+int blk_init(sg_thermal_solver *s, const double *b, double *x, cudaStream_t st) {
+    k_pcg_init_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, b, x, s->r,
+                                                         s->p, s->red, s->S, s->ctrl);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;
 }
 template <int NLD>
 int blk_update_xr(sg_thermal_solver *s, double *x, const double *Scur, double *Snext, cudaStream_t st) {
-    MassInv<NLD> mi;
-    for (int i = 0; i < NLD * NLD; ++i) mi.a[i] = s->mass_inv[i];
-    k_update_xr_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mi, s->n_cells, s->clo, s->chi, s->detJ, s->p, s->Ap, x, s->r, s->red,
-                                                          Scur, s->S + 4, Snext);
+    k_update_xr_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, s->p, s->Ap,
+                                                          x, s->r, s->red, Scur, s->S + 4, Snext, s->ctrl);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;
 }
 template <int NLD>
-int blk_update_p(sg_thermal_solver *s, const double *Scur, const double *Snext, cudaStream_t st) {
-    MassInv<NLD> mi;
-    for (int i = 0; i < NLD * NLD; ++i) mi.a[i] = s->mass_inv[i];
-    k_update_p_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mi, s->n_cells, s->detJ, s->r, s->p, Scur, Snext);
+int blk_update_p(sg_thermal_solver *s, const double *Scur, const double *Snext, double tol2, int it, cudaStream_t st) {
+    k_update_p_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->detJ, s->r, s->p, Scur, Snext,
+                                                         s->ctrl, tol2, it);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;
@@ -384,12 +425,16 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     s->red.counter = nullptr;
     s->S = nullptr;
     s->S_host = nullptr;
-    cudaError_t e = cudaMalloc(&s->red.partials, sizeof(double) * MAX_BLOCKS * 2);
+    s->ctrl = s->ctrl_host = nullptr;
+    cudaError_t e = cudaMalloc(&s->red.partials, sizeof(double) * (SG_MAX_BLOCKS * 2 + 2));
     if (e == cudaSuccess) e = cudaMalloc(&s->red.counter, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(s->red.counter, 0, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&s->S, sizeof(double) * 8);
     if (e == cudaSuccess) e = cudaMemset(s->S, 0, sizeof(double) * 8);
     if (e == cudaSuccess) e = cudaMallocHost(&s->S_host, sizeof(double) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->ctrl, sizeof(PcgCtrl));
+    if (e == cudaSuccess) e = cudaMemset(s->ctrl, 0, sizeof(PcgCtrl));
+    if (e == cudaSuccess) e = cudaMallocHost(&s->ctrl_host, sizeof(PcgCtrl));
     if (e != cudaSuccess) {
         sg_set_error("sg_thermal_solver_create: %s", cudaGetErrorString(e));
         sg_thermal_solver_destroy(s);
@@ -405,6 +450,8 @@ int sg_thermal_solver_destroy(sg_thermal_solver *s) {
     if (s->red.counter) cudaFree(s->red.counter);
     if (s->S) cudaFree(s->S);
     if (s->S_host) cudaFreeHost(s->S_host);
+    if (s->ctrl) cudaFree(s->ctrl);
+    if (s->ctrl_host) cudaFreeHost(s->ctrl_host);
     delete s;
     return SG_OK;
 }
@@ -414,14 +461,14 @@ int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, dou
     SG_REQUIRE(s && T_lin && b && x, "sg_pcg_solve: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     const long n = s->n, lo = s->lo, hi = s->hi;
-    const unsigned g = vgrid(n), go = vgrid(hi - lo);
+    const unsigned g = vgrid(n);
     double *S = s->S;
     int rc;
     if (s->blk_nld) {
         SG_BLK_DISPATCH(blk_init, s, b, x, st);
         if (rc) return rc;
     } else {
-        k_pcg_init<<<g, VB, 0, st>>>(n, lo, hi, b, s->dinv, x, s->r, s->p, s->red, S);
+        k_pcg_init<<<g, VB, 0, st>>>(n, lo, hi, b, s->dinv, x, s->r, s->p, s->red, S, s->ctrl);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
     }
@@ -430,48 +477,53 @@ int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, dou
     const double rr0 = s->S_host[1];
     s->last_rhs_norm = sqrt(rr0 > 0.0 ? rr0 : 0.0);
     const double tol2 = fmax(rtol * rtol * rr0, atol * atol);
-    int it = 0;
-    double rr = rr0;
     if (!(rr0 >= 0.0) || !isfinite(rr0)) {
         sg_set_error("sg_pcg_solve: right-hand side is not finite");
         return SG_E_NOCONV;
     }
-    while (rr > tol2 && it < max_it) {
-        double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
-        if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
-        if ((rc = sg_thermal_jac_apply(s->op, T_lin, s->p, s->Ap, st))) return rc;
-        k_dot<<<go, VB, 0, st>>>(lo, hi, s->p, s->Ap, s->red, S + 4);
-        SG_CHECK_CUDA(cudaGetLastError());
-        sg_count_launch();
-        if ((rc = allreduce(s, S + 4, 1, st))) return rc;
-        if (s->blk_nld) {
-            SG_BLK_DISPATCH(blk_update_xr, s, x, Scur, Snext, st);
-            if (rc) return rc;
-        } else {
-            k_update_xr<<<g, VB, 0, st>>>(n, lo, hi, s->p, s->Ap, s->dinv, x, s->r, s->red, Scur, S + 4, Snext);
-            SG_CHECK_CUDA(cudaGetLastError());
-            sg_count_launch();
+    int it = 0, done = rr0 > tol2 ? 0 : 1;
+    double rr = rr0;
+    // Iterations are enqueued BATCH at a time without host synchronisation: the kernels test convergence
+    // themselves (pcg_check) and the launches after the converged iteration return immediately.
+    while (!done && it < max_it) {
+        const int nb = (max_it - it < BATCH) ? max_it - it : BATCH;
+        for (int k = 0; k < nb; ++k, ++it) {
+            double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
+            if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
+            if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, &s->ctrl->done, st))) return rc;
+            if ((rc = allreduce(s, S + 4, 2, st))) return rc;
+            if (s->blk_nld) {
+                SG_BLK_DISPATCH(blk_update_xr, s, x, Scur, Snext, st);
+                if (rc) return rc;
+            } else {
+                k_update_xr<<<g, VB, 0, st>>>(n, lo, hi, s->p, s->Ap, s->dinv, x, s->r, s->red, Scur, S + 4, Snext, s->ctrl);
+                SG_CHECK_CUDA(cudaGetLastError());
+                sg_count_launch();
+            }
+            if ((rc = allreduce(s, Snext, 2, st))) return rc;
+            if (s->blk_nld) {
+                SG_BLK_DISPATCH(blk_update_p, s, Scur, Snext, tol2, it, st);
+                if (rc) return rc;
+            } else {
+                k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, Scur, Snext, s->ctrl, tol2, it);
+                SG_CHECK_CUDA(cudaGetLastError());
+                sg_count_launch();
+            }
         }
-        if ((rc = allreduce(s, Snext, 2, st))) return rc;
-        if (s->blk_nld) {
-            SG_BLK_DISPATCH(blk_update_p, s, Scur, Snext, st);
-            if (rc) return rc;
-        } else {
-            k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, Scur, Snext);
-            SG_CHECK_CUDA(cudaGetLastError());
-            sg_count_launch();
-        }
-        ++it;
-        if ((rc = read_scalars(s, 2 * (it & 1), 2, st))) return rc;
-        rr = s->S_host[2 * (it & 1) + 1];
-        if (!isfinite(rr)) {
-            sg_set_error("sg_pcg_solve: residual became non-finite at iteration %d (operator not SPD?)", it);
-            return SG_E_NOCONV;
-        }
+        SG_CHECK_CUDA(cudaMemcpyAsync(s->ctrl_host, s->ctrl, sizeof(PcgCtrl), cudaMemcpyDeviceToHost, st));
+        SG_CHECK_CUDA(cudaMemcpyAsync(s->S_host + 2 * (it & 1), S + 2 * (it & 1), sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        SG_CHECK_CUDA(cudaStreamSynchronize(st));
+        done = s->ctrl_host->done;
+        rr = done ? s->ctrl_host->rr : s->S_host[2 * (it & 1) + 1];
+        if (done) it = s->ctrl_host->iters;
     }
     if (iters) *iters = it;
     if (rel_res) *rel_res = rr0 > 0.0 ? sqrt(rr / rr0) : 0.0;
-    if (rr > tol2) {
+    if (done == 2 || !isfinite(rr)) {
+        sg_set_error("sg_pcg_solve: residual became non-finite at iteration %d (operator not SPD?)", it);
+        return SG_E_NOCONV;
+    }
+    if (!done) {
         sg_set_error("sg_pcg_solve: no convergence in %d iterations (relative residual %.3e)", it,
                      rr0 > 0 ? sqrt(rr / rr0) : 0.0);
         return SG_E_NOCONV;
@@ -505,11 +557,12 @@ int sg_thermal_timestep(sg_thermal_solver *s, double *T, const double *T_prev, c
         if (it == 1) lin_target = fmax(o->lin_atol, o->lin_rtol * s->last_rhs_norm);
         lin_total += lin_it;
         if (rc) return rc;
-        k_newton_update<<<g, VB, 0, st>>>(n, s->lo, s->hi, T, s->dx, s->red, s->S + 5);  // T <- T - dx
+        k_newton_update<<<g, VB, 0, st>>>(n, s->lo, s->hi, T, s->dx, s->red, s->S + 6);  // T <- T - dx
         SG_CHECK_CUDA(cudaGetLastError());
-        if ((rc = allreduce(s, s->S + 5, 1, st))) return rc;
-        if ((rc = read_scalars(s, 5, 1, st))) return rc;
-        r = sqrt(s->S_host[5]);
+        sg_count_launch();
+        if ((rc = allreduce(s, s->S + 6, 1, st))) return rc;
+        if ((rc = read_scalars(s, 6, 1, st))) return rc;
+        r = sqrt(s->S_host[6]);
         // dolfinx NewtonSolver, convergence_criterion = "incremental": iteration 1 only records r0
         if (it == 1) {
             r0 = r;

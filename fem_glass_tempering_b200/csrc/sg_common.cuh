@@ -33,6 +33,22 @@ struct SgOpInfo {
 };
 void sg_op_info(const sg_thermal_op *op, SgOpInfo *info);
 
+// Grid-wide deterministic reduction scratch: per-block partials + a completion counter (see sg_grid_reduce).
+constexpr int SG_MAX_BLOCKS = 1184;  // 8 * 148 resident blocks; kernels that reduce are grid-stride beyond that
+struct SgRed {
+    double *partials;   // [SG_MAX_BLOCKS * 2]
+    unsigned *counter;  // zero between kernels
+};
+
+// y = J(T_lin) x fused with the owned-dof dot product: dot2[0] + dot2[1] = sum over owned dofs of x*y
+// (cells + exterior facets).  When *skip != 0 (device flag, may be NULL) every kernel returns at once.
+int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
+                         const int *skip, cudaStream_t st);
+
+// classify.cu: equivalence classes of 64-bit keys.  cls_out[i] = class of keys[i] in [0, *n_cls),
+// rep_out[k] = index of one member of class k; both are cudaMalloc'ed here and freed by the caller.
+int sg_classify_u64(const uint64_t *keys_dev, int64_t n, int32_t **cls_out, int32_t *n_cls, int32_t **rep_out);
+
 #define SG_CHECK_CUDA(expr)                                                                  \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \
@@ -115,7 +131,7 @@ __device__ __forceinline__ double sg_warp_sum(double v) {
     return v;
 }
 
-// Block-wide sum, result valid in thread 0.  `scratch` holds >= 32 doubles.
+// Block-wide sum, result valid in thread 0 (warp 0).  `scratch` holds >= 32 doubles.
 __device__ __forceinline__ double sg_block_sum(double v, double *scratch) {
     v = sg_warp_sum(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -126,4 +142,35 @@ __device__ __forceinline__ double sg_block_sum(double v, double *scratch) {
     if (warp == 0) v = sg_warp_sum(v);
     __syncthreads();
     return v;
+}
+
+// Sum NR per-thread values over the grid; the LAST block to finish adds the per-block partials in block
+// order (deterministic) and stores the totals in out[0..NR).  Must be reached by every thread of every
+// block; gridDim.x <= SG_MAX_BLOCKS.
+template <int NR>
+__device__ __forceinline__ void sg_grid_reduce(double (&v)[NR], const SgRed red, double *out) {
+    __shared__ double scratch[32];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        const double s = sg_block_sum(v[k], scratch);
+        if (threadIdx.x == 0) red.partials[blockIdx.x * NR + k] = s;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(red.counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            double s = 0.0;
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += red.partials[b * NR + k];
+            s = sg_block_sum(s, scratch);
+            if (threadIdx.x == 0) out[k] = s;
+        }
+        if (threadIdx.x == 0) *red.counter = 0u;
+    }
 }

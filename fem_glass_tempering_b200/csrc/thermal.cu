@@ -45,6 +45,7 @@ struct Tab {
 
 struct OpDev {
     long n_cells, cell_lo, cell_hi;
+    long dot_lo, dot_hi;    // cells whose x_K . y_K enters the fused dot product
     long n_dofs;
     const int32_t *dofmap;  // CG: [NLD][n_cells]
     const double *geom;     // [D*D + 2][n_cells]
@@ -73,13 +74,25 @@ __device__ __forceinline__ double dlam_dot(const double (&v)[D], int i) {
     return v[i - 1];
 }
 
-template <int D, int P, bool DG, int MODE>
-__global__ void __launch_bounds__(TB) cell_kernel(const __grid_constant__ Tab<D, P, DG> tab, const __grid_constant__ OpDev op, const double *__restrict__ x,
-                                                  const double *__restrict__ xprev, double *__restrict__ y) {
+// Where the input vector comes from: the global array (the operator kernels) or a unit vector (the
+// builder of the local-matrix class tables, which thereby shares every line of arithmetic with the
+// general kernel).
+struct XGlobal {
+    const double *x;
+    __device__ __forceinline__ double at(long dof) const { return x[dof]; }
+};
+struct XUnit {
+    long sel;
+    __device__ __forceinline__ double at(long dof) const { return dof == sel ? 1.0 : 0.0; }
+};
+
+// Element vector of cell c: yk = (cell integrals + DG interior-facet terms)(x), MODE as below.
+template <int D, int P, bool DG, int MODE, class XA>
+__device__ __forceinline__ void cell_compute(const Tab<D, P, DG> &tab, const OpDev &op, const long c, const XA xa,
+                                             const double *__restrict__ xprev, long (&dof)[nld_of(D, P)],
+                                             double (&yk)[nld_of(D, P)]) {
     using T = Tab<D, P, DG>;
     constexpr int NLD = T::NLD, NQC = T::NQC, NQF = T::NQF;
-    const long c = op.cell_lo + (long)blockIdx.x * TB + threadIdx.x;
-    if (c >= op.cell_hi) return;
     const long nc = op.n_cells;
 
     double Jinv[D][D];
@@ -89,12 +102,11 @@ __global__ void __launch_bounds__(TB) cell_kernel(const __grid_constant__ Tab<D,
         for (int b = 0; b < D; ++b) Jinv[a][b] = op.geom[(long)(a * D + b) * nc + c];
     const double detJ = op.geom[(long)(D * D) * nc + c];
 
-    long dof[NLD];
-    double xk[NLD], yk[NLD];
+    double xk[NLD];
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
         dof[i] = DG ? c * NLD + i : (long)op.dofmap[(long)i * nc + c];
-        if (MODE != MODE_DIAG) xk[i] = x[dof[i]];
+        if (MODE != MODE_DIAG) xk[i] = xa.at(dof[i]);
     }
 
     // ---- cell integrals: |detJ| * Mhat  +  dt*alpha * sum_q w_q detJ (Jinv^T grad)^T (Jinv^T grad) ----
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(TB) cell_kernel(const __grid_constant__ Tab<D,
                 for (int b = 0; b < D; ++b) jnN[a] += op.geom[(long)(a * D + b) * nc + nb] * n[b];
             }
 #pragma unroll
-            for (int j = 0; j < NLD; ++j) xn[j] = x[nb * NLD + j];
+            for (int j = 0; j < NLD; ++j) xn[j] = xa.at(nb * NLD + j);
             double dphK[NLD], dnK = 0.0, dnN = 0.0;
             if constexpr (P == 1) {
 #pragma unroll
@@ -274,7 +286,17 @@ __global__ void __launch_bounds__(TB) cell_kernel(const __grid_constant__ Tab<D,
         }
     }
 
-    // ---- write / scatter ----
+}
+
+template <int D, int P, bool DG, int MODE>
+__global__ void __launch_bounds__(TB) cell_kernel(const __grid_constant__ Tab<D, P, DG> tab, const __grid_constant__ OpDev op, const double *__restrict__ x,
+                                                  const double *__restrict__ xprev, double *__restrict__ y) {
+    constexpr int NLD = nld_of(D, P);
+    const long c = op.cell_lo + (long)blockIdx.x * TB + threadIdx.x;
+    if (c >= op.cell_hi) return;
+    long dof[NLD];
+    double yk[NLD];
+    cell_compute<D, P, DG, MODE>(tab, op, c, XGlobal{x}, xprev, dof, yk);
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
         if (DG)
@@ -284,49 +306,337 @@ __global__ void __launch_bounds__(TB) cell_kernel(const __grid_constant__ Tab<D,
     }
 }
 
-// Exterior facets: radiation + convection (TVP:302-304) and their linearisation.
-template <int D, int P, bool DG, int MODE>
+// Exterior facets: radiation + convection (TVP:302-304) and their linearisation.  Grid-stride; with DOT the
+// kernel also reduces sum_i x_i * (its own contribution to y_i) over facets of cells in [dot_lo, dot_hi).
+template <int D, int P, bool DG, int MODE, bool DOT>
 __global__ void __launch_bounds__(TB) bfacet_kernel(const OpDev op, const double *__restrict__ Tlin,
-                                                    const double *__restrict__ x, double *__restrict__ y) {
+                                                    const double *__restrict__ x, double *__restrict__ y, SgRed red,
+                                                    double *dot_out, const int *skip) {
     constexpr int NLD = nld_of(D, P);
-    const long b = (long)blockIdx.x * TB + threadIdx.x;
-    if (b >= op.n_bf) return;
-    const long c = op.bf_cell[b];
-    if (c < op.cell_lo || c >= op.cell_hi) return;
-    const int f = op.bf_facet[b];
-    const double area = op.bf_area[b];
+    if (skip && *skip) return;
+    double dsum[1] = {0.0};
+    for (long b = (long)blockIdx.x * TB + threadIdx.x; b < op.n_bf; b += (long)gridDim.x * TB) {
+        const long c = op.bf_cell[b];
+        if (c < op.cell_lo || c >= op.cell_hi) continue;
+        const int f = op.bf_facet[b];
+        const double area = op.bf_area[b];
+        long dof[NLD];
+        double Tk[NLD], xk[NLD], acc[NLD];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            dof[i] = DG ? c * NLD + i : (long)op.dofmap[(long)i * op.n_cells + c];
+            Tk[i] = Tlin[dof[i]];
+            xk[i] = (MODE == MODE_APPLY) ? x[dof[i]] : 0.0;
+            acc[i] = 0.0;
+        }
+        for (int q = 0; q < op.nqb; ++q) {
+            const double *ph = op.btab + ((long)f * op.nqb + q) * NLD;
+            double Tq = 0.0, xq = 0.0;
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) {
+                Tq += ph[j] * Tk[j];
+                xq += ph[j] * xk[j];
+            }
+            const double w = area * op.bw[q] * op.dt * 0.001;
+            if (MODE == MODE_RESID) {
+                const double T2 = Tq * Tq, Ta2 = op.Ta * op.Ta;
+                const double flux = w * (op.se * (T2 * T2 - Ta2 * Ta2) + op.htc * (Tq - op.Ta));
+#pragma unroll
+                for (int i = 0; i < NLD; ++i) acc[i] += flux * ph[i];
+            } else {
+                const double coef = w * (4.0 * op.se * Tq * Tq * Tq + op.htc);
+#pragma unroll
+                for (int i = 0; i < NLD; ++i) acc[i] += (MODE == MODE_APPLY) ? coef * xq * ph[i] : coef * ph[i] * ph[i];
+            }
+        }
+        const bool counted = DOT && c >= op.dot_lo && c < op.dot_hi;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i)
+            if (acc[i] != 0.0) {
+                atomicAdd(&y[dof[i]], acc[i]);
+                if (counted) dsum[0] += xk[i] * acc[i];
+            }
+    }
+    if (DOT) sg_grid_reduce<1>(dsum, red, dot_out);
+}
+
+// sum over [lo, hi) of a*b (general path of sg_thermal_apply_dot)
+__global__ void __launch_bounds__(256) k_dot_range(long lo, long hi, const double *__restrict__ a, const double *__restrict__ b,
+                                                   SgRed red, double *out, const int *skip) {
+    if (skip && *skip) return;
+    double acc[2] = {0.0, 0.0};  // out[1] = 0: the exterior-facet part is already inside a.b
+    for (long i = lo + (long)blockIdx.x * 256 + threadIdx.x; i < hi; i += (long)gridDim.x * 256) acc[0] += a[i] * b[i];
+    sg_grid_reduce<2>(acc, red, out);
+}
+
+// ================================================================ local-matrix classes (fast apply path)
+//
+// On the plates of the benchmark (and on any mesh with few distinct cell shapes) the cell part of the
+// Jacobian is a handful of distinct local matrices:
+//     y_K = A_self[s(K)] x_K + sum_f A_nb[u(K,f)] x_{N(K,f)}          (DG; CG: only A_self, scattered)
+// s(K) = class of (cell shape, which facets are interior, the facet classes), u(K,f) = class of (shape of
+// K, f, shape of N, N's local facet, vertex permutation, which side is '+').  The classes are found at
+// operator creation by hashing the cell geometry rounded to 40 mantissa bits (GPU, classify.cu), the
+// tables are produced by running cell_compute on unit vectors for one representative per class, and the
+// apply kernel keeps them in shared memory: per cell it reads 8 B of class ids, the neighbour ids and
+// x, and writes y — no geometry, no square roots, no divisions.  Meshes with too many classes keep
+// using cell_kernel.
+
+__device__ __forceinline__ uint64_t key_mix(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    return h;
+}
+// round the mantissa to 40 bits; values below `cut` count as zero
+__device__ __forceinline__ uint64_t key_round(double v, double cut) {
+    if (!(fabs(v) >= cut)) return 0ull;
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b + 0x800ull) & ~0xFFFull;
+}
+
+template <int D>
+__device__ __forceinline__ void geom_rounded(const double *geom, long nc, long c, uint64_t (&q)[D * D + 2]) {
+    double v[D * D + 2], mx = 0.0;
+#pragma unroll
+    for (int k = 0; k < D * D + 2; ++k) v[k] = geom[(long)k * nc + c];
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) mx = fmax(mx, fabs(v[k]));
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) q[k] = key_round(v[k], mx * 0x1p-38);
+    q[D * D] = key_round(v[D * D], 0.0);
+    q[D * D + 1] = key_round(v[D * D + 1], 0.0);
+}
+
+template <int D>
+__global__ void k_geom_key(const double *geom, long nc, uint64_t *keys) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    uint64_t q[D * D + 2], h = 0x243F6A8885A308D3ull;
+    geom_rounded<D>(geom, nc, c, q);
+#pragma unroll
+    for (int k = 0; k < D * D + 2; ++k) h = key_mix(h, q[k]);
+    keys[c] = h;
+}
+
+// counts cells whose rounded geometry differs from their class representative's (hash collisions)
+template <int D>
+__global__ void k_geom_verify(const double *geom, long nc, const int32_t *gcls, const int32_t *rep, unsigned *bad) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    uint64_t q[D * D + 2], r[D * D + 2];
+    geom_rounded<D>(geom, nc, c, q);
+    geom_rounded<D>(geom, nc, rep[gcls[c]], r);
+    bool same = true;
+#pragma unroll
+    for (int k = 0; k < D * D + 2; ++k) same = same && q[k] == r[k];
+    if (!same) atomicAdd(bad, 1u);
+}
+
+// key of (cell c, local facet f), layout [f][c]; 0 = no neighbour
+__global__ void k_facet_key(int nnb, long nc, const int32_t *nbr, const int32_t *nbinfo, const int32_t *gcls, uint64_t *keys) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nc * nnb) return;
+    const int f = (int)(t / nc);
+    const long c = t % nc;
+    const long nb = nbr[t];
+    if (nb < 0) {
+        keys[t] = 0ull;
+        return;
+    }
+    const int info = (nbinfo[c] >> (5 * f)) & 31;
+    uint64_t h = 0x13198A2E03707344ull;
+    h = key_mix(h, (uint64_t)gcls[c]);
+    h = key_mix(h, (uint64_t)gcls[nb]);
+    h = key_mix(h, (uint64_t)(f * 64 + info * 2 + (c < nb ? 1 : 0)));
+    keys[t] = h | 1ull;
+}
+
+__global__ void k_self_key(int nnb, long nc, const int32_t *nbr, const int32_t *gcls, const int32_t *fcls, uint64_t *keys) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    uint64_t h = key_mix(0xA4093822299F31D0ull, (uint64_t)gcls[c]);
+    for (int f = 0; f < nnb; ++f) {
+        const long t = (long)f * nc + c;
+        h = key_mix(h, nbr[t] < 0 ? 0ull : (uint64_t)fcls[t] + 1ull);
+    }
+    keys[c] = h;
+}
+
+// DG: 16 bits self class | 12 bits per facet (0 = no neighbour, else facet class + 1)
+__global__ void k_pack_dg(int nnb, long nc, const int32_t *nbr, const int32_t *scls, const int32_t *fcls, uint64_t *out) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    uint64_t w = (uint64_t)scls[c];
+    for (int f = 0; f < nnb; ++f) {
+        const long t = (long)f * nc + c;
+        const uint64_t u = nbr[t] < 0 ? 0ull : (uint64_t)fcls[t] + 1ull;
+        w |= u << (16 + 12 * f);
+    }
+    out[c] = w;
+}
+__global__ void k_pack_cg(long nc, const int32_t *gcls, uint16_t *out) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nc) out[c] = (uint16_t)gcls[c];
+}
+
+// One thread per (class, column j): column j of the class's local matrix = cell_compute(unit vector).
+// Table layout: class k at tab_out + k*S, entry (i, j) at [i*NLD + j]; self classes first, then facet classes.
+template <int D, int P, bool DG>
+__global__ void k_build_tables(const __grid_constant__ Tab<D, P, DG> tab, const __grid_constant__ OpDev op, int n_self,
+                               const int32_t *rep_self, int n_nb, const int32_t *rep_nb, int S, double *tab_out) {
+    constexpr int NLD = nld_of(D, P);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (n_self + n_nb) * NLD) return;
+    const int k = t / NLD, j = t % NLD;
+    long c, sel;
+    if (k < n_self) {
+        c = rep_self[k];
+        sel = DG ? c * NLD + j : (long)op.dofmap[(long)j * op.n_cells + c];
+    } else {
+        const long r = rep_nb[k - n_self];
+        c = r % op.n_cells;
+        const long nb = op.nbr[r];
+        if (nb < 0) {
+            for (int i = 0; i < NLD; ++i) tab_out[(long)k * S + i * NLD + j] = 0.0;
+            return;
+        }
+        sel = nb * NLD + j;
+    }
     long dof[NLD];
-    double Tk[NLD], xk[NLD], acc[NLD];
+    double yk[NLD];
+    cell_compute<D, P, DG, MODE_APPLY>(tab, op, c, XUnit{sel}, nullptr, dof, yk);
 #pragma unroll
-    for (int i = 0; i < NLD; ++i) {
-        dof[i] = DG ? c * NLD + i : (long)op.dofmap[(long)i * op.n_cells + c];
-        Tk[i] = Tlin[dof[i]];
-        xk[i] = (MODE == MODE_APPLY) ? x[dof[i]] : 0.0;
-        acc[i] = 0.0;
-    }
-    for (int q = 0; q < op.nqb; ++q) {
-        const double *ph = op.btab + ((long)f * op.nqb + q) * NLD;
-        double Tq = 0.0, xq = 0.0;
+    for (int i = 0; i < NLD; ++i) tab_out[(long)k * S + i * NLD + j] = yk[i];
+}
+
+struct ClsDev {
+    long n_cells, cell_lo, cell_hi, dot_lo, dot_hi;
+    const int32_t *nbr;     // DG [NNB][n_cells]
+    const int32_t *dofmap;  // CG [NLD][n_cells]
+    const uint64_t *cls64;  // DG
+    const uint16_t *cls16;  // CG
+    const double *tab;      // [(n_self + n_nb) * S]
+    int n_self, n_nb, S;
+};
+
+constexpr int CB = 256;  // threads per block of the class kernels
+
+template <int NLD>
+__device__ __forceinline__ void load_row(const double *__restrict__ p, double (&v)[NLD]) {
+    if constexpr (NLD % 2 == 0) {
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) {
-            Tq += ph[j] * Tk[j];
-            xq += ph[j] * xk[j];
+        for (int i = 0; i < NLD / 2; ++i) {
+            const double2 t = reinterpret_cast<const double2 *>(p)[i];
+            v[2 * i] = t.x;
+            v[2 * i + 1] = t.y;
         }
-        const double w = area * op.bw[q] * op.dt * 0.001;
-        if (MODE == MODE_RESID) {
-            const double T2 = Tq * Tq, Ta2 = op.Ta * op.Ta;
-            const double flux = w * (op.se * (T2 * T2 - Ta2 * Ta2) + op.htc * (Tq - op.Ta));
+    } else {
 #pragma unroll
-            for (int i = 0; i < NLD; ++i) acc[i] += flux * ph[i];
-        } else {
-            const double coef = w * (4.0 * op.se * Tq * Tq * Tq + op.htc);
-#pragma unroll
-            for (int i = 0; i < NLD; ++i) acc[i] += (MODE == MODE_APPLY) ? coef * xq * ph[i] : coef * ph[i] * ph[i];
-        }
+        for (int i = 0; i < NLD; ++i) v[i] = p[i];
     }
+}
+template <int NLD>
+__device__ __forceinline__ void store_row(double *__restrict__ p, const double (&v)[NLD]) {
+    if constexpr (NLD % 2 == 0) {
 #pragma unroll
-    for (int i = 0; i < NLD; ++i)
-        if (acc[i] != 0.0) atomicAdd(&y[dof[i]], acc[i]);
+        for (int i = 0; i < NLD / 2; ++i) reinterpret_cast<double2 *>(p)[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) p[i] = v[i];
+    }
+}
+
+// DG fast apply: persistent grid-stride blocks, class tables in shared memory, fused x.y reduction.
+template <int NLD, int NNB>
+__global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
+                                                     SgRed red, double *dot_out, const int *skip) {
+    extern __shared__ double s_tab[];
+    if (skip && *skip) return;
+    const int ntab = (cd.n_self + cd.n_nb) * cd.S;
+    for (int i = threadIdx.x; i < ntab; i += CB) s_tab[i] = cd.tab[i];
+    __syncthreads();
+    const double *s_nb = s_tab + cd.n_self * cd.S;
+    const long nc = cd.n_cells;
+    double dsum[1] = {0.0};
+    for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
+        const uint64_t w = cd.cls64[c];
+        int nb[NNB];
+#pragma unroll
+        for (int f = 0; f < NNB; ++f) nb[f] = cd.nbr[(long)f * nc + c];
+        double xk[NLD], yk[NLD];
+        load_row<NLD>(x + c * NLD, xk);
+        double xn[NNB][NLD];
+#pragma unroll
+        for (int f = 0; f < NNB; ++f) {
+            if (nb[f] >= 0) {
+                load_row<NLD>(x + (long)nb[f] * NLD, xn[f]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NLD; ++j) xn[f][j] = 0.0;
+            }
+        }
+        const double *As = s_tab + (int)(w & 0xFFFFull) * cd.S;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) a += As[i * NLD + j] * xk[j];
+            yk[i] = a;
+        }
+#pragma unroll
+        for (int f = 0; f < NNB; ++f) {
+            const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
+            if (u) {
+                const double *An = s_nb + (u - 1) * cd.S;
+#pragma unroll
+                for (int i = 0; i < NLD; ++i) {
+                    double a = yk[i];
+#pragma unroll
+                    for (int j = 0; j < NLD; ++j) a += An[i * NLD + j] * xn[f][j];
+                    yk[i] = a;
+                }
+            }
+        }
+        store_row<NLD>(y + c * NLD, yk);
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
+    }
+    sg_grid_reduce<1>(dsum, red, dot_out);
+}
+
+// CG fast apply: gather through the dofmap, class matrix from shared memory, scatter with RED.ADD.F64.
+// x.y is reduced cell-wise as x_K . (A_K x_K) over the cells [dot_lo, dot_hi) (each global cell on one rank).
+template <int NLD>
+__global__ void __launch_bounds__(CB) cg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
+                                                     SgRed red, double *dot_out, const int *skip) {
+    extern __shared__ double s_tab[];
+    if (skip && *skip) return;
+    const int ntab = cd.n_self * cd.S;
+    for (int i = threadIdx.x; i < ntab; i += CB) s_tab[i] = cd.tab[i];
+    __syncthreads();
+    const long nc = cd.n_cells;
+    double dsum[1] = {0.0};
+    for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
+        const double *As = s_tab + (int)cd.cls16[c] * cd.S;
+        int dof[NLD];
+        double xk[NLD];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) dof[i] = cd.dofmap[(long)i * nc + c];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) xk[i] = x[dof[i]];
+        double d = 0.0;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) a += As[i * NLD + j] * xk[j];
+            atomicAdd(&y[dof[i]], a);
+            d += xk[i] * a;
+        }
+        if (c >= cd.dot_lo && c < cd.dot_hi) dsum[0] += d;
+    }
+    sg_grid_reduce<1>(dsum, red, dot_out);
 }
 
 }  // namespace
@@ -339,46 +649,199 @@ struct sg_thermal_op {
     void *tab_host;      // Tab<D,P,DG> instance
     size_t tab_bytes;
     double *btab_dev, *bw_dev;
-    // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
     double mass_inv[100];
+    // local-matrix classes (fast apply path); cls.tab == nullptr when not available
+    ClsDev cls;
+    void *cls_words;       // cls64 / cls16 storage
+    double *cls_tab;
+    int cls_grid;
+    size_t cls_smem;
+    int32_t n_geom_classes;
+    SgRed own_red;         // reduction scratch of sg_thermal_jac_apply (solver-less use of the fast path)
+    // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
     int prof_on, prof_n, prof_cap;
     cudaEvent_t *prof_ev;
     int (*launch)(const sg_thermal_op *, int mode, const double *T, const double *x, const double *xprev, double *y,
-                  cudaStream_t st);
+                  SgRed red, double *dot2, const int *skip, cudaStream_t st);
+    int (*build_classes)(sg_thermal_op *);
 };
 
 namespace {
 
+inline unsigned capped_grid(long n, int tb) {
+    long g = (n + tb - 1) / tb;
+    if (g < 1) g = 1;
+    return (unsigned)(g > SG_MAX_BLOCKS ? SG_MAX_BLOCKS : g);
+}
+
+struct ProfScope {  // CUDA-event pair around the apply cell kernel when profiling is on
+    const sg_thermal_op *op;
+    cudaStream_t st;
+    bool on;
+    ProfScope(const sg_thermal_op *o, int mode, cudaStream_t s) : op(o), st(s) {
+        on = mode == MODE_APPLY && o->prof_on && o->prof_n < o->prof_cap;
+        if (on) cudaEventRecord(o->prof_ev[2 * o->prof_n], st);
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(op->prof_ev[2 * op->prof_n + 1], st);
+            const_cast<sg_thermal_op *>(op)->prof_n++;
+        }
+    }
+};
+
+// dot2 != nullptr (MODE_APPLY only): also produce dot2[0] + dot2[1] = x.y over the owned dofs.
 template <int D, int P, bool DG>
 int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const double *x, const double *xprev, double *y,
-              cudaStream_t st) {
+              SgRed red, double *dot2, const int *skip, cudaStream_t st) {
     using T = Tab<D, P, DG>;
+    constexpr int NLD = T::NLD;
     const T &tab = *static_cast<const T *>(op->tab_host);
     const OpDev &dv = op->dev;
     const long ncell = dv.cell_hi - dv.cell_lo;
-    const unsigned gc = (unsigned)((ncell + TB - 1) / TB), gb = (unsigned)((dv.n_bf + TB - 1) / TB);
+    const unsigned gc = (unsigned)((ncell + TB - 1) / TB), gb = capped_grid(dv.n_bf, TB);
+    const bool fast = mode == MODE_APPLY && op->cls.tab != nullptr;
     if (!DG) SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
-    if (ncell > 0) {
-        const bool prof = mode == MODE_APPLY && op->prof_on && op->prof_n < op->prof_cap;
-        sg_thermal_op *mop = const_cast<sg_thermal_op *>(op);
-        if (prof) SG_CHECK_CUDA(cudaEventRecord(op->prof_ev[2 * op->prof_n], st));
-        if (mode == MODE_APPLY) cell_kernel<D, P, DG, MODE_APPLY><<<gc, TB, 0, st>>>(tab, dv, x, nullptr, y);
-        if (prof) {
-            SG_CHECK_CUDA(cudaEventRecord(op->prof_ev[2 * op->prof_n + 1], st));
-            mop->prof_n++;
-        }
+    if (fast) {
+        // the class kernels always reduce x.y; without a consumer it lands in a scratch slot
+        double *dst = dot2 ? dot2 : red.partials + 2 * SG_MAX_BLOCKS;
+        ProfScope ps(op, mode, st);
+        if (DG)
+            dg_class_apply<NLD, D + 1><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+        else
+            cg_class_apply<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+        SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
+    } else if (ncell > 0) {
+        ProfScope ps(op, mode, st);
+        if (mode == MODE_APPLY) cell_kernel<D, P, DG, MODE_APPLY><<<gc, TB, 0, st>>>(tab, dv, x, nullptr, y);
         if (mode == MODE_RESID) cell_kernel<D, P, DG, MODE_RESID><<<gc, TB, 0, st>>>(tab, dv, x, xprev, y);
         if (mode == MODE_DIAG) cell_kernel<D, P, DG, MODE_DIAG><<<gc, TB, 0, st>>>(tab, dv, nullptr, nullptr, y);
         SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
     }
-    if (dv.n_bf > 0) {
-        if (mode == MODE_APPLY) bfacet_kernel<D, P, DG, MODE_APPLY><<<gb, TB, 0, st>>>(dv, Tlin, x, y);
-        if (mode == MODE_RESID) bfacet_kernel<D, P, DG, MODE_RESID><<<gb, TB, 0, st>>>(dv, x, nullptr, y);
-        if (mode == MODE_DIAG) bfacet_kernel<D, P, DG, MODE_DIAG><<<gb, TB, 0, st>>>(dv, Tlin, nullptr, y);
+    const bool bdot = fast && dot2;
+    if (dv.n_bf > 0 || bdot) {
+        if (mode == MODE_APPLY && bdot) bfacet_kernel<D, P, DG, MODE_APPLY, true><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, dot2 + 1, skip);
+        if (mode == MODE_APPLY && !bdot) bfacet_kernel<D, P, DG, MODE_APPLY, false><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, nullptr, skip);
+        if (mode == MODE_RESID) bfacet_kernel<D, P, DG, MODE_RESID, false><<<gb, TB, 0, st>>>(dv, x, nullptr, y, red, nullptr, nullptr);
+        if (mode == MODE_DIAG) bfacet_kernel<D, P, DG, MODE_DIAG, false><<<gb, TB, 0, st>>>(dv, Tlin, nullptr, y, red, nullptr, nullptr);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
     }
+    if (dot2 && !fast) {
+        const long lo = op->d.own_lo, hi = op->d.own_hi;
+        k_dot_range<<<capped_grid(hi - lo, 256), 256, 0, st>>>(lo, hi, x, y, red, dot2, skip);
+        SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
+    }
+    return SG_OK;
+}
+
+struct DevBuf {  // scoped cudaMalloc
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    template <class T>
+    T *as() { return static_cast<T *>(p); }
+};
+
+// Find the local-matrix classes of this mesh and build the tables (see the comment above key_mix).
+// Leaves op->cls.tab == nullptr (general kernel stays in use) when the mesh has too many classes.
+template <int D, int P, bool DG>
+int build_classes_t(sg_thermal_op *op) {
+    using T = Tab<D, P, DG>;
+    constexpr int NLD = T::NLD, NNB = DG ? D + 1 : 0;
+    constexpr int S = (NLD * NLD) | 1;  // odd stride: classes start in different shared-memory banks
+    const OpDev &dv = op->dev;
+    const long nc = dv.n_cells;
+    if (nc <= 0 || dv.cell_hi <= dv.cell_lo) return SG_OK;
+    const unsigned g1 = (unsigned)((nc + 255) / 256);
+    DevBuf keys, gcls, grep, fcls, frep, scls, srep, bad;
+    SG_CHECK_CUDA(cudaMalloc(&keys.p, sizeof(uint64_t) * (size_t)nc * (NNB > 0 ? NNB : 1)));
+    k_geom_key<D><<<g1, 256>>>(dv.geom, nc, keys.as<uint64_t>());
+    SG_CHECK_CUDA(cudaGetLastError());
+    int32_t G = 0, NF = 0, NS = 0;
+    int rc = sg_classify_u64(keys.as<uint64_t>(), nc, (int32_t **)&gcls.p, &G, (int32_t **)&grep.p);
+    if (rc) return rc;
+    SG_CHECK_CUDA(cudaMalloc(&bad.p, sizeof(unsigned)));
+    SG_CHECK_CUDA(cudaMemset(bad.p, 0, sizeof(unsigned)));
+    k_geom_verify<D><<<g1, 256>>>(dv.geom, nc, gcls.as<int32_t>(), grep.as<int32_t>(), bad.as<unsigned>());
+    unsigned nbad = 0;
+    SG_CHECK_CUDA(cudaMemcpy(&nbad, bad.p, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    op->n_geom_classes = G;
+    if (nbad) return SG_OK;  // 64-bit hash collision: keep the general kernel
+    const int32_t *rep_self = grep.as<int32_t>(), *rep_nb = nullptr;
+    if (DG) {
+        const unsigned gf = (unsigned)((nc * NNB + 255) / 256);
+        k_facet_key<<<gf, 256>>>(NNB, nc, dv.nbr, dv.nbinfo, gcls.as<int32_t>(), keys.as<uint64_t>());
+        SG_CHECK_CUDA(cudaGetLastError());
+        if ((rc = sg_classify_u64(keys.as<uint64_t>(), nc * NNB, (int32_t **)&fcls.p, &NF, (int32_t **)&frep.p))) return rc;
+        k_self_key<<<g1, 256>>>(NNB, nc, dv.nbr, gcls.as<int32_t>(), fcls.as<int32_t>(), keys.as<uint64_t>());
+        SG_CHECK_CUDA(cudaGetLastError());
+        if ((rc = sg_classify_u64(keys.as<uint64_t>(), nc, (int32_t **)&scls.p, &NS, (int32_t **)&srep.p))) return rc;
+        rep_self = srep.as<int32_t>();
+        rep_nb = frep.as<int32_t>();
+        if (NS > 65535 || NF > 4094) return SG_OK;
+    } else {
+        NS = G;
+        if (NS > 65535) return SG_OK;
+    }
+    const size_t smem = sizeof(double) * (size_t)(NS + NF) * S;
+    if (smem > 96 * 1024) return SG_OK;
+    // tables
+    SG_CHECK_CUDA(cudaMalloc(&op->cls_tab, smem));
+    const T &tab = *static_cast<const T *>(op->tab_host);
+    const int nthreads = (NS + NF) * NLD;
+    k_build_tables<D, P, DG><<<(nthreads + 63) / 64, 64>>>(tab, dv, NS, rep_self, NF, rep_nb, S, op->cls_tab);
+    SG_CHECK_CUDA(cudaGetLastError());
+    // per-cell class words
+    if (DG) {
+        SG_CHECK_CUDA(cudaMalloc(&op->cls_words, sizeof(uint64_t) * (size_t)nc));
+        k_pack_dg<<<g1, 256>>>(NNB, nc, dv.nbr, scls.as<int32_t>(), fcls.as<int32_t>(), (uint64_t *)op->cls_words);
+    } else {
+        SG_CHECK_CUDA(cudaMalloc(&op->cls_words, sizeof(uint16_t) * (size_t)nc));
+        k_pack_cg<<<g1, 256>>>(nc, gcls.as<int32_t>(), (uint16_t *)op->cls_words);
+    }
+    SG_CHECK_CUDA(cudaGetLastError());
+    SG_CHECK_CUDA(cudaDeviceSynchronize());
+    // launch geometry: persistent blocks, as many as fit per SM
+    int per_sm = 0;
+    if (DG) {
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, (DG ? D + 1 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, (DG ? D + 1 : 1)>, CB, smem));
+    } else {
+        SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_apply<NLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_class_apply<NLD>, CB, smem));
+    }
+    if (per_sm < 1) {
+        cudaFree(op->cls_tab);
+        cudaFree(op->cls_words);
+        op->cls_tab = nullptr;
+        op->cls_words = nullptr;
+        return SG_OK;
+    }
+    long grid = (long)per_sm * op->ctx->sm_count;
+    const long need = (dv.cell_hi - dv.cell_lo + CB - 1) / CB;
+    if (grid > need) grid = need;
+    if (grid > SG_MAX_BLOCKS) grid = SG_MAX_BLOCKS;
+    op->cls_grid = (int)grid;
+    op->cls_smem = smem;
+    ClsDev &cd = op->cls;
+    cd.n_cells = nc;
+    cd.cell_lo = dv.cell_lo;
+    cd.cell_hi = dv.cell_hi;
+    cd.dot_lo = dv.dot_lo;
+    cd.dot_hi = dv.dot_hi;
+    cd.nbr = dv.nbr;
+    cd.dofmap = dv.dofmap;
+    cd.cls64 = DG ? (const uint64_t *)op->cls_words : nullptr;
+    cd.cls16 = DG ? nullptr : (const uint16_t *)op->cls_words;
+    cd.n_self = NS;
+    cd.n_nb = NF;
+    cd.S = S;
+    cd.tab = op->cls_tab;  // set last: marks the fast path as available
     return SG_OK;
 }
 
@@ -405,6 +868,7 @@ int build_tab(sg_thermal_op *op) {
     op->tab_host = t;
     op->tab_bytes = sizeof(T);
     op->launch = &launch_op<D, P, DG>;
+    op->build_classes = &build_classes_t<D, P, DG>;
     return SG_OK;
 }
 
@@ -432,6 +896,11 @@ void sg_op_info(const sg_thermal_op *op, SgOpInfo *o) {
     o->cell_hi = op->d.cell_hi;
     o->detJ = op->d.geom + (int64_t)op->d.dim * op->d.dim * op->d.n_cells;
     o->mass_inv = op->mass_inv;
+}
+
+int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
+                         const int *skip, cudaStream_t st) {
+    return op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, red, dot2, skip, st);
 }
 
 // Gauss-Jordan inverse of the (SPD, n <= 10) reference mass matrix
@@ -472,18 +941,18 @@ int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *d, sg_thermal_op **
     SG_REQUIRE(d->n_cells >= 0 && d->cell_lo >= 0 && d->cell_lo <= d->cell_hi && d->cell_hi <= d->n_cells,
                "sg_thermal_op_create: bad cell range");
     SG_REQUIRE(d->own_lo >= 0 && d->own_lo <= d->own_hi && d->own_hi <= d->n_dofs, "sg_thermal_op_create: bad owned dof range");
+    SG_REQUIRE(d->own_cell_lo >= 0 && d->own_cell_lo <= d->own_cell_hi && d->own_cell_hi <= d->n_cells,
+               "sg_thermal_op_create: bad owned cell range");
     SG_REQUIRE(d->geom && d->mass && d->load && d->cq_w && d->cq_grad, "sg_thermal_op_create: missing geometry/tables");
     SG_REQUIRE(d->family == 1 || d->dofmap, "sg_thermal_op_create: CG needs a dofmap");
     SG_REQUIRE(d->family == 0 || (d->nbr && d->nbinfo), "sg_thermal_op_create: DG needs neighbour maps");
     SG_REQUIRE(d->n_bfacets == 0 || (d->bf_cell && d->bf_facet && d->bf_area && d->bq_w && d->bq_val && d->nqb > 0),
                "sg_thermal_op_create: missing exterior-facet data");
+    SG_CHECK_CUDA(cudaSetDevice(ctx->device));
     sg_thermal_op *op = new sg_thermal_op();
+    memset(op, 0, sizeof(*op));
     op->ctx = ctx;
     op->d = *d;
-    op->tab_host = nullptr;
-    op->btab_dev = op->bw_dev = nullptr;
-    op->prof_on = op->prof_n = op->prof_cap = 0;
-    op->prof_ev = nullptr;
     int rc = SG_E_INVALID;
     if (d->dim == 1) rc = build_tab_d<1>(op);
     if (d->dim == 2) rc = build_tab_d<2>(op);
@@ -498,6 +967,9 @@ int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *d, sg_thermal_op **
     dv.n_cells = d->n_cells;
     dv.cell_lo = d->cell_lo;
     dv.cell_hi = d->cell_hi;
+    const bool own_given = d->own_cell_hi > d->own_cell_lo;
+    dv.dot_lo = own_given ? d->own_cell_lo : d->cell_lo;
+    dv.dot_hi = own_given ? d->own_cell_hi : d->cell_hi;
     dv.n_dofs = d->n_dofs;
     dv.dofmap = d->dofmap;
     dv.geom = d->geom;
@@ -533,6 +1005,13 @@ int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *d, sg_thermal_op **
     op->d.mass = op->d.load = op->d.cq_w = op->d.cq_grad = op->d.fq_w = op->d.fq_val = op->d.fq_grad = nullptr;
     op->d.fq_perm = nullptr;
     op->d.bq_w = op->d.bq_val = nullptr;
+    if (!(d->flags & SG_THERMAL_NO_CLASSES)) {
+        rc = op->build_classes(op);
+        if (rc != SG_OK) {
+            sg_thermal_op_destroy(op);
+            return rc;
+        }
+    }
     *out = op;
     return SG_OK;
 }
@@ -541,6 +1020,10 @@ int sg_thermal_op_destroy(sg_thermal_op *op) {
     if (!op) return SG_OK;
     if (op->btab_dev) cudaFree(op->btab_dev);
     if (op->bw_dev) cudaFree(op->bw_dev);
+    if (op->cls_tab) cudaFree(op->cls_tab);
+    if (op->cls_words) cudaFree(op->cls_words);
+    if (op->own_red.partials) cudaFree(op->own_red.partials);
+    if (op->own_red.counter) cudaFree(op->own_red.counter);
     for (int i = 0; i < 2 * op->prof_cap; ++i) cudaEventDestroy(op->prof_ev[i]);
     delete[] op->prof_ev;
     ::operator delete(op->tab_host);
@@ -548,19 +1031,35 @@ int sg_thermal_op_destroy(sg_thermal_op *op) {
     return SG_OK;
 }
 
+static SgRed no_red() { return SgRed{nullptr, nullptr}; }
+
 int sg_thermal_residual(sg_thermal_op *op, const double *T, const double *T_prev, double *F, void *stream) {
     SG_REQUIRE(op && T && T_prev && F, "sg_thermal_residual: NULL argument");
-    return op->launch(op, MODE_RESID, T, T, T_prev, F, (cudaStream_t)stream);
+    return op->launch(op, MODE_RESID, T, T, T_prev, F, no_red(), nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int sg_thermal_jac_apply(sg_thermal_op *op, const double *T_lin, const double *x, double *y, void *stream) {
     SG_REQUIRE(op && T_lin && x && y, "sg_thermal_jac_apply: NULL argument");
-    return op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, (cudaStream_t)stream);
+    if (op->cls.tab && !op->own_red.partials) {
+        // the class kernels reduce x.y as they go and need scratch for it even when nobody reads the result
+        SG_CHECK_CUDA(cudaMalloc(&op->own_red.partials, sizeof(double) * (2 * SG_MAX_BLOCKS + 2)));
+        SG_CHECK_CUDA(cudaMalloc(&op->own_red.counter, sizeof(unsigned)));
+        SG_CHECK_CUDA(cudaMemset(op->own_red.counter, 0, sizeof(unsigned)));
+    }
+    return op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, op->own_red, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int sg_thermal_jac_diag(sg_thermal_op *op, const double *T_lin, double *diag, void *stream) {
     SG_REQUIRE(op && T_lin && diag, "sg_thermal_jac_diag: NULL argument");
-    return op->launch(op, MODE_DIAG, T_lin, nullptr, nullptr, diag, (cudaStream_t)stream);
+    return op->launch(op, MODE_DIAG, T_lin, nullptr, nullptr, diag, no_red(), nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int sg_thermal_class_info(const sg_thermal_op *op, int32_t *n_geometry, int32_t *n_self, int32_t *n_facet) {
+    SG_REQUIRE(op, "sg_thermal_class_info: NULL operator");
+    if (n_geometry) *n_geometry = op->n_geom_classes;
+    if (n_self) *n_self = op->cls.tab ? op->cls.n_self : 0;
+    if (n_facet) *n_facet = op->cls.tab ? op->cls.n_nb : 0;
+    return op->cls.tab ? 1 : 0;
 }
 
 int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity) {
@@ -591,15 +1090,22 @@ int sg_thermal_profile_read(sg_thermal_op *op, int64_t *n_launches, double *ms_t
     return SG_OK;
 }
 
+// Algorithmic HBM bytes of the cell kernel of one Jacobian apply, for the layout actually in use.
 int64_t sg_thermal_apply_bytes(const sg_thermal_op *op) {
     if (!op) return -1;
     const sg_thermal_desc &d = op->d;
     const int64_t ncell = d.cell_hi - d.cell_lo;
-    int64_t per_cell = 8 * (d.dim * d.dim + 1);            // Jinv + detJ
-    if (d.family == 1) per_cell += 8 + 4 * (d.dim + 1) + 4;  // h, neighbour ids, packed facet info
-    else per_cell += 4 * d.n_ld;                            // dofmap
     const int64_t ndof = d.family == 1 ? ncell * d.n_ld : d.n_dofs;
-    return ncell * per_cell + 16 * ndof;                    // + read x, write y
+    int64_t per_cell;
+    if (op->cls.tab) {
+        per_cell = d.family == 1 ? 8 + 4 * (d.dim + 1)   // class word + neighbour ids
+                                 : 2 + 4 * d.n_ld;        // class id + dofmap
+    } else {
+        per_cell = 8 * (d.dim * d.dim + 1);                     // Jinv + detJ
+        if (d.family == 1) per_cell += 8 + 4 * (d.dim + 1) + 4;  // h, neighbour ids, packed facet info
+        else per_cell += 4 * d.n_ld;                            // dofmap
+    }
+    return ncell * per_cell + 16 * ndof;                        // + read x, write y
 }
 
 }  // extern "C"

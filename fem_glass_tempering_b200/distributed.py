@@ -97,19 +97,21 @@ def slab_partition(dim: int, n, lengths, family: str, degree: int, rank: int, wo
         if rank < world - 1:
             halo.append((rank + 1, own_hi - blk, blk, own_hi, blk))
         owned_points = (c1 - c0) * col_cells * n_ld
+        own_cells = (cell_lo, cell_hi)
     else:
         gp = degree                                        # ghost planes on the left: 1 (P1) or 2 (P2)
         planes_owned = (c1 - c0) * degree + (1 if rank == world - 1 else 0)
         own_lo = gl * gp * plane
         own_hi = own_lo + planes_owned * plane
         cell_lo, cell_hi = 0, m.n_cells
+        own_cells = (gl * col_cells, (gl + c1 - c0) * col_cells)
         if rank > 0:
             halo.append((rank - 1, own_lo, plane, 0, gp * plane))
         if rank < world - 1:
             halo.append((rank + 1, own_hi - gp * plane, gp * plane, own_hi, plane))
         owned_points = (c1 - c0) * col_cells * n_ld
     part = dict(cell_lo=cell_lo, cell_hi=cell_hi, own_lo=own_lo, own_hi=own_hi, exterior_mask=exterior_mask,
-                halo=halo)
+                halo=halo, own_cell_lo=own_cells[0], own_cell_hi=own_cells[1])
     info = dict(columns=(c0, c1), ghost_left=gl, ghost_right=gr, owned_cell_points=owned_points,
                 owned_nodes=own_hi - own_lo)
     return m, part, info

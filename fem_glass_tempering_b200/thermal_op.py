@@ -29,7 +29,8 @@ class ThermalOperator:
                   recv_off, recv_cnt), ...]) describing this rank's slab; default: everything owned.
     """
 
-    def __init__(self, ctx: _lib.Context, space: fe.ScalarSpace, params: dict, dt: float, partition: dict | None = None):
+    def __init__(self, ctx: _lib.Context, space: fe.ScalarSpace, params: dict, dt: float, partition: dict | None = None,
+                 use_classes: bool = True):
         import torch
         self.ctx, self.space, self.dt = ctx, space, float(dt)
         mesh, d = space.mesh, space.mesh.dim
@@ -69,6 +70,8 @@ class ThermalOperator:
         desc.dim, desc.degree, desc.family = d, space.degree, 1 if dg else 0
         desc.n_cells, desc.cell_lo, desc.cell_hi = nc, part.get("cell_lo", 0), part.get("cell_hi", nc)
         desc.n_dofs, desc.own_lo, desc.own_hi = space.n_nodes, part.get("own_lo", 0), part.get("own_hi", space.n_nodes)
+        desc.own_cell_lo, desc.own_cell_hi = part.get("own_cell_lo", desc.cell_lo), part.get("own_cell_hi", desc.cell_hi)
+        desc.flags = 0 if use_classes else 1     # SG_THERMAL_NO_CLASSES
         for name in ("dofmap", "geom", "nbr", "nbinfo", "bf_cell", "bf_facet", "bf_area"):
             setattr(desc, name, _lib.ptr(keep.get(name)))
         desc.n_bfacets = nbf
@@ -119,6 +122,14 @@ class ThermalOperator:
     def jac_diag(self, T_lin, out):
         _lib.check(_lib.lib().sg_thermal_jac_diag(self.handle, _lib.ptr(T_lin), _lib.ptr(out), _lib.current_stream_ptr()))
         return out
+
+    def class_info(self) -> dict:
+        """Local-matrix classes found by the library (sg_thermal_class_info)."""
+        g, s_, f = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        rc = _lib.lib().sg_thermal_class_info(self.handle, C.byref(g), C.byref(s_), C.byref(f))
+        if rc < 0:
+            _lib.check(rc)
+        return dict(active=bool(rc), geometry=g.value, self=s_.value, facet=f.value)
 
     def apply_bytes(self) -> int:
         return int(_lib.lib().sg_thermal_apply_bytes(self.handle))

@@ -166,7 +166,16 @@ typedef struct {
     const double *bq_w, *bq_val;
     /* physics: main.py:29-55 / TM:18-27; penalty = 5.0 (TVP:313) */
     double dt, alpha, f, sigma, epsilon, htc, T_ambient, penalty;
+    /* Cells whose element contribution x_K . A_K x_K enters the fused x.Ax reduction of the solver: every
+     * global cell must be in this range on exactly one rank (CG slabs integrate a ghost column too).
+     * own_cell_lo == own_cell_hi means [cell_lo, cell_hi). */
+    int64_t own_cell_lo, own_cell_hi;
+    int32_t flags;                  /* SG_THERMAL_* */
 } sg_thermal_desc;
+
+enum {
+    SG_THERMAL_NO_CLASSES = 1       /* never use the local-matrix class tables (general per-cell-geometry kernel only) */
+};
 
 typedef struct sg_thermal_op sg_thermal_op;
 int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *desc, sg_thermal_op **out);
@@ -178,6 +187,10 @@ int sg_thermal_residual(sg_thermal_op *op, const double *T, const double *T_prev
 int sg_thermal_jac_apply(sg_thermal_op *op, const double *T_lin, const double *x, double *y, void *stream);
 /* diag J(T_lin) (Jacobi preconditioner; the reference uses GAMG, TVP:344). */
 int sg_thermal_jac_diag(sg_thermal_op *op, const double *T_lin, double *diag, void *stream);
+/* Local-matrix classes found at creation (cells with equal shape and neighbourhood share one
+ * precomputed element matrix; sg_thermal_jac_apply then reads no geometry).  Returns 1 when the class
+ * tables are in use, 0 when the mesh has too many classes and the general kernel runs, <0 on error. */
+int sg_thermal_class_info(const sg_thermal_op *op, int32_t *n_geometry, int32_t *n_self, int32_t *n_facet);
 /* Optional timing of the Jacobian-apply cell kernel with CUDA event pairs on its launch stream
  * (measurement harness only; at most `capacity` launches are recorded after each enable). */
 int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity);

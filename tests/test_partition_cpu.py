@@ -88,6 +88,15 @@ def _worker(rank, world, port, results):
             dist.all_reduce(loc)
             assert abs(loc[0].item() - float(np.dot(pert, yg))) <= 1e-9 * abs(float(np.dot(pert, yg)))
             assert int(loc[1].item()) == gs.n_nodes
+            # the solver's fused reduction: x_K . (A_K x_K) over each rank's OWN cells (sg_thermal_desc.own_cell_lo/hi)
+            # sums to the global x.Ax, i.e. every global cell is owned by exactly one rank
+            yo = kernel_mirror.jac_apply(space, tabs, fe.cell_geometry(m), fe.facet_topology(m, part["exterior_mask"]),
+                                         MAIN_PARAMS, 0.1, pert[l2g], T_lin=ug[l2g], cell_lo=part["own_cell_lo"],
+                                         cell_hi=part["own_cell_hi"])
+            cw = torch.tensor([float(np.dot(pert[l2g], yo))], dtype=torch.float64)
+            dist.all_reduce(cw)
+            assert abs(cw.item() - float(np.dot(pert, yg))) <= 1e-9 * abs(float(np.dot(pert, yg))), \
+                f"{family}{degree} d={dim}: cell-wise x.Ax does not tile"
             pts = torch.tensor([float(info["owned_cell_points"])], dtype=torch.float64)
             dist.all_reduce(pts)
             assert int(pts.item()) == gm.n_cells * space.n_ld

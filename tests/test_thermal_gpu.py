@@ -24,10 +24,10 @@ def make_mesh(dim):
     return msh.box_mesh(5, 4, 3, 5.0, 4.0, 3.0)
 
 
-def setup(sg_ctx, dim, family, degree, dt=0.1, params=MAIN_PARAMS):
+def setup(sg_ctx, dim, family, degree, dt=0.1, params=MAIN_PARAMS, use_classes=True):
     m = make_mesh(dim)
     space = fe.ScalarSpace(m, family, degree)
-    op = ThermalOperator(sg_ctx, space, params, dt)
+    op = ThermalOperator(sg_ctx, space, params, dt, use_classes=use_classes)
     orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, family, degree, params, dt)
     return m, space, op, orc
 
@@ -36,9 +36,15 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0")
 
 
+@pytest.mark.parametrize("use_classes", [True, False], ids=["class_tables", "per_cell_geometry"])
 @pytest.mark.parametrize("dim,family,degree", CASES)
-def test_operator_matches_assembled_oracle(sg_ctx, dim, family, degree):
-    m, space, op, orc = setup(sg_ctx, dim, family, degree)
+def test_operator_matches_assembled_oracle(sg_ctx, dim, family, degree, use_classes):
+    m, space, op, orc = setup(sg_ctx, dim, family, degree, use_classes=use_classes)
+    info = op.class_info()
+    assert info["active"] == use_classes          # the plates have a handful of cell shapes: the fast path must engage
+    if use_classes and dim > 1:
+        # Kuhn triangulation of a uniform box: d! cell shapes (rounding noise of the coordinates may split a few)
+        assert 1 <= info["geometry"] <= 4 * (2 if dim == 2 else 6), info
     rng = np.random.default_rng(dim * 10 + degree)
     n = space.n_nodes
     T = 700 + 100 * rng.random(n)
@@ -93,6 +99,45 @@ def test_time_steps_match_oracle_newton(sg_ctx, dim, family, degree):
         dT_d = T_d.cpu().numpy() - Tp_d.cpu().numpy()
         assert np.max(np.abs(dT_d - dT_o)) <= 1e-8 * np.max(np.abs(dT_o))
         Tp_d.copy_(T_d)
+
+
+@pytest.mark.parametrize("dim,family,degree", [(3, "DG", 1), (3, "CG", 2), (2, "DG", 2), (2, "CG", 1)])
+def test_fused_dot_product_of_the_solver(sg_ctx, dim, family, degree):
+    """The PCG iteration count and solution must not depend on which apply kernel runs (class tables with the
+    fused x.Ax reduction, or per-cell geometry + separate dot kernel)."""
+    res = {}
+    for uc in (True, False):
+        m, space, op, orc = setup(sg_ctx, dim, family, degree, use_classes=uc)
+        n = space.n_nodes
+        rng = np.random.default_rng(11)
+        T = np.full(n, 790.0) - rng.random(n)
+        b = rng.standard_normal(n)
+        Td, bd, xd = dev(T), dev(b), torch.zeros(n, dtype=torch.float64, device="cuda:0")
+        op.prepare_preconditioner(Td)
+        its, rr = op.pcg(Td, bd, xd, rtol=1e-12)
+        res[uc] = (its, xd.cpu().numpy())
+    assert abs(res[True][0] - res[False][0]) <= 1
+    assert np.max(np.abs(res[True][1] - res[False][1])) <= 1e-10 * np.max(np.abs(res[False][1]))
+
+
+def test_many_shapes_fall_back_to_per_cell_geometry(sg_ctx):
+    """A mesh whose cells all differ (randomly perturbed vertices) has too many classes for the shared-memory tables:
+    the library must keep the general kernel and still match the oracle."""
+    m = msh.box_mesh(7, 6, 5, 7.0, 6.0, 5.0)
+    rng = np.random.default_rng(0)
+    m.x += 0.05 * rng.standard_normal(m.x.shape)
+    space = fe.ScalarSpace(m, "DG", 1)
+    op = ThermalOperator(sg_ctx, space, MAIN_PARAMS, 0.1)
+    orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "DG", 1, MAIN_PARAMS, 0.1)
+    info = op.class_info()
+    assert not info["active"] and info["geometry"] == m.n_cells
+    n = space.n_nodes
+    T = 700 + 100 * rng.random(n)
+    x = rng.standard_normal(n)
+    out = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    y = op.jac_apply(dev(T), dev(x), out).cpu().numpy()
+    yo = orc.jacobian(T) @ x
+    assert np.max(np.abs(y - yo)) <= 1e-12 * np.max(np.abs(yo))
 
 
 def test_nonconvergence_is_reported(sg_ctx):
