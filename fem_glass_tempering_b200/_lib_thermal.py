@@ -24,7 +24,8 @@ class HaloSegmentC(C.Structure):
 
 class NewtonOptsC(C.Structure):
     _fields_ = [("newton_rtol", C.c_double), ("newton_atol", C.c_double), ("newton_max_it", C.c_int32),
-                ("lin_rtol", C.c_double), ("lin_atol", C.c_double), ("lin_max_it", C.c_int32)]
+                ("lin_rtol", C.c_double), ("lin_atol", C.c_double), ("lin_max_it", C.c_int32),
+                ("forcing_eta", C.c_double)]
 
 
 class NewtonStatsC(C.Structure):

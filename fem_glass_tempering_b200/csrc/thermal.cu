@@ -522,9 +522,22 @@ struct ClsDev {
 
 constexpr int CB = 256;  // threads per block of the class kernels
 
-template <int NLD>
+struct __align__(32) Row4 {
+    double v[4];
+};
+
+// One cell row (NLD contiguous doubles): 256-bit accesses (LDG.E.256 / STG.E.256, sm_100) when WIDE and
+// NLD is a multiple of 4, 128-bit when NLD is even, scalar otherwise.
+template <int NLD, bool WIDE>
 __device__ __forceinline__ void load_row(const double *__restrict__ p, double (&v)[NLD]) {
-    if constexpr (NLD % 2 == 0) {
+    if constexpr (WIDE && NLD % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NLD / 4; ++i) {
+            const Row4 t = reinterpret_cast<const Row4 *>(p)[i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[4 * i + k] = t.v[k];
+        }
+    } else if constexpr (NLD % 2 == 0) {
 #pragma unroll
         for (int i = 0; i < NLD / 2; ++i) {
             const double2 t = reinterpret_cast<const double2 *>(p)[i];
@@ -536,9 +549,17 @@ __device__ __forceinline__ void load_row(const double *__restrict__ p, double (&
         for (int i = 0; i < NLD; ++i) v[i] = p[i];
     }
 }
-template <int NLD>
+template <int NLD, bool WIDE>
 __device__ __forceinline__ void store_row(double *__restrict__ p, const double (&v)[NLD]) {
-    if constexpr (NLD % 2 == 0) {
+    if constexpr (WIDE && NLD % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NLD / 4; ++i) {
+            Row4 t;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t.v[k] = v[4 * i + k];
+            reinterpret_cast<Row4 *>(p)[i] = t;
+        }
+    } else if constexpr (NLD % 2 == 0) {
 #pragma unroll
         for (int i = 0; i < NLD / 2; ++i) reinterpret_cast<double2 *>(p)[i] = make_double2(v[2 * i], v[2 * i + 1]);
     } else {
@@ -547,11 +568,35 @@ __device__ __forceinline__ void store_row(double *__restrict__ p, const double (
     }
 }
 
+// acc[i] += sum_j A[i*NLD + j] * x[j] with A in shared memory (128-bit reads when the rows are 16-B aligned)
+template <int NLD>
+__device__ __forceinline__ void smem_matvec_acc(const double *__restrict__ A, const double (&x)[NLD], double (&acc)[NLD]) {
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        double a = acc[i];
+        if constexpr (NLD % 2 == 0) {
+            const double2 *row = reinterpret_cast<const double2 *>(A + i * NLD);
+#pragma unroll
+            for (int j = 0; j < NLD / 2; ++j) {
+                const double2 t = row[j];
+                a += t.x * x[2 * j];
+                a += t.y * x[2 * j + 1];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) a += A[i * NLD + j] * x[j];
+        }
+        acc[i] = a;
+    }
+}
+
 // DG fast apply: persistent grid-stride blocks, class tables in shared memory, fused x.y reduction.
-template <int NLD, int NNB>
+// A warp handles 32 consecutive cells; when these share their classes (the plate meshes number the cells
+// in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.
+template <int NLD, int NNB, bool WIDE>
 __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
                                                      SgRed red, double *dot_out, const int *skip) {
-    extern __shared__ double s_tab[];
+    extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
     const int ntab = (cd.n_self + cd.n_nb) * cd.S;
     for (int i = threadIdx.x; i < ntab; i += CB) s_tab[i] = cd.tab[i];
@@ -565,40 +610,26 @@ __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const doub
 #pragma unroll
         for (int f = 0; f < NNB; ++f) nb[f] = cd.nbr[(long)f * nc + c];
         double xk[NLD], yk[NLD];
-        load_row<NLD>(x + c * NLD, xk);
+        load_row<NLD, WIDE>(x + c * NLD, xk);
         double xn[NNB][NLD];
 #pragma unroll
         for (int f = 0; f < NNB; ++f) {
             if (nb[f] >= 0) {
-                load_row<NLD>(x + (long)nb[f] * NLD, xn[f]);
+                load_row<NLD, WIDE>(x + (long)nb[f] * NLD, xn[f]);
             } else {
 #pragma unroll
                 for (int j = 0; j < NLD; ++j) xn[f][j] = 0.0;
             }
         }
-        const double *As = s_tab + (int)(w & 0xFFFFull) * cd.S;
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-            double a = 0.0;
-#pragma unroll
-            for (int j = 0; j < NLD; ++j) a += As[i * NLD + j] * xk[j];
-            yk[i] = a;
-        }
+        for (int i = 0; i < NLD; ++i) yk[i] = 0.0;
+        smem_matvec_acc<NLD>(s_tab + (int)(w & 0xFFFFull) * cd.S, xk, yk);
 #pragma unroll
         for (int f = 0; f < NNB; ++f) {
             const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
-            if (u) {
-                const double *An = s_nb + (u - 1) * cd.S;
-#pragma unroll
-                for (int i = 0; i < NLD; ++i) {
-                    double a = yk[i];
-#pragma unroll
-                    for (int j = 0; j < NLD; ++j) a += An[i * NLD + j] * xn[f][j];
-                    yk[i] = a;
-                }
-            }
+            if (u) smem_matvec_acc<NLD>(s_nb + (u - 1) * cd.S, xn[f], yk);
         }
-        store_row<NLD>(y + c * NLD, yk);
+        store_row<NLD, WIDE>(y + c * NLD, yk);
 #pragma unroll
         for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
     }
@@ -610,7 +641,7 @@ __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const doub
 template <int NLD>
 __global__ void __launch_bounds__(CB) cg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
                                                      SgRed red, double *dot_out, const int *skip) {
-    extern __shared__ double s_tab[];
+    extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
     const int ntab = cd.n_self * cd.S;
     for (int i = threadIdx.x; i < ntab; i += CB) s_tab[i] = cd.tab[i];
@@ -625,14 +656,14 @@ __global__ void __launch_bounds__(CB) cg_class_apply(const ClsDev cd, const doub
         for (int i = 0; i < NLD; ++i) dof[i] = cd.dofmap[(long)i * nc + c];
 #pragma unroll
         for (int i = 0; i < NLD; ++i) xk[i] = x[dof[i]];
-        double d = 0.0;
+        double yk[NLD], d = 0.0;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) yk[i] = 0.0;
+        smem_matvec_acc<NLD>(As, xk, yk);
 #pragma unroll
         for (int i = 0; i < NLD; ++i) {
-            double a = 0.0;
-#pragma unroll
-            for (int j = 0; j < NLD; ++j) a += As[i * NLD + j] * xk[j];
-            atomicAdd(&y[dof[i]], a);
-            d += xk[i] * a;
+            atomicAdd(&y[dof[i]], yk[i]);
+            d += xk[i] * yk[i];
         }
         if (c >= cd.dot_lo && c < cd.dot_hi) dsum[0] += d;
     }
@@ -706,8 +737,11 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         // the class kernels always reduce x.y; without a consumer it lands in a scratch slot
         double *dst = dot2 ? dot2 : red.partials + 2 * SG_MAX_BLOCKS;
         ProfScope ps(op, mode, st);
-        if (DG)
-            dg_class_apply<NLD, D + 1><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+        const bool wide = (((uintptr_t)x | (uintptr_t)y) & 31) == 0;
+        if (DG && wide)
+            dg_class_apply<NLD, D + 1, true><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+        else if (DG)
+            dg_class_apply<NLD, D + 1, false><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
         else
             cg_class_apply<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
         SG_CHECK_CUDA(cudaGetLastError());
@@ -753,7 +787,7 @@ template <int D, int P, bool DG>
 int build_classes_t(sg_thermal_op *op) {
     using T = Tab<D, P, DG>;
     constexpr int NLD = T::NLD, NNB = DG ? D + 1 : 0;
-    constexpr int S = (NLD * NLD) | 1;  // odd stride: classes start in different shared-memory banks
+    constexpr int S = (NLD * NLD + 1) & ~1;  // even: every class matrix is 16-B aligned in shared memory
     const OpDev &dv = op->dev;
     const long nc = dv.n_cells;
     if (nc <= 0 || dv.cell_hi <= dv.cell_lo) return SG_OK;
@@ -809,8 +843,9 @@ int build_classes_t(sg_thermal_op *op) {
     // launch geometry: persistent blocks, as many as fit per SM
     int per_sm = 0;
     if (DG) {
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, (DG ? D + 1 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, (DG ? D + 1 : 1)>, CB, smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, (DG ? D + 1 : 1), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, (DG ? D + 1 : 1), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, (DG ? D + 1 : 1), true>, CB, smem));
     } else {
         SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_apply<NLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_class_apply<NLD>, CB, smem));

@@ -45,13 +45,15 @@ class NewtonSolverGPU:
         self.rtol, self.atol, self.max_it = 1e-12, 1e-10, 50
         self.report = False
         self.krylov_solver = _KrylovStub()
-        self.linear_rtol = 1e-10   # PCG residual target, relative to the first Newton residual of the step
+        self.linear_rtol = 1e-12   # final linear-residual target of a step, relative to the first Newton residual
+        self.forcing_eta = 1e-3    # inexact Newton: first forcing term (0 = every PCG solve runs to the target)
         self.last_stats = None
 
     def solve(self, u: Function):
         op = self._p._thermal_op
         op.opts.newton_rtol, op.opts.newton_atol, op.opts.newton_max_it = self.rtol, self.atol, self.max_it
         op.opts.lin_rtol = self.linear_rtol
+        op.opts.forcing_eta = self.forcing_eta
         try:
             st = op.timestep(u.x.array, self._p.functions_previous["T"].x.array)
         except _lib.SgError as e:

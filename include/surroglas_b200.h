@@ -215,9 +215,11 @@ typedef struct {
     double newton_rtol;   /* 1e-12, TVP:336 */
     double newton_atol;   /* 1e-10, dolfinx default */
     int32_t newton_max_it;/* 50, dolfinx default */
-    double lin_rtol;      /* relative residual of each PCG solve */
-    double lin_atol;
+    double lin_rtol;      /* final linear-residual target of the step, relative to |F(T_0)| */
+    double lin_atol;      /* absolute floor of that target */
     int32_t lin_max_it;
+    double forcing_eta;   /* > 0: inexact Newton, first forcing term eta_1 (Eisenstat-Walker choice 2 afterwards);
+                             0: every PCG solve runs to the final target (PETSc-like fixed tolerance) */
 } sg_newton_opts;
 
 typedef struct {
