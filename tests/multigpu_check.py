@@ -24,11 +24,13 @@ from fem_glass_tempering_b200 import mesh as msh  # noqa: E402
 PARAMS = {"f": 0.0, "epsilon": 0.93, "sigma": 5.670e-8, "T_ambient": 600.0, "T_0": 800.0, "alpha": 1.0, "htc": 280.1,
           "rho": 2500.0, "cp": 1433.0, "k": 1.0, "H": 627.8e3, "Tb": 869.0e0, "Rg": 8.314,
           "alpha_solid": 9.10e-6, "alpha_liquid": 25.10e-6, "Tf_init": 873.0}
+# (dim, cells per axis PER RANK, cell edge [mm], fe_config).  The reference's SIP penalty 5.0/h (TVP:313) does not
+# depend on the degree and is only coercive for P2 while the mass term dominates: the DG2 case uses 3 mm cells.
 CASES = [
-    (3, (6, 5, 3), {"T": {"element": "DG", "degree": 1}, "sigma": {"element": "DG", "degree": 1}}),
-    (3, (4, 4, 2), {"T": {"element": "CG", "degree": 2}, "sigma": {"element": "CG", "degree": 2}}),
-    (2, (9, 6), {"T": {"element": "CG", "degree": 2}, "sigma": {"element": "CG", "degree": 2}}),
-    (2, (8, 5), {"T": {"element": "DG", "degree": 2}, "sigma": {"element": "DG", "degree": 2}}),
+    (3, (6, 5, 3), 1.0, {"T": {"element": "DG", "degree": 1}, "sigma": {"element": "DG", "degree": 1}}),
+    (3, (4, 4, 2), 1.0, {"T": {"element": "CG", "degree": 2}, "sigma": {"element": "CG", "degree": 2}}),
+    (2, (9, 6), 1.0, {"T": {"element": "CG", "degree": 2}, "sigma": {"element": "CG", "degree": 2}}),
+    (2, (8, 5), 3.0, {"T": {"element": "DG", "degree": 2}, "sigma": {"element": "DG", "degree": 2}}),
 ]
 STEPS = 4
 
@@ -48,14 +50,21 @@ def main():
     ctx1 = _lib.Context(local) if rank == 0 else None
     ok = True
     report = []
-    for dim, n_per, cfg in CASES:
+    for dim, n_per, edge, cfg in CASES:
         n = (n_per[0] * world,) + tuple(n_per[1:])
-        lengths = tuple(float(k) for k in n)
+        lengths = tuple(edge * k for k in n)
         fam, deg = cfg["T"]["element"], cfg["T"]["degree"]
         m, part, info = distributed.slab_partition(dim, n, lengths, fam, deg, rank, world)
         prob = make_problem(m, cfg, ctx, part)
-        for _ in range(STEPS):
-            prob.solve_timestep(t=0.0)
+        try:
+            for _ in range(STEPS):
+                prob.solve_timestep(t=0.0)
+        except AssertionError as e:      # non-convergence is raised on every rank alike (all-reduced scalars)
+            ok = False
+            report.append(f"{fam}{deg} d={dim} n={n}: partitioned solve FAILED: {e}")
+            if rank == 0:
+                print(report[-1], flush=True)
+            continue
         space = prob.functionSpaces["T"].scalar
         own = slice(part["own_lo"], part["own_hi"])
         xl = space.tabulate_dof_coordinates()[own]
