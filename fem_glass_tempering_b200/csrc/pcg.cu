@@ -510,6 +510,7 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
     }
     int it = 0, done = rr0 > tol2 ? 0 : 1;
     double rr = rr0;
+    if (!done && (rc = sg_thermal_linearize(s->op, T_lin, st))) return rc;
     // Iterations are enqueued BATCH at a time without host synchronisation: the kernels test convergence
     // themselves (pcg_check) and the launches after the converged iteration return immediately.
     while (!done && it < max_it) {

@@ -42,6 +42,8 @@ struct SgRed {
 
 // y = J(T_lin) x fused with the owned-dof dot product: dot2[0] + dot2[1] = sum over owned dofs of x*y
 // (cells + exterior facets).  When *skip != 0 (device flag, may be NULL) every kernel returns at once.
+// Must precede sg_thermal_apply_dot whenever T_lin changed (refreshes the linearised boundary matrices).
+int sg_thermal_linearize(sg_thermal_op *op, const double *T_lin, cudaStream_t st);
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
                          const int *skip, cudaStream_t st);
 

@@ -510,6 +510,48 @@ __global__ void k_build_tables(const __grid_constant__ Tab<D, P, DG> tab, const 
     for (int i = 0; i < NLD; ++i) tab_out[(long)k * S + i * NLD + j] = yk[i];
 }
 
+__global__ void k_mark_exterior(long n_bf, long nc, const int32_t *bf_cell, const int32_t *bf_facet, int32_t *nbr_ext) {
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_bf) nbr_ext[(long)bf_facet[b] * nc + bf_cell[b]] = (int32_t)(-2 - b);
+}
+
+// P1: k-th dof on local facet f (the vertices other than f, ascending)
+__host__ __device__ constexpr int p1_facet_dof(int f, int k) { return k < f ? k : k + 1; }
+
+// Linearised Robin + radiation matrix of every exterior facet at the temperature T_lin (TVP:302-304), P1.
+// bmat[b][k <= l packed row-wise over the D facet dofs].
+template <int D, bool DG>
+__global__ void __launch_bounds__(TB) k_bfacet_mats(const OpDev op, const double *__restrict__ Tlin, double *__restrict__ bmat) {
+    constexpr int NLD = D + 1, NFD = D, NFDP = NFD * (NFD + 1) / 2;
+    const long b = (long)blockIdx.x * TB + threadIdx.x;
+    if (b >= op.n_bf) return;
+    const long c = op.bf_cell[b];
+    const int f = op.bf_facet[b];
+    const double area = op.bf_area[b];
+    double Tk[NLD], B[NFDP];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) Tk[i] = Tlin[DG ? c * NLD + i : (long)op.dofmap[(long)i * op.n_cells + c]];
+#pragma unroll
+    for (int k = 0; k < NFDP; ++k) B[k] = 0.0;
+    for (int q = 0; q < op.nqb; ++q) {
+        const double *ph = op.btab + ((long)f * op.nqb + q) * NLD;
+        double Tq = 0.0;
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) Tq += ph[j] * Tk[j];
+        const double coef = area * op.bw[q] * op.dt * 0.001 * (4.0 * op.se * Tq * Tq * Tq + op.htc);
+        double pf[NFD];
+#pragma unroll
+        for (int k = 0; k < NFD; ++k) pf[k] = ph[k < f ? k : k + 1];
+        int m = 0;
+#pragma unroll
+        for (int k = 0; k < NFD; ++k)
+#pragma unroll
+            for (int l = k; l < NFD; ++l) B[m++] += coef * pf[k] * pf[l];
+    }
+#pragma unroll
+    for (int k = 0; k < NFDP; ++k) bmat[b * NFDP + k] = B[k];
+}
+
 struct ClsDev {
     long n_cells, cell_lo, cell_hi, dot_lo, dot_hi;
     const int32_t *nbr;     // DG [NNB][n_cells]
@@ -518,6 +560,9 @@ struct ClsDev {
     const uint16_t *cls16;  // CG
     const double *tab;      // [(n_self + n_nb) * S]
     int n_self, n_nb, S;
+    // exterior facets handled inside the DG class kernel (P1): nbr holds -2 - b for exterior facet b and
+    // bmat[b] the packed symmetric matrix  dt*0.001*int (4 sigma eps T^3 + htc) phi_k phi_l ds  over the facet's dofs
+    const double *bmat;
 };
 
 constexpr int CB = 256;  // threads per block of the class kernels
@@ -593,7 +638,7 @@ __device__ __forceinline__ void smem_matvec_acc(const double *__restrict__ A, co
 // DG fast apply: persistent grid-stride blocks, class tables in shared memory, fused x.y reduction.
 // A warp handles 32 consecutive cells; when these share their classes (the plate meshes number the cells
 // in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.
-template <int NLD, int NNB, bool WIDE>
+template <int NLD, int NNB, bool WIDE, bool BND>
 __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
                                                      SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) double s_tab[];
@@ -603,7 +648,7 @@ __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const doub
     __syncthreads();
     const double *s_nb = s_tab + cd.n_self * cd.S;
     const long nc = cd.n_cells;
-    double dsum[1] = {0.0};
+    double dsum[2] = {0.0, 0.0};   // [1] stays 0: slot of the separate exterior-facet kernel (overwritten by it when it runs)
     for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
         const uint64_t w = cd.cls64[c];
         int nb[NNB];
@@ -628,12 +673,31 @@ __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const doub
         for (int f = 0; f < NNB; ++f) {
             const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
             if (u) smem_matvec_acc<NLD>(s_nb + (u - 1) * cd.S, xn[f], yk);
+            if constexpr (BND) {
+                if (nb[f] < -1) {   // exterior facet: y_K += B_f x_K on the facet's dofs (P1: NLD - 1 of them)
+                    constexpr int NFD = NLD - 1, NFDP = NFD * (NFD + 1) / 2;
+                    const double *Bp = cd.bmat + (long)(-2 - nb[f]) * NFDP;
+                    double B[NFDP];
+#pragma unroll
+                    for (int k = 0; k < NFDP; ++k) B[k] = Bp[k];
+                    int m = 0;
+#pragma unroll
+                    for (int k = 0; k < NFD; ++k)
+#pragma unroll
+                        for (int l = k; l < NFD; ++l) {
+                            const int ik = p1_facet_dof(f, k), il = p1_facet_dof(f, l);
+                            yk[ik] += B[m] * xk[il];
+                            if (l != k) yk[il] += B[m] * xk[ik];
+                            ++m;
+                        }
+                }
+            }
         }
         store_row<NLD, WIDE>(y + c * NLD, yk);
 #pragma unroll
         for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
     }
-    sg_grid_reduce<1>(dsum, red, dot_out);
+    sg_grid_reduce<2>(dsum, red, dot_out);
 }
 
 // CG fast apply: gather through the dofmap, class matrix from shared memory, scatter with RED.ADD.F64.
@@ -647,7 +711,7 @@ __global__ void __launch_bounds__(CB) cg_class_apply(const ClsDev cd, const doub
     for (int i = threadIdx.x; i < ntab; i += CB) s_tab[i] = cd.tab[i];
     __syncthreads();
     const long nc = cd.n_cells;
-    double dsum[1] = {0.0};
+    double dsum[2] = {0.0, 0.0};
     for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
         const double *As = s_tab + (int)cd.cls16[c] * cd.S;
         int dof[NLD];
@@ -667,7 +731,7 @@ __global__ void __launch_bounds__(CB) cg_class_apply(const ClsDev cd, const doub
         }
         if (c >= cd.dot_lo && c < cd.dot_hi) dsum[0] += d;
     }
-    sg_grid_reduce<1>(dsum, red, dot_out);
+    sg_grid_reduce<2>(dsum, red, dot_out);
 }
 
 }  // namespace
@@ -689,6 +753,9 @@ struct sg_thermal_op {
     size_t cls_smem;
     int32_t n_geom_classes;
     SgRed own_red;         // reduction scratch of sg_thermal_jac_apply (solver-less use of the fast path)
+    int32_t *nbr_ext;      // DG P1: neighbour ids with exterior facets encoded (see ClsDev::bmat)
+    double *bmat;
+    int (*linearize)(const sg_thermal_op *, const double *T_lin, cudaStream_t st);
     // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
     int prof_on, prof_n, prof_cap;
     cudaEvent_t *prof_ev;
@@ -738,11 +805,11 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         double *dst = dot2 ? dot2 : red.partials + 2 * SG_MAX_BLOCKS;
         ProfScope ps(op, mode, st);
         const bool wide = (((uintptr_t)x | (uintptr_t)y) & 31) == 0;
-        if (DG && wide)
-            dg_class_apply<NLD, D + 1, true><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
-        else if (DG)
-            dg_class_apply<NLD, D + 1, false><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
-        else
+        if constexpr (DG) {
+            auto k = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, true, true> : dg_class_apply<NLD, D + 1, false, true>)
+                              : (wide ? dg_class_apply<NLD, D + 1, true, false> : dg_class_apply<NLD, D + 1, false, false>);
+            k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+        } else
             cg_class_apply<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
@@ -755,7 +822,9 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         sg_count_launch();
     }
     const bool bdot = fast && dot2;
-    if (dv.n_bf > 0 || bdot) {
+    if (fast && op->bmat) {
+        // exterior facets were applied inside the class kernel
+    } else if (dv.n_bf > 0 || bdot) {
         if (mode == MODE_APPLY && bdot) bfacet_kernel<D, P, DG, MODE_APPLY, true><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, dot2 + 1, skip);
         if (mode == MODE_APPLY && !bdot) bfacet_kernel<D, P, DG, MODE_APPLY, false><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, nullptr, skip);
         if (mode == MODE_RESID) bfacet_kernel<D, P, DG, MODE_RESID, false><<<gb, TB, 0, st>>>(dv, x, nullptr, y, red, nullptr, nullptr);
@@ -768,6 +837,19 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         k_dot_range<<<capped_grid(hi - lo, 256), 256, 0, st>>>(lo, hi, x, y, red, dot2, skip);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
+    }
+    return SG_OK;
+}
+
+// Refresh the per-facet boundary matrices for a new linearisation point (no-op unless they are in use).
+template <int D, int P, bool DG>
+int linearize_t(const sg_thermal_op *op, const double *T_lin, cudaStream_t st) {
+    if constexpr (P == 1) {
+        if (op->bmat && op->dev.n_bf > 0) {
+            k_bfacet_mats<D, DG><<<(unsigned)((op->dev.n_bf + TB - 1) / TB), TB, 0, st>>>(op->dev, T_lin, op->bmat);
+            SG_CHECK_CUDA(cudaGetLastError());
+            sg_count_launch();
+        }
     }
     return SG_OK;
 }
@@ -843,9 +925,12 @@ int build_classes_t(sg_thermal_op *op) {
     // launch geometry: persistent blocks, as many as fit per SM
     int per_sm = 0;
     if (DG) {
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, (DG ? D + 1 : 1), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, (DG ? D + 1 : 1), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, (DG ? D + 1 : 1), true>, CB, smem));
+        constexpr int NB = DG ? D + 1 : 1;
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, NB, true, true>, CB, smem));
     } else {
         SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_apply<NLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_class_apply<NLD>, CB, smem));
@@ -876,6 +961,20 @@ int build_classes_t(sg_thermal_op *op) {
     cd.n_self = NS;
     cd.n_nb = NF;
     cd.S = S;
+    cd.bmat = nullptr;
+    if (DG && P == 1 && dv.n_bf > 0) {
+        // exterior facets inside the class kernel: own copy of the neighbour ids with the facets encoded
+        constexpr int NFDP = D * (D + 1) / 2;
+        SG_CHECK_CUDA(cudaMalloc(&op->nbr_ext, sizeof(int32_t) * (size_t)nc * NNB));
+        SG_CHECK_CUDA(cudaMemcpy(op->nbr_ext, dv.nbr, sizeof(int32_t) * (size_t)nc * NNB, cudaMemcpyDeviceToDevice));
+        k_mark_exterior<<<(unsigned)((dv.n_bf + 255) / 256), 256>>>(dv.n_bf, nc, dv.bf_cell, dv.bf_facet, op->nbr_ext);
+        SG_CHECK_CUDA(cudaGetLastError());
+        SG_CHECK_CUDA(cudaMalloc(&op->bmat, sizeof(double) * (size_t)dv.n_bf * NFDP));
+        SG_CHECK_CUDA(cudaMemset(op->bmat, 0, sizeof(double) * (size_t)dv.n_bf * NFDP));
+        SG_CHECK_CUDA(cudaDeviceSynchronize());
+        cd.nbr = op->nbr_ext;
+        cd.bmat = op->bmat;
+    }
     cd.tab = op->cls_tab;  // set last: marks the fast path as available
     return SG_OK;
 }
@@ -904,6 +1003,7 @@ int build_tab(sg_thermal_op *op) {
     op->tab_bytes = sizeof(T);
     op->launch = &launch_op<D, P, DG>;
     op->build_classes = &build_classes_t<D, P, DG>;
+    op->linearize = &linearize_t<D, P, DG>;
     return SG_OK;
 }
 
@@ -932,6 +1032,8 @@ void sg_op_info(const sg_thermal_op *op, SgOpInfo *o) {
     o->detJ = op->d.geom + (int64_t)op->d.dim * op->d.dim * op->d.n_cells;
     o->mass_inv = op->mass_inv;
 }
+
+int sg_thermal_linearize(sg_thermal_op *op, const double *T_lin, cudaStream_t st) { return op->linearize(op, T_lin, st); }
 
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
                          const int *skip, cudaStream_t st) {
@@ -1057,6 +1159,8 @@ int sg_thermal_op_destroy(sg_thermal_op *op) {
     if (op->bw_dev) cudaFree(op->bw_dev);
     if (op->cls_tab) cudaFree(op->cls_tab);
     if (op->cls_words) cudaFree(op->cls_words);
+    if (op->nbr_ext) cudaFree(op->nbr_ext);
+    if (op->bmat) cudaFree(op->bmat);
     if (op->own_red.partials) cudaFree(op->own_red.partials);
     if (op->own_red.counter) cudaFree(op->own_red.counter);
     for (int i = 0; i < 2 * op->prof_cap; ++i) cudaEventDestroy(op->prof_ev[i]);
@@ -1081,6 +1185,8 @@ int sg_thermal_jac_apply(sg_thermal_op *op, const double *T_lin, const double *x
         SG_CHECK_CUDA(cudaMalloc(&op->own_red.counter, sizeof(unsigned)));
         SG_CHECK_CUDA(cudaMemset(op->own_red.counter, 0, sizeof(unsigned)));
     }
+    int rc = op->linearize(op, T_lin, (cudaStream_t)stream);
+    if (rc) return rc;
     return op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, op->own_red, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -1140,7 +1246,8 @@ int64_t sg_thermal_apply_bytes(const sg_thermal_op *op) {
         if (d.family == 1) per_cell += 8 + 4 * (d.dim + 1) + 4;  // h, neighbour ids, packed facet info
         else per_cell += 4 * d.n_ld;                            // dofmap
     }
-    return ncell * per_cell + 16 * ndof;                        // + read x, write y
+    const int64_t bnd = op->bmat ? d.n_bfacets * 8 * (d.dim * (d.dim + 1) / 2) : 0;   // packed facet matrices
+    return ncell * per_cell + 16 * ndof + bnd;                  // + read x, write y
 }
 
 }  // extern "C"

@@ -226,3 +226,27 @@ def test_minimal_materialisation_matches_full(sg_ctx):
         assert rel_err(cpu(a.functions_next[k]), cpu(b.functions_next[k])) <= 1e-10, k
     with pytest.raises(RuntimeError):
         b.functions["ds_partial"].x.array
+
+
+def test_field_writer_records_every_step(sg_ctx, tmp_path):
+    """output_dir switches on the per-step output of TVP:357-364: T, phi, Tf, xi, sigma captured after the
+    viscoelastic update and before T_prev <- T_cur, through pinned double buffers on a side stream."""
+    from fem_glass_tempering_b200.output import read_series
+    prob = ThermoViscoProblem(mesh_path="", time=(0.0, 0.5), dt=0.1, config=MAIN_CONFIG, model_parameters=MAIN_PARAMS,
+                              mesh=msh.graded_line_mesh(), ctx=sg_ctx, verbose=False)
+    prob.output_dir = str(tmp_path / "output")
+    prob.setup(dirichlet_bc=False)
+    snaps = {k: [cpu(f).copy()] for k, f in (("T", prob.functions_current["T"]), ("sigma", prob.functions_next["sigma"]))}
+    for _ in range(prob.n_steps):
+        prob.t += prob.dt
+        prob.solve_timestep(t=prob.t)
+        snaps["T"].append(cpu(prob.functions_current["T"]).copy())
+        snaps["sigma"].append(cpu(prob.functions_next["sigma"]).copy())
+    prob._finalize()
+    for key in ("T", "sigma"):
+        t, v = read_series(prob.output_dir, key)
+        assert len(t) == prob.n_steps + 1 and abs(t[-1] - 0.5) < 1e-12
+        for a, b in zip(v, snaps[key]):
+            assert_same(a, b, f"written {key}")
+    t, xi = read_series(prob.output_dir, "xi")
+    assert xi.shape == (prob.n_steps + 1, prob.functionSpaces["T"].n_nodes)
