@@ -515,33 +515,61 @@ __global__ void k_mark_exterior(long n_bf, long nc, const int32_t *bf_cell, cons
     if (b < n_bf) nbr_ext[(long)bf_facet[b] * nc + bf_cell[b]] = (int32_t)(-2 - b);
 }
 
-// P1: k-th dof on local facet f (the vertices other than f, ascending)
-__host__ __device__ constexpr int p1_facet_dof(int f, int k) { return k < f ? k : k + 1; }
+// Dofs on local facet f (fe.py LagrangeElement.facet_dofs): the vertices other than f, ascending, then (P2) the
+// edges joining two of them in the order of ref_edges(dim).  Basis functions of all other dofs vanish on f.
+__host__ __device__ constexpr int nfd_of(int D, int P) { return P == 1 ? D : D * (D + 1) / 2; }
+__host__ __device__ constexpr int ref_edge_vertex(int D, int e, int side) {
+    // ref_edges: 1-D (0,1); 2-D (1,2),(0,2),(0,1); 3-D (2,3),(1,3),(1,2),(0,3),(0,2),(0,1)
+    if (D == 1) return side;
+    if (D == 2) return side == 0 ? (e == 0 ? 1 : 0) : (e == 2 ? 1 : 2);
+    const int a[6] = {2, 1, 1, 0, 0, 0}, b[6] = {3, 3, 2, 3, 2, 1};
+    return side == 0 ? a[e] : b[e];
+}
+__host__ __device__ constexpr int facet_dof(int D, int P, int f, int k) {
+    if (k < D) return k < f ? k : k + 1;
+    if (P == 1) return -1;
+    int m = D;
+    const int ne = D * (D + 1) / 2;
+    for (int e = 0; e < ne; ++e) {
+        if (ref_edge_vertex(D, e, 0) == f || ref_edge_vertex(D, e, 1) == f) continue;
+        if (m == k) return D + 1 + e;
+        ++m;
+    }
+    return -1;
+}
 
-// Linearised Robin + radiation matrix of every exterior facet at the temperature T_lin (TVP:302-304), P1.
-// bmat[b][k <= l packed row-wise over the D facet dofs].
-template <int D, bool DG>
+// Linearised Robin + radiation matrix of every exterior facet at the temperature T_lin (TVP:302-304):
+// bmat[b][k <= l packed row-wise over the facet's dofs] = dt*0.001 * int (4 sigma eps T^3 + htc) phi_k phi_l ds.
+template <int D, int P, bool DG>
 __global__ void __launch_bounds__(TB) k_bfacet_mats(const OpDev op, const double *__restrict__ Tlin, double *__restrict__ bmat) {
-    constexpr int NLD = D + 1, NFD = D, NFDP = NFD * (NFD + 1) / 2;
+    constexpr int NLD = nld_of(D, P), NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
     const long b = (long)blockIdx.x * TB + threadIdx.x;
     if (b >= op.n_bf) return;
     const long c = op.bf_cell[b];
     const int f = op.bf_facet[b];
     const double area = op.bf_area[b];
-    double Tk[NLD], B[NFDP];
+    int fd[NFD];
 #pragma unroll
-    for (int i = 0; i < NLD; ++i) Tk[i] = Tlin[DG ? c * NLD + i : (long)op.dofmap[(long)i * op.n_cells + c]];
+    for (int k = 0; k < NFD; ++k) {
+        fd[k] = 0;
+#pragma unroll
+        for (int ff = 0; ff < D + 1; ++ff)
+            if (ff == f) fd[k] = facet_dof(D, P, ff, k);
+    }
+    double Tk[NFD], B[NFDP];
+#pragma unroll
+    for (int k = 0; k < NFD; ++k) Tk[k] = Tlin[DG ? c * NLD + fd[k] : (long)op.dofmap[(long)fd[k] * op.n_cells + c]];
 #pragma unroll
     for (int k = 0; k < NFDP; ++k) B[k] = 0.0;
     for (int q = 0; q < op.nqb; ++q) {
         const double *ph = op.btab + ((long)f * op.nqb + q) * NLD;
-        double Tq = 0.0;
+        double pf[NFD], Tq = 0.0;
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) Tq += ph[j] * Tk[j];
+        for (int k = 0; k < NFD; ++k) {
+            pf[k] = ph[fd[k]];
+            Tq += pf[k] * Tk[k];
+        }
         const double coef = area * op.bw[q] * op.dt * 0.001 * (4.0 * op.se * Tq * Tq * Tq + op.htc);
-        double pf[NFD];
-#pragma unroll
-        for (int k = 0; k < NFD; ++k) pf[k] = ph[k < f ? k : k + 1];
         int m = 0;
 #pragma unroll
         for (int k = 0; k < NFD; ++k)
@@ -550,6 +578,51 @@ __global__ void __launch_bounds__(TB) k_bfacet_mats(const OpDev op, const double
     }
 #pragma unroll
     for (int k = 0; k < NFDP; ++k) bmat[b * NFDP + k] = B[k];
+}
+
+// CG: y += B_f x on the facet's dofs from the precomputed matrices (the DG class kernel does this inline);
+// reduces x.(B_f x) over facets of the cells [dot_lo, dot_hi).
+template <int D, int P>
+__global__ void __launch_bounds__(TB) cg_bfacet_apply(const OpDev op, const double *__restrict__ bmat, const double *__restrict__ x,
+                                                      double *__restrict__ y, SgRed red, double *dot_out, const int *skip) {
+    constexpr int NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
+    if (skip && *skip) return;
+    double dsum[1] = {0.0};
+    for (long b = (long)blockIdx.x * TB + threadIdx.x; b < op.n_bf; b += (long)gridDim.x * TB) {
+        const long c = op.bf_cell[b];
+        if (c < op.cell_lo || c >= op.cell_hi) continue;
+        const int f = op.bf_facet[b];
+        long dof[NFD];
+        double xk[NFD], yk[NFD], B[NFDP];
+#pragma unroll
+        for (int k = 0; k < NFD; ++k) {
+            int fd = 0;
+#pragma unroll
+            for (int ff = 0; ff < D + 1; ++ff)
+                if (ff == f) fd = facet_dof(D, P, ff, k);
+            dof[k] = op.dofmap[(long)fd * op.n_cells + c];
+            xk[k] = x[dof[k]];
+            yk[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < NFDP; ++k) B[k] = bmat[b * NFDP + k];
+        int m = 0;
+#pragma unroll
+        for (int k = 0; k < NFD; ++k)
+#pragma unroll
+            for (int l = k; l < NFD; ++l) {
+                yk[k] += B[m] * xk[l];
+                if (l != k) yk[l] += B[m] * xk[k];
+                ++m;
+            }
+        const bool counted = c >= op.dot_lo && c < op.dot_hi;
+#pragma unroll
+        for (int k = 0; k < NFD; ++k) {
+            atomicAdd(&y[dof[k]], yk[k]);
+            if (counted) dsum[0] += xk[k] * yk[k];
+        }
+    }
+    sg_grid_reduce<1>(dsum, red, dot_out);
 }
 
 struct ClsDev {
@@ -638,7 +711,7 @@ __device__ __forceinline__ void smem_matvec_acc(const double *__restrict__ A, co
 // DG fast apply: persistent grid-stride blocks, class tables in shared memory, fused x.y reduction.
 // A warp handles 32 consecutive cells; when these share their classes (the plate meshes number the cells
 // in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.
-template <int NLD, int NNB, bool WIDE, bool BND>
+template <int NLD, int NNB, int P, bool WIDE, bool BND>
 __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
                                                      SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) double s_tab[];
@@ -674,8 +747,8 @@ __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const doub
             const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
             if (u) smem_matvec_acc<NLD>(s_nb + (u - 1) * cd.S, xn[f], yk);
             if constexpr (BND) {
-                if (nb[f] < -1) {   // exterior facet: y_K += B_f x_K on the facet's dofs (P1: NLD - 1 of them)
-                    constexpr int NFD = NLD - 1, NFDP = NFD * (NFD + 1) / 2;
+                if (nb[f] < -1) {   // exterior facet: y_K += B_f x_K on the facet's dofs
+                    constexpr int D = NNB - 1, NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
                     const double *Bp = cd.bmat + (long)(-2 - nb[f]) * NFDP;
                     double B[NFDP];
 #pragma unroll
@@ -685,7 +758,7 @@ __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const doub
                     for (int k = 0; k < NFD; ++k)
 #pragma unroll
                         for (int l = k; l < NFD; ++l) {
-                            const int ik = p1_facet_dof(f, k), il = p1_facet_dof(f, l);
+                            const int ik = facet_dof(D, P, f, k), il = facet_dof(D, P, f, l);
                             yk[ik] += B[m] * xk[il];
                             if (l != k) yk[il] += B[m] * xk[ik];
                             ++m;
@@ -806,8 +879,8 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         ProfScope ps(op, mode, st);
         const bool wide = (((uintptr_t)x | (uintptr_t)y) & 31) == 0;
         if constexpr (DG) {
-            auto k = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, true, true> : dg_class_apply<NLD, D + 1, false, true>)
-                              : (wide ? dg_class_apply<NLD, D + 1, true, false> : dg_class_apply<NLD, D + 1, false, false>);
+            auto k = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true> : dg_class_apply<NLD, D + 1, P, false, true>)
+                              : (wide ? dg_class_apply<NLD, D + 1, P, true, false> : dg_class_apply<NLD, D + 1, P, false, false>);
             k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
         } else
             cg_class_apply<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
@@ -822,8 +895,15 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         sg_count_launch();
     }
     const bool bdot = fast && dot2;
-    if (fast && op->bmat) {
+    if (fast && op->bmat && DG) {
         // exterior facets were applied inside the class kernel
+    } else if (fast && op->bmat) {
+        if constexpr (!DG) {
+            double *dst = dot2 ? dot2 + 1 : red.partials + 2 * SG_MAX_BLOCKS;
+            cg_bfacet_apply<D, P><<<gb, TB, 0, st>>>(dv, op->bmat, x, y, red, dst, skip);
+            SG_CHECK_CUDA(cudaGetLastError());
+            sg_count_launch();
+        }
     } else if (dv.n_bf > 0 || bdot) {
         if (mode == MODE_APPLY && bdot) bfacet_kernel<D, P, DG, MODE_APPLY, true><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, dot2 + 1, skip);
         if (mode == MODE_APPLY && !bdot) bfacet_kernel<D, P, DG, MODE_APPLY, false><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, nullptr, skip);
@@ -844,12 +924,10 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
 // Refresh the per-facet boundary matrices for a new linearisation point (no-op unless they are in use).
 template <int D, int P, bool DG>
 int linearize_t(const sg_thermal_op *op, const double *T_lin, cudaStream_t st) {
-    if constexpr (P == 1) {
-        if (op->bmat && op->dev.n_bf > 0) {
-            k_bfacet_mats<D, DG><<<(unsigned)((op->dev.n_bf + TB - 1) / TB), TB, 0, st>>>(op->dev, T_lin, op->bmat);
-            SG_CHECK_CUDA(cudaGetLastError());
-            sg_count_launch();
-        }
+    if (op->bmat && op->dev.n_bf > 0) {
+        k_bfacet_mats<D, P, DG><<<(unsigned)((op->dev.n_bf + TB - 1) / TB), TB, 0, st>>>(op->dev, T_lin, op->bmat);
+        SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
     }
     return SG_OK;
 }
@@ -925,12 +1003,12 @@ int build_classes_t(sg_thermal_op *op) {
     // launch geometry: persistent blocks, as many as fit per SM
     int per_sm = 0;
     if (DG) {
-        constexpr int NB = DG ? D + 1 : 1;
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, NB, true, true>, CB, smem));
+        constexpr int NB = D + 1;
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, NB, P, true, true>, CB, smem));
     } else {
         SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_apply<NLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_class_apply<NLD>, CB, smem));
@@ -962,17 +1040,20 @@ int build_classes_t(sg_thermal_op *op) {
     cd.n_nb = NF;
     cd.S = S;
     cd.bmat = nullptr;
-    if (DG && P == 1 && dv.n_bf > 0) {
-        // exterior facets inside the class kernel: own copy of the neighbour ids with the facets encoded
-        constexpr int NFDP = D * (D + 1) / 2;
-        SG_CHECK_CUDA(cudaMalloc(&op->nbr_ext, sizeof(int32_t) * (size_t)nc * NNB));
-        SG_CHECK_CUDA(cudaMemcpy(op->nbr_ext, dv.nbr, sizeof(int32_t) * (size_t)nc * NNB, cudaMemcpyDeviceToDevice));
-        k_mark_exterior<<<(unsigned)((dv.n_bf + 255) / 256), 256>>>(dv.n_bf, nc, dv.bf_cell, dv.bf_facet, op->nbr_ext);
-        SG_CHECK_CUDA(cudaGetLastError());
+    if (dv.n_bf > 0) {
+        // exterior facets from per-facet linearised boundary matrices (sg_thermal_linearize); DG applies them inside
+        // the class kernel through its own copy of the neighbour ids with the exterior facets encoded
+        constexpr int NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
+        if (DG) {
+            SG_CHECK_CUDA(cudaMalloc(&op->nbr_ext, sizeof(int32_t) * (size_t)nc * NNB));
+            SG_CHECK_CUDA(cudaMemcpy(op->nbr_ext, dv.nbr, sizeof(int32_t) * (size_t)nc * NNB, cudaMemcpyDeviceToDevice));
+            k_mark_exterior<<<(unsigned)((dv.n_bf + 255) / 256), 256>>>(dv.n_bf, nc, dv.bf_cell, dv.bf_facet, op->nbr_ext);
+            SG_CHECK_CUDA(cudaGetLastError());
+            cd.nbr = op->nbr_ext;
+        }
         SG_CHECK_CUDA(cudaMalloc(&op->bmat, sizeof(double) * (size_t)dv.n_bf * NFDP));
         SG_CHECK_CUDA(cudaMemset(op->bmat, 0, sizeof(double) * (size_t)dv.n_bf * NFDP));
         SG_CHECK_CUDA(cudaDeviceSynchronize());
-        cd.nbr = op->nbr_ext;
         cd.bmat = op->bmat;
     }
     cd.tab = op->cls_tab;  // set last: marks the fast path as available
@@ -1246,7 +1327,8 @@ int64_t sg_thermal_apply_bytes(const sg_thermal_op *op) {
         if (d.family == 1) per_cell += 8 + 4 * (d.dim + 1) + 4;  // h, neighbour ids, packed facet info
         else per_cell += 4 * d.n_ld;                            // dofmap
     }
-    const int64_t bnd = op->bmat ? d.n_bfacets * 8 * (d.dim * (d.dim + 1) / 2) : 0;   // packed facet matrices
+    const int nfd = d.degree == 1 ? d.dim : d.dim * (d.dim + 1) / 2;
+    const int64_t bnd = (op->bmat && d.family == 1) ? d.n_bfacets * 8 * (nfd * (nfd + 1) / 2) : 0;   // packed facet matrices (DG: same kernel)
     return ncell * per_cell + 16 * ndof + bnd;                  // + read x, write y
 }
 
