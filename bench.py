@@ -223,6 +223,8 @@ def run_gpu(args):
     prob.setup(dirichlet_bc=False)
     t_setup = time.time() - t_setup
     op = prob._thermal_op
+    if args.cheb is not None:
+        op.set_chebyshev(args.cheb)
     L = _lib.lib()
     nT = prob.functionSpaces["T"].n_nodes
     nS = prob.functionSpaces["sigma"].n_nodes
@@ -329,7 +331,11 @@ def run_gpu(args):
                    "plate_mm": list(lengths), "partition": f"x-slabs over {world} GPU(s)",
                    "cache": "state per GPU (>17 GB) is far larger than the 126 MB L2; no L2 flush needed",
                    "newton_its_per_step": newton_its / args.steps, "pcg_its_per_step": lin_its / args.steps,
-                   "setup_s": round(t_setup, 1), "local_matrix_classes": cls},
+                   "setup_s": round(t_setup, 1), "local_matrix_classes": cls,
+                   "preconditioner": (f"Chebyshev degree {op.chebyshev_info()['degree']} in M^-1 J on "
+                                      f"[{op.chebyshev_info()['lo']:.3g}, {op.chebyshev_info()['hi']:.3g}] (pcg its = outer iterations)"
+                                      if op.chebyshev_info()["degree"] else
+                                      ("element-mass blocks" if fam == "DG" else "point Jacobi"))},
         "timesteps_per_s": args.steps / (ms_total * 1e-3),
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
@@ -361,6 +367,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cheb", type=int, default=None, help="Chebyshev preconditioner degree of the DG solver (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -52,6 +52,8 @@ def bind(L) -> None:
     L.sg_thermal_solver_workspace_doubles.restype = C.c_int64
     L.sg_thermal_solver_create.argtypes = [vp, vp, vp, C.POINTER(vp)]
     L.sg_thermal_solver_destroy.argtypes = [vp]
+    L.sg_thermal_solver_set_chebyshev.argtypes = [vp, C.c_int32, C.c_double, C.c_double]
+    L.sg_thermal_solver_get_chebyshev.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.sg_pcg_solve.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_int32),
                                C.POINTER(C.c_double), vp]
     L.sg_thermal_timestep.argtypes = [vp, vp, vp, C.POINTER(NewtonOptsC), C.POINTER(NewtonStatsC), vp]

@@ -253,6 +253,130 @@ __global__ void __launch_bounds__(VB) k_update_p_blk(const __grid_constant__ Mas
     if (blockIdx.x == 0 && threadIdx.x == 0) pcg_check(ctrl, Snext, tol2, it);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chebyshev-polynomial preconditioned CG (DG): z = q_k(M^-1 J) M^-1 r from k fused operator steps
+// (thermal.cu dg_cheb_step).  The vector kernels around it:
+//   init:   x = 0, r = b, z1 = M^-1 b / theta, |b|^2
+//   x,r:    x += alpha p, r -= alpha Ap, z1 = M^-1 r / theta, |r|^2
+//   p:      p = z + beta p
+template <int NLD>
+__global__ void __launch_bounds__(VB) k_pcg_init_cheb(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
+                                                      const double *__restrict__ detJ, const double *__restrict__ b,
+                                                      double *__restrict__ x, double *__restrict__ r, double *__restrict__ z1,
+                                                      double inv_theta, Red red, double *S1, PcgCtrl *ctrl) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctrl->done = 0;
+        ctrl->iters = 0;
+        ctrl->rr = 0.0;
+    }
+    double acc[1] = {0.0};
+    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
+        double rk[NLD], zk[NLD], zero[NLD];
+        ld_row<NLD>(b + c * NLD, rk);
+        mass_solve<NLD>(mi, inv_theta / detJ[c], rk, zk);
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) zero[i] = 0.0;
+        st_row<NLD>(x + c * NLD, zero);
+        st_row<NLD>(r + c * NLD, rk);
+        st_row<NLD>(z1 + c * NLD, zk);
+        if (c >= clo && c < chi) {
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) acc[0] += rk[i] * rk[i];
+        }
+    }
+    grid_reduce<1>(acc, red, S1);
+}
+
+template <int NLD>
+__global__ void __launch_bounds__(VB) k_update_xr_cheb(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
+                                                       const double *__restrict__ detJ, const double *__restrict__ p,
+                                                       const double *__restrict__ Ap, double *__restrict__ x,
+                                                       double *__restrict__ r, double *__restrict__ z1, double inv_theta,
+                                                       Red red, const double *Scur, const double *SpAp, double *Snext1,
+                                                       const PcgCtrl *ctrl) {
+    if (ctrl->done) return;
+    const double alpha = Scur[0] / (SpAp[0] + SpAp[1]);
+    double acc[1] = {0.0};
+    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
+        double pk[NLD], ak[NLD], xk[NLD], rk[NLD], zk[NLD];
+        ld_row<NLD>(p + c * NLD, pk);
+        ld_row<NLD>(Ap + c * NLD, ak);
+        ld_row<NLD>(x + c * NLD, xk);
+        ld_row<NLD>(r + c * NLD, rk);
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            xk[i] += alpha * pk[i];
+            rk[i] -= alpha * ak[i];
+        }
+        mass_solve<NLD>(mi, inv_theta / detJ[c], rk, zk);
+        st_row<NLD>(x + c * NLD, xk);
+        st_row<NLD>(r + c * NLD, rk);
+        st_row<NLD>(z1 + c * NLD, zk);
+        if (c >= clo && c < chi) {
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) acc[0] += rk[i] * rk[i];
+        }
+    }
+    grid_reduce<1>(acc, red, Snext1);
+}
+
+__global__ void k_pcg_check(PcgCtrl *ctrl, const double *Snext, double tol2, int it) {
+    if (!ctrl->done) pcg_check(ctrl, Snext, tol2, it);
+}
+
+// p = z + beta p, beta = Snext[0]/Scur[0]  (first == 1: p = z)
+__global__ void __launch_bounds__(VB) k_axpy_p(long n, const double *__restrict__ z, double *__restrict__ p, const double *Scur,
+                                               const double *Snext, int first, const PcgCtrl *ctrl) {
+    if (ctrl->done) return;
+    const double beta = first ? 0.0 : Snext[0] / Scur[0];
+    const long n2 = n >> 1;
+    const double2 *z2 = reinterpret_cast<const double2 *>(z);
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n2; i += (long)gridDim.x * VB) {
+        const double2 a = z2[i];
+        double2 q = first ? make_double2(0.0, 0.0) : p2[i];
+        q.x = a.x + beta * q.x;
+        q.y = a.y + beta * q.y;
+        p2[i] = q;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = z[n - 1] + (first ? 0.0 : beta * p[n - 1]);
+}
+
+// power iteration for the largest eigenvalue of M^-1 J:  v = scale * M^-1 w,  out = |v|^2 over owned cells
+template <int NLD>
+__global__ void __launch_bounds__(VB) k_precond_scale(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
+                                                      const double *__restrict__ detJ, const double *__restrict__ w,
+                                                      double scale, double *__restrict__ v, Red red, double *out) {
+    double acc[1] = {0.0};
+    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
+        double wk[NLD], vk[NLD];
+        ld_row<NLD>(w + c * NLD, wk);
+        mass_solve<NLD>(mi, scale / detJ[c], wk, vk);
+        st_row<NLD>(v + c * NLD, vk);
+        if (c >= clo && c < chi) {
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) acc[0] += vk[i] * vk[i];
+        }
+    }
+    grid_reduce<1>(acc, red, out);
+}
+
+// deterministic pseudo-random start vector in (-1, 1) from the GLOBAL dof index (same field for every partition)
+__global__ void __launch_bounds__(VB) k_hash_fill(long n, long global_offset, long lo, long hi, double *__restrict__ v, Red red,
+                                                  double *out) {
+    double acc[1] = {0.0};
+    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
+        unsigned long long h = (unsigned long long)(i + global_offset) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+        h *= 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 32;
+        const double val = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        v[i] = val;
+        if (owned(i, lo, hi)) acc[0] += val * val;
+    }
+    grid_reduce<1>(acc, red, out);
+}
+
 inline unsigned vgrid(long n) {
     long g = (n + VB - 1) / VB;
     if (g < 1) g = 1;
@@ -260,6 +384,26 @@ inline unsigned vgrid(long n) {
 }
 
 }  // namespace
+
+// Tolerance policy of one PCG solve: the |r|^2 target as a function of |b|^2, which is only known after
+// the first reduction.  Returning >= |b|^2 means "nothing to do": zero iterations, x = 0.
+struct PcgTol {
+    double rtol, atol;   // plain solve: |r| <= max(rtol |b|, atol).  Inexact Newton: the FINAL target of the time step
+    bool forcing;        // inexact Newton (Eisenstat-Walker choice 2)
+    double eta1, gamma;  // eta_k = min(eta1, gamma (|F_k| / |F_{k-1}|)^2)
+    double F_prev;       // |F_{k-1}| (0 for the first Newton iteration)
+    double target;       // final absolute target fixed by the first iteration (0 while unknown)
+    double tol2(double rr0) const {
+        if (!forcing) return fmax(rtol * rtol * rr0, atol * atol);
+        const double nb = sqrt(rr0);
+        const double tgt = target > 0.0 ? target : fmax(atol, rtol * nb);
+        if (target > 0.0 && nb <= tgt) return rr0;   // the nonlinear residual already meets the target: dx = 0
+        double eta = eta1;
+        if (F_prev > 0.0) eta = fmin(eta1, gamma * (nb / F_prev) * (nb / F_prev));
+        const double tol = fmax(eta * nb, 0.5 * tgt);
+        return tol * tol;
+    }
+};
 
 struct sg_halo_plan {
     sg_ctx *ctx;
@@ -283,6 +427,11 @@ struct sg_thermal_solver {
     const double *detJ;
     double mass_inv[100];
     double last_rhs_norm;
+    // Chebyshev polynomial preconditioner (DG + class tables): degree = operator applications inside it
+    int cheb_degree;            // 0 = off
+    double cheb_lo, cheb_hi;    // spectrum bounds of M^-1 J in use (hi <= 0: estimate at first use)
+    double *zA, *zB, *dbuf;     // workspace views
+    int cheb_failed;
 };
 
 namespace {
@@ -341,6 +490,164 @@ int blk_update_p(sg_thermal_solver *s, const double *Scur, const double *Snext, 
         default: sg_set_error("unsupported dofs per cell %d", s->blk_nld); rc = SG_E_UNSUPPORTED; \
     }
 
+template <int NLD>
+int blk_init_cheb(sg_thermal_solver *s, const double *b, double *x, double inv_theta, cudaStream_t st) {
+    k_pcg_init_cheb<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, b, x, s->r,
+                                                          s->zA, inv_theta, s->red, s->S + 1, s->ctrl);
+    SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
+    return SG_OK;
+}
+template <int NLD>
+int blk_update_xr_cheb(sg_thermal_solver *s, double *x, double inv_theta, const double *Scur, double *Snext, cudaStream_t st) {
+    k_update_xr_cheb<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, s->p, s->Ap,
+                                                           x, s->r, s->zA, inv_theta, s->red, Scur, s->S + 4, Snext + 1, s->ctrl);
+    SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
+    return SG_OK;
+}
+template <int NLD>
+int blk_precond_scale(sg_thermal_solver *s, const double *w, double scale, double *v, double *out, cudaStream_t st) {
+    k_precond_scale<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, w, scale, v,
+                                                          s->red, out);
+    SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
+    return SG_OK;
+}
+
+// Largest eigenvalue of M^-1 J(T_lin) by 20 power iterations (v in s->p, J v in s->Ap); sets cheb_lo/hi.
+// An UNDER-estimated upper bound makes the polynomial preconditioner indefinite, so the estimate (which
+// approaches lambda_max from below) gets a 25 % margin; an over-estimate only costs a few per cent.
+int estimate_spectrum(sg_thermal_solver *s, const double *T_lin, cudaStream_t st) {
+    int rc;
+    double *S7 = s->S + 7;
+    k_hash_fill<<<vgrid(s->n), VB, 0, st>>>(s->n, 0, s->lo, s->hi, s->p, s->red, S7);
+    SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
+    if ((rc = allreduce(s, S7, 1, st))) return rc;
+    if ((rc = read_scalars(s, 7, 1, st))) return rc;
+    double nrm = sqrt(s->S_host[7]), lam = 0.0;
+    if ((rc = sg_thermal_linearize(s->op, T_lin, st))) return rc;
+    for (int i = 0; i < 20; ++i) {
+        if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
+        if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, s->S + 4, nullptr, st))) return rc;
+        SG_BLK_DISPATCH(blk_precond_scale, s, s->Ap, 1.0 / nrm, s->p, S7, st);
+        if (rc) return rc;
+        if ((rc = allreduce(s, S7, 1, st))) return rc;
+        if ((rc = read_scalars(s, 7, 1, st))) return rc;
+        lam = sqrt(s->S_host[7]);
+        if (!(lam > 0.0) || !isfinite(lam)) {
+            sg_set_error("estimate_spectrum: power iteration broke down (|M^-1 J v| = %g)", lam);
+            return SG_E_NOCONV;
+        }
+        nrm = lam;
+    }
+    s->cheb_hi = 1.25 * lam;
+    s->cheb_lo = fmin(0.9, s->cheb_hi / 4.0);
+    return SG_OK;
+}
+
+constexpr int CHEB_MAX = 8;
+constexpr int CHEB_BATCH = 4;
+
+// PCG with the Chebyshev polynomial preconditioner z = q_k(M^-1 J) M^-1 r.  One outer iteration costs k + 1
+// operator applications but only ONE set of CG vector updates, which is what the plain iteration spends most
+// of its time on.  Same device-side convergence logic as pcg_run.
+int pcg_run_cheb(sg_thermal_solver *s, const double *T_lin, const double *b, double *x, const PcgTol &tp, int32_t max_it,
+                 int32_t *iters, double *rel_res, cudaStream_t st) {
+    int rc;
+    const int k = s->cheb_degree;
+    if (s->cheb_hi <= 0.0 && (rc = estimate_spectrum(s, T_lin, st))) return rc;
+    const double theta = 0.5 * (s->cheb_hi + s->cheb_lo), delta = 0.5 * (s->cheb_hi - s->cheb_lo), sigma1 = theta / delta;
+    double ca[CHEB_MAX], cb[CHEB_MAX], rho = 1.0 / sigma1;
+    for (int j = 0; j < k; ++j) {
+        const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+        ca[j] = rho_new * rho;
+        cb[j] = 2.0 * rho_new / delta;
+        rho = rho_new;
+    }
+    const double inv_theta = 1.0 / theta;
+    double *S = s->S;
+    const unsigned g = vgrid(s->n);
+    SG_BLK_DISPATCH(blk_init_cheb, s, b, x, inv_theta, st);
+    if (rc) return rc;
+    if ((rc = allreduce(s, S + 1, 1, st))) return rc;
+    if ((rc = read_scalars(s, 1, 1, st))) return rc;
+    const double rr0 = s->S_host[1];
+    s->last_rhs_norm = sqrt(rr0 > 0.0 ? rr0 : 0.0);
+    if (!(rr0 >= 0.0) || !isfinite(rr0)) {
+        sg_set_error("sg_pcg_solve: right-hand side is not finite");
+        return SG_E_NOCONV;
+    }
+    const double tol2 = tp.tol2(rr0);
+    int it = 0, done = rr0 > tol2 ? 0 : 1;
+    double rr = rr0;
+    const int *skip = &s->ctrl->done;
+    // z = q_k(M^-1 J) M^-1 r from z1 (in zA); the result's address depends on the parity of k
+    double *zfinal = (k % 2 == 0) ? s->zA : s->zB;
+    auto precondition = [&](double *Srz) -> int {
+        double *zin = s->zA, *zout = s->zB;
+        for (int j = 0; j < k; ++j) {
+            int r2;
+            if (s->halo && (r2 = sg_halo_forward(s->halo, zin, 1, st))) return r2;
+            SgChebStep cs{zin, s->r, j == 0 ? zin : s->dbuf, s->dbuf, zout, ca[j], cb[j], j == k - 1 ? 1 : 0};
+            if ((r2 = sg_thermal_cheb_step(s->op, cs, s->red, Srz, skip, st))) return r2;
+            double *t = zin;
+            zin = zout;
+            zout = t;
+        }
+        return allreduce(s, Srz, 1, st);
+    };
+    if (!done) {
+        if ((rc = sg_thermal_linearize(s->op, T_lin, st))) return rc;
+        if ((rc = precondition(S))) return rc;
+        k_axpy_p<<<g, VB, 0, st>>>(s->n, zfinal, s->p, S, S, 1, s->ctrl);
+        SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
+    }
+    while (!done && it < max_it) {
+        const int nb = (max_it - it < CHEB_BATCH) ? max_it - it : CHEB_BATCH;
+        for (int q = 0; q < nb; ++q, ++it) {
+            double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
+            if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
+            if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, skip, st))) return rc;
+            if ((rc = allreduce(s, S + 4, 2, st))) return rc;
+            SG_BLK_DISPATCH(blk_update_xr_cheb, s, x, inv_theta, Scur, Snext, st);
+            if (rc) return rc;
+            if ((rc = allreduce(s, Snext + 1, 1, st))) return rc;
+            k_pcg_check<<<1, 1, 0, st>>>(s->ctrl, Snext, tol2, it);
+            SG_CHECK_CUDA(cudaGetLastError());
+            if ((rc = precondition(Snext))) return rc;
+            k_axpy_p<<<g, VB, 0, st>>>(s->n, zfinal, s->p, Scur, Snext, 0, s->ctrl);
+            SG_CHECK_CUDA(cudaGetLastError());
+            sg_count_launch(2);
+        }
+        SG_CHECK_CUDA(cudaMemcpyAsync(s->ctrl_host, s->ctrl, sizeof(PcgCtrl), cudaMemcpyDeviceToHost, st));
+        SG_CHECK_CUDA(cudaMemcpyAsync(s->S_host + 2 * (it & 1), S + 2 * (it & 1), sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        SG_CHECK_CUDA(cudaStreamSynchronize(st));
+        done = s->ctrl_host->done;
+        rr = done ? s->ctrl_host->rr : s->S_host[2 * (it & 1) + 1];
+        if (done) it = s->ctrl_host->iters;
+        if (!done && !(s->S_host[2 * (it & 1)] > 0.0)) {   // r.z <= 0: the polynomial is not positive on the spectrum
+            sg_set_error("Chebyshev preconditioner is not positive definite (r.z = %g): eigenvalue bound %g too small",
+                         s->S_host[2 * (it & 1)], s->cheb_hi);
+            return SG_E_NOCONV;
+        }
+    }
+    if (iters) *iters = it;
+    if (rel_res) *rel_res = rr0 > 0.0 ? sqrt(rr / rr0) : 0.0;
+    if (done == 2 || !isfinite(rr)) {
+        sg_set_error("sg_pcg_solve (Chebyshev): residual became non-finite at iteration %d", it);
+        return SG_E_NOCONV;
+    }
+    if (!done) {
+        sg_set_error("sg_pcg_solve (Chebyshev): no convergence in %d iterations (relative residual %.3e)", it,
+                     rr0 > 0 ? sqrt(rr / rr0) : 0.0);
+        return SG_E_NOCONV;
+    }
+    return SG_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -393,7 +700,7 @@ int64_t sg_thermal_solver_workspace_doubles(const sg_thermal_op *op) {
     if (!op) return -1;
     SgOpInfo oi;
     sg_op_info(op, &oi);
-    return 6 * oi.n_dofs;
+    return 8 * oi.n_dofs;
 }
 
 int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan *halo, sg_thermal_solver **out) {
@@ -421,6 +728,12 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     s->p = w + 3 * s->n;
     s->Ap = w + 4 * s->n;
     s->dinv = w + 5 * s->n;
+    s->dbuf = s->dinv;            // the DG solver has no Jacobi diagonal: the slot holds the Chebyshev direction
+    s->zA = w + 6 * s->n;
+    s->zB = w + 7 * s->n;
+    s->cheb_degree = 0;
+    s->cheb_lo = s->cheb_hi = 0.0;
+    s->cheb_failed = 0;
     s->red.partials = nullptr;
     s->red.counter = nullptr;
     s->S = nullptr;
@@ -456,26 +769,6 @@ int sg_thermal_solver_destroy(sg_thermal_solver *s) {
     return SG_OK;
 }
 
-// Tolerance policy of one PCG solve: the |r|^2 target as a function of |b|^2, which is only known after
-// the first reduction.  Returning >= |b|^2 means "nothing to do": zero iterations, x = 0.
-struct PcgTol {
-    double rtol, atol;   // plain solve: |r| <= max(rtol |b|, atol).  Inexact Newton: the FINAL target of the time step
-    bool forcing;        // inexact Newton (Eisenstat-Walker choice 2)
-    double eta1, gamma;  // eta_k = min(eta1, gamma (|F_k| / |F_{k-1}|)^2)
-    double F_prev;       // |F_{k-1}| (0 for the first Newton iteration)
-    double target;       // final absolute target fixed by the first iteration (0 while unknown)
-    double tol2(double rr0) const {
-        if (!forcing) return fmax(rtol * rtol * rr0, atol * atol);
-        const double nb = sqrt(rr0);
-        const double tgt = target > 0.0 ? target : fmax(atol, rtol * nb);
-        if (target > 0.0 && nb <= tgt) return rr0;   // the nonlinear residual already meets the target: dx = 0
-        double eta = eta1;
-        if (F_prev > 0.0) eta = fmin(eta1, gamma * (nb / F_prev) * (nb / F_prev));
-        const double tol = fmax(eta * nb, 0.5 * tgt);
-        return tol * tol;
-    }
-};
-
 static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, double *x, const PcgTol &tp,
                    int32_t max_it, int32_t *iters, double *rel_res, cudaStream_t st);
 
@@ -485,8 +778,36 @@ int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, dou
     return pcg_run(s, T_lin, b, x, PcgTol{rtol, atol, false, 0.0, 0.0, 0.0, 0.0}, max_it, iters, rel_res, (cudaStream_t)stream);
 }
 
+int sg_thermal_solver_set_chebyshev(sg_thermal_solver *s, int32_t degree, double lo, double hi) {
+    SG_REQUIRE(s && degree >= 0 && degree <= CHEB_MAX, "sg_thermal_solver_set_chebyshev: degree must be 0..%d", CHEB_MAX);
+    if (degree > 0 && !(s->blk_nld && sg_thermal_has_cheb(s->op))) return 0;   // not available: plain PCG stays in use
+    s->cheb_degree = degree;
+    s->cheb_failed = 0;
+    if (hi > 0.0) {
+        SG_REQUIRE(lo > 0.0 && lo < hi, "sg_thermal_solver_set_chebyshev: need 0 < lo < hi");
+        s->cheb_lo = lo;
+        s->cheb_hi = hi;
+    } else {
+        s->cheb_lo = s->cheb_hi = 0.0;
+    }
+    return degree > 0 ? 1 : 0;
+}
+
+int sg_thermal_solver_get_chebyshev(const sg_thermal_solver *s, int32_t *degree, double *lo, double *hi) {
+    SG_REQUIRE(s, "sg_thermal_solver_get_chebyshev: NULL solver");
+    if (degree) *degree = s->cheb_failed ? 0 : s->cheb_degree;
+    if (lo) *lo = s->cheb_lo;
+    if (hi) *hi = s->cheb_hi;
+    return SG_OK;
+}
+
 static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, double *x, const PcgTol &tp,
                    int32_t max_it, int32_t *iters, double *rel_res, cudaStream_t st) {
+    if (s->cheb_degree > 0 && !s->cheb_failed) {
+        const int rc_c = pcg_run_cheb(s, T_lin, b, x, tp, max_it, iters, rel_res, st);
+        if (rc_c != SG_E_NOCONV) return rc_c;
+        s->cheb_failed = 1;   // eigenvalue bound too small or breakdown: fall back to the block-Jacobi iteration for good
+    }
     const long n = s->n, lo = s->lo, hi = s->hi;
     const unsigned g = vgrid(n);
     double *S = s->S;

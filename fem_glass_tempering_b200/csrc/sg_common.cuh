@@ -47,6 +47,17 @@ int sg_thermal_linearize(sg_thermal_op *op, const double *T_lin, cudaStream_t st
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
                          const int *skip, cudaStream_t st);
 
+// One fused Chebyshev step of the polynomial preconditioner (DG + class tables only, see dg_cheb_step):
+// d_out = a d_in + b M^-1 (r - J z_in), z_out = z_in + d_out; last: d_out is not stored, *dot_out = r.z_out.
+struct SgChebStep {
+    const double *z_in, *r, *d_in;
+    double *d_out, *z_out;
+    double a, b;
+    int last;
+};
+bool sg_thermal_has_cheb(const sg_thermal_op *op);
+int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
+
 // classify.cu: equivalence classes of 64-bit keys.  cls_out[i] = class of keys[i] in [0, *n_cls),
 // rep_out[k] = index of one member of class k; both are cudaMalloc'ed here and freed by the caller.
 int sg_classify_u64(const uint64_t *keys_dev, int64_t n, int32_t **cls_out, int32_t *n_cls, int32_t **rep_out);

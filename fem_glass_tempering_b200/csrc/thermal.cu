@@ -708,6 +708,61 @@ __device__ __forceinline__ void smem_matvec_acc(const double *__restrict__ A, co
     }
 }
 
+// Element vector of DG cell c from the class tables: loads the class word, the neighbour ids, the cell's row
+// xk and the neighbours' rows of x, returns yk = A_self x_K + sum_f A_nb x_N (+ exterior-facet matrices).
+template <int NLD, int NNB, int P, bool WIDE, bool BND>
+__device__ __forceinline__ void dg_cell_apply(const ClsDev &cd, const double *s_tab, const double *s_nb, const long c,
+                                              const double *__restrict__ x, double (&xk)[NLD], double (&yk)[NLD]) {
+    const long nc = cd.n_cells;
+    const uint64_t w = cd.cls64[c];
+    int nb[NNB];
+#pragma unroll
+    for (int f = 0; f < NNB; ++f) nb[f] = cd.nbr[(long)f * nc + c];
+    load_row<NLD, WIDE>(x + c * NLD, xk);
+    double xn[NNB][NLD];
+#pragma unroll
+    for (int f = 0; f < NNB; ++f) {
+        if (nb[f] >= 0) {
+            load_row<NLD, WIDE>(x + (long)nb[f] * NLD, xn[f]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) xn[f][j] = 0.0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) yk[i] = 0.0;
+    smem_matvec_acc<NLD>(s_tab + (int)(w & 0xFFFFull) * cd.S, xk, yk);
+#pragma unroll
+    for (int f = 0; f < NNB; ++f) {
+        const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
+        if (u) smem_matvec_acc<NLD>(s_nb + (u - 1) * cd.S, xn[f], yk);
+        if constexpr (BND) {
+            if (nb[f] < -1) {   // exterior facet: y_K += B_f x_K on the facet's dofs
+                constexpr int D = NNB - 1, NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
+                const double *Bp = cd.bmat + (long)(-2 - nb[f]) * NFDP;
+                double B[NFDP];
+#pragma unroll
+                for (int k = 0; k < NFDP; ++k) B[k] = Bp[k];
+                int m = 0;
+#pragma unroll
+                for (int k = 0; k < NFD; ++k)
+#pragma unroll
+                    for (int l = k; l < NFD; ++l) {
+                        const int ik = facet_dof(D, P, f, k), il = facet_dof(D, P, f, l);
+                        yk[ik] += B[m] * xk[il];
+                        if (l != k) yk[il] += B[m] * xk[ik];
+                        ++m;
+                    }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void load_class_tables(const ClsDev &cd, double *s_tab, int ntab) {
+    for (int i = threadIdx.x; i < ntab; i += CB) s_tab[i] = cd.tab[i];
+    __syncthreads();
+}
+
 // DG fast apply: persistent grid-stride blocks, class tables in shared memory, fused x.y reduction.
 // A warp handles 32 consecutive cells; when these share their classes (the plate meshes number the cells
 // in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.
@@ -716,61 +771,63 @@ __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const doub
                                                      SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
-    const int ntab = (cd.n_self + cd.n_nb) * cd.S;
-    for (int i = threadIdx.x; i < ntab; i += CB) s_tab[i] = cd.tab[i];
-    __syncthreads();
+    load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
     const double *s_nb = s_tab + cd.n_self * cd.S;
-    const long nc = cd.n_cells;
     double dsum[2] = {0.0, 0.0};   // [1] stays 0: slot of the separate exterior-facet kernel (overwritten by it when it runs)
     for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
-        const uint64_t w = cd.cls64[c];
-        int nb[NNB];
-#pragma unroll
-        for (int f = 0; f < NNB; ++f) nb[f] = cd.nbr[(long)f * nc + c];
         double xk[NLD], yk[NLD];
-        load_row<NLD, WIDE>(x + c * NLD, xk);
-        double xn[NNB][NLD];
-#pragma unroll
-        for (int f = 0; f < NNB; ++f) {
-            if (nb[f] >= 0) {
-                load_row<NLD, WIDE>(x + (long)nb[f] * NLD, xn[f]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < NLD; ++j) xn[f][j] = 0.0;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < NLD; ++i) yk[i] = 0.0;
-        smem_matvec_acc<NLD>(s_tab + (int)(w & 0xFFFFull) * cd.S, xk, yk);
-#pragma unroll
-        for (int f = 0; f < NNB; ++f) {
-            const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
-            if (u) smem_matvec_acc<NLD>(s_nb + (u - 1) * cd.S, xn[f], yk);
-            if constexpr (BND) {
-                if (nb[f] < -1) {   // exterior facet: y_K += B_f x_K on the facet's dofs
-                    constexpr int D = NNB - 1, NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
-                    const double *Bp = cd.bmat + (long)(-2 - nb[f]) * NFDP;
-                    double B[NFDP];
-#pragma unroll
-                    for (int k = 0; k < NFDP; ++k) B[k] = Bp[k];
-                    int m = 0;
-#pragma unroll
-                    for (int k = 0; k < NFD; ++k)
-#pragma unroll
-                        for (int l = k; l < NFD; ++l) {
-                            const int ik = facet_dof(D, P, f, k), il = facet_dof(D, P, f, l);
-                            yk[ik] += B[m] * xk[il];
-                            if (l != k) yk[il] += B[m] * xk[ik];
-                            ++m;
-                        }
-                }
-            }
-        }
+        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
         store_row<NLD, WIDE>(y + c * NLD, yk);
 #pragma unroll
         for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
     }
     sg_grid_reduce<2>(dsum, red, dot_out);
+}
+
+// One step of the Chebyshev iteration for  (M^-1 J) z = M^-1 r  (M = block-diagonal element mass matrix), the
+// polynomial preconditioner of the DG solver (pcg.cu):
+//     d' = a d + b M^-1 (r - J z),   z' = z + d'
+// fused into the operator apply: J z never goes to memory.  z' is written to a second buffer because the
+// neighbours still read z.  LAST: d' is not stored and r.z' is reduced into dot_out[0].
+struct ChebDev {
+    const double *r, *d_in, *detJ;
+    double *d_out, *z_out;
+    double a, b;
+    double minv[100];   // Mhat^-1, row-major NLD x NLD
+};
+
+template <int NLD, int NNB, int P, bool WIDE, bool BND, bool LAST>
+__global__ void __launch_bounds__(CB) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
+                                                   SgRed red, double *dot_out, const int *skip) {
+    extern __shared__ __align__(16) double s_tab[];
+    if (skip && *skip) return;
+    load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
+    const double *s_nb = s_tab + cd.n_self * cd.S;
+    double dsum[1] = {0.0};
+    for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
+        double zk[NLD], Jz[NLD], rk[NLD], dk[NLD];
+        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
+        load_row<NLD, WIDE>(ch.r + c * NLD, rk);
+        load_row<NLD, WIDE>(ch.d_in + c * NLD, dk);
+        const double idet = ch.b / ch.detJ[c];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) Jz[i] = rk[i] - Jz[i];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            double m = 0.0;
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) m += ch.minv[i * NLD + j] * Jz[j];
+            dk[i] = ch.a * dk[i] + idet * m;
+            zk[i] += dk[i];
+        }
+        if (!LAST) store_row<NLD, WIDE>(ch.d_out + c * NLD, dk);
+        store_row<NLD, WIDE>(ch.z_out + c * NLD, zk);
+        if (LAST) {
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) dsum[0] += rk[i] * zk[i];
+        }
+    }
+    if (LAST) sg_grid_reduce<1>(dsum, red, dot_out);
 }
 
 // CG fast apply: gather through the dofmap, class matrix from shared memory, scatter with RED.ADD.F64.
@@ -829,6 +886,7 @@ struct sg_thermal_op {
     int32_t *nbr_ext;      // DG P1: neighbour ids with exterior facets encoded (see ClsDev::bmat)
     double *bmat;
     int (*linearize)(const sg_thermal_op *, const double *T_lin, cudaStream_t st);
+    int (*cheb_step)(const sg_thermal_op *, const SgChebStep &, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
     // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
     int prof_on, prof_n, prof_cap;
     cudaEvent_t *prof_ev;
@@ -930,6 +988,40 @@ int linearize_t(const sg_thermal_op *op, const double *T_lin, cudaStream_t st) {
         sg_count_launch();
     }
     return SG_OK;
+}
+
+template <int D, int P, bool DG>
+int cheb_step_t(const sg_thermal_op *op, const SgChebStep &cs, SgRed red, double *dot_out, const int *skip, cudaStream_t st) {
+    if constexpr (DG) {
+        constexpr int NLD = nld_of(D, P), NNB = D + 1;
+        SG_REQUIRE(op->cls.tab, "Chebyshev step needs the class tables");
+        ChebDev ch;
+        ch.r = cs.r;
+        ch.d_in = cs.d_in;
+        ch.d_out = cs.d_out;
+        ch.z_out = cs.z_out;
+        ch.detJ = op->d.geom + (int64_t)D * D * op->d.n_cells;
+        ch.a = cs.a;
+        ch.b = cs.b;
+        for (int i = 0; i < NLD * NLD; ++i) ch.minv[i] = op->mass_inv[i];
+        const uintptr_t al = (uintptr_t)cs.z_in | (uintptr_t)cs.r | (uintptr_t)cs.d_in | (uintptr_t)cs.d_out | (uintptr_t)cs.z_out;
+        const bool wide = (al & 31) == 0, bnd = op->bmat != nullptr;
+        void (*k)(const ClsDev, const ChebDev, const double *, SgRed, double *, const int *);
+        if (cs.last)
+            k = bnd ? (wide ? dg_cheb_step<NLD, NNB, P, true, true, true> : dg_cheb_step<NLD, NNB, P, false, true, true>)
+                    : (wide ? dg_cheb_step<NLD, NNB, P, true, false, true> : dg_cheb_step<NLD, NNB, P, false, false, true>);
+        else
+            k = bnd ? (wide ? dg_cheb_step<NLD, NNB, P, true, true, false> : dg_cheb_step<NLD, NNB, P, false, true, false>)
+                    : (wide ? dg_cheb_step<NLD, NNB, P, true, false, false> : dg_cheb_step<NLD, NNB, P, false, false, false>);
+        SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
+        k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, ch, cs.z_in, red, dot_out, skip);
+        SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
+        return SG_OK;
+    } else {
+        sg_set_error("Chebyshev step is only available for DG spaces");
+        return SG_E_UNSUPPORTED;
+    }
 }
 
 struct DevBuf {  // scoped cudaMalloc
@@ -1085,6 +1177,7 @@ int build_tab(sg_thermal_op *op) {
     op->launch = &launch_op<D, P, DG>;
     op->build_classes = &build_classes_t<D, P, DG>;
     op->linearize = &linearize_t<D, P, DG>;
+    op->cheb_step = &cheb_step_t<D, P, DG>;
     return SG_OK;
 }
 
@@ -1115,6 +1208,15 @@ void sg_op_info(const sg_thermal_op *op, SgOpInfo *o) {
 }
 
 int sg_thermal_linearize(sg_thermal_op *op, const double *T_lin, cudaStream_t st) { return op->linearize(op, T_lin, st); }
+
+bool sg_thermal_has_cheb(const sg_thermal_op *op) {
+    // the exterior facets must be inside the class kernel (bmat) or absent, so that J z is complete per cell
+    return op->d.family == 1 && op->cls.tab != nullptr && (op->bmat != nullptr || op->d.n_bfacets == 0);
+}
+
+int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, double *dot_out, const int *skip, cudaStream_t st) {
+    return op->cheb_step(op, cs, red, dot_out, skip, st);
+}
 
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
                          const int *skip, cudaStream_t st) {

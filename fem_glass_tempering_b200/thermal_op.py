@@ -30,7 +30,7 @@ class ThermalOperator:
     """
 
     def __init__(self, ctx: _lib.Context, space: fe.ScalarSpace, params: dict, dt: float, partition: dict | None = None,
-                 use_classes: bool = True):
+                 use_classes: bool = True, cheb_degree: int = 3):
         import torch
         self.ctx, self.space, self.dt = ctx, space, float(dt)
         mesh, d = space.mesh, space.mesh.dim
@@ -106,6 +106,9 @@ class ThermalOperator:
         _lib.check(L.sg_thermal_solver_create(self.handle, self.workspace.data_ptr(), self.halo, C.byref(sh)))
         self.solver = sh
         self.opts = NewtonOptsC(1e-12, 1e-10, 50, 1e-12, 0.0, 10000, 1e-3)
+        self.chebyshev_degree = 0
+        if cheb_degree:
+            self.set_chebyshev(cheb_degree)
         self.last_stats = None
 
     # -- raw operator calls (asynchronous on the current stream) ---------------------------------
@@ -122,6 +125,19 @@ class ThermalOperator:
     def jac_diag(self, T_lin, out):
         _lib.check(_lib.lib().sg_thermal_jac_diag(self.handle, _lib.ptr(T_lin), _lib.ptr(out), _lib.current_stream_ptr()))
         return out
+
+    def set_chebyshev(self, degree: int, lo: float = 0.0, hi: float = 0.0) -> bool:
+        """Chebyshev polynomial preconditioner of the DG solver (sg_thermal_solver_set_chebyshev); False if unavailable."""
+        rc = _lib.lib().sg_thermal_solver_set_chebyshev(self.solver, int(degree), float(lo), float(hi))
+        if rc < 0:
+            _lib.check(rc)
+        self.chebyshev_degree = int(degree) if rc == 1 else 0
+        return rc == 1
+
+    def chebyshev_info(self) -> dict:
+        d, lo, hi = C.c_int32(0), C.c_double(0.0), C.c_double(0.0)
+        _lib.check(_lib.lib().sg_thermal_solver_get_chebyshev(self.solver, C.byref(d), C.byref(lo), C.byref(hi)))
+        return dict(degree=d.value, lo=lo.value, hi=hi.value)
 
     def class_info(self) -> dict:
         """Local-matrix classes found by the library (sg_thermal_class_info)."""

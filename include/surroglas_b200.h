@@ -231,6 +231,14 @@ typedef struct sg_thermal_solver sg_thermal_solver;
 int64_t sg_thermal_solver_workspace_doubles(const sg_thermal_op *op);
 int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan *halo, sg_thermal_solver **out);
 int sg_thermal_solver_destroy(sg_thermal_solver *s);
+/* DG spaces with the class tables in use: precondition CG with the degree-`degree` Chebyshev polynomial in
+ * M^-1 J (M = element mass blocks) instead of M^-1 alone: one CG iteration then does degree + 1 operator
+ * applications (fused with the polynomial recurrence, J z never goes to memory) but only one set of CG vector
+ * updates and reductions.  [lo, hi] bounds the spectrum of M^-1 J; hi <= 0: estimated by power iteration at
+ * first use (+25 %).  Returns 1 when enabled, 0 when not available (CG spaces, general kernel) or degree == 0.
+ * If the polynomial turns out not to be positive definite the solver falls back to M^-1 for good. */
+int sg_thermal_solver_set_chebyshev(sg_thermal_solver *s, int32_t degree, double lo, double hi);
+int sg_thermal_solver_get_chebyshev(const sg_thermal_solver *s, int32_t *degree, double *lo, double *hi);
 /* Solve J(T_lin) x = b with Jacobi-PCG from x = 0; blocks until converged (KSP 'cg', TVP:343). */
 int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, double *x, double rtol, double atol,
                  int32_t max_it, int32_t *iters, double *rel_res, void *stream);
