@@ -30,7 +30,7 @@ class ThermalOperator:
     """
 
     def __init__(self, ctx: _lib.Context, space: fe.ScalarSpace, params: dict, dt: float, partition: dict | None = None,
-                 use_classes: bool = True, cheb_degree: int = 3):
+                 use_classes: bool = True, cheb_degree: int | None = None):
         import torch
         self.ctx, self.space, self.dt = ctx, space, float(dt)
         mesh, d = space.mesh, space.mesh.dim
@@ -107,6 +107,10 @@ class ThermalOperator:
         self.solver = sh
         self.opts = NewtonOptsC(1e-12, 1e-10, 50, 1e-12, 0.0, 10000, 1e-3)
         self.chebyshev_degree = 0
+        if cheb_degree is None:
+            # polynomial preconditioning trades CG vector updates for operator applications: worth it on large DG
+            # meshes, not on the 48-cell line of main.py (plain CG terminates early there)
+            cheb_degree = 3 if space.mesh.n_cells >= 20000 else 0
         if cheb_degree:
             self.set_chebyshev(cheb_degree)
         self.last_stats = None

@@ -56,6 +56,8 @@ def main():
         fam, deg = cfg["T"]["element"], cfg["T"]["degree"]
         m, part, info = distributed.slab_partition(dim, n, lengths, fam, deg, rank, world)
         prob = make_problem(m, cfg, ctx, part)
+        if fam == "DG":      # the partitioned run uses the Chebyshev-preconditioned solver (halo exchange of every
+            assert prob._thermal_op.set_chebyshev(3)      # polynomial step), the single-GPU reference the plain one
         try:
             for _ in range(STEPS):
                 prob.solve_timestep(t=0.0)

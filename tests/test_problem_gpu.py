@@ -250,3 +250,17 @@ def test_field_writer_records_every_step(sg_ctx, tmp_path):
             assert_same(a, b, f"written {key}")
     t, xi = read_series(prob.output_dir, "xi")
     assert xi.shape == (prob.n_steps + 1, prob.functionSpaces["T"].n_nodes)
+
+
+def test_chebyshev_solver_gives_the_same_histories(sg_ctx):
+    """The polynomial-preconditioned DG solve (default on large meshes) lands on the same discrete solution."""
+    cfg = {"T": {"element": "DG", "degree": 1}, "sigma": {"element": "DG", "degree": 1}}
+    prob, orc = make_pair(sg_ctx, msh.box_mesh(6, 6, 3, 6.0, 6.0, 3.0), cfg)
+    assert prob._thermal_op.set_chebyshev(3)
+    for step in range(6):
+        prob.solve_timestep(t=0.0)
+        orc.step()
+        assert rel_err(cpu(prob.functions_current["T"]), orc.f["T_cur"]) <= 1e-10
+        assert rel_err(cpu(prob.functions_current["Tf"]), orc.f["Tf_cur"]) <= 1e-10
+        orc.end_step()
+    assert prob._thermal_op.chebyshev_info()["degree"] == 3
