@@ -767,7 +767,7 @@ __device__ __forceinline__ void load_class_tables(const ClsDev &cd, double *s_ta
 // A warp handles 32 consecutive cells; when these share their classes (the plate meshes number the cells
 // in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.
 template <int NLD, int NNB, int P, bool WIDE, bool BND>
-__global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
+__global__ void __launch_bounds__(CB, 3) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
                                                      SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
@@ -784,6 +784,68 @@ __global__ void __launch_bounds__(CB) dg_class_apply(const ClsDev cd, const doub
     sg_grid_reduce<2>(dsum, red, dot_out);
 }
 
+// Residual from the class tables: F_K = (cell + interior-facet part of J) T  -  |detJ| Mhat T_prev  -  dt f |detJ| load.
+// The cell part of the Jacobian is linear in T (the nonlinearity sits on the exterior facets, added afterwards by
+// bfacet_kernel<MODE_RESID>), so the tables of the apply kernel serve the residual too.
+struct ResidDev {
+    const double *xprev, *detJ;
+    double dt_f;
+    double mass[100];   // Mhat, row-major NLD x NLD
+    double load[10];
+};
+
+template <int NLD>
+__device__ __forceinline__ void resid_correction(const ResidDev &rd, const long c, const double (&xp)[NLD], double (&yk)[NLD]) {
+    const double dj = rd.detJ[c];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        double m = rd.dt_f * rd.load[i];
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) m += rd.mass[i * NLD + j] * xp[j];
+        yk[i] -= dj * m;
+    }
+}
+
+template <int NLD, int NNB, int P, bool WIDE>
+__global__ void __launch_bounds__(CB, 3) dg_class_resid(const ClsDev cd, const __grid_constant__ ResidDev rd, const double *__restrict__ x,
+                                                     double *__restrict__ y) {
+    extern __shared__ __align__(16) double s_tab[];
+    load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
+    const double *s_nb = s_tab + cd.n_self * cd.S;
+    for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
+        double xk[NLD], yk[NLD], xp[NLD];
+        dg_cell_apply<NLD, NNB, P, WIDE, false>(cd, s_tab, s_nb, c, x, xk, yk);   // nbr < 0 (incl. encoded exterior facets): no term
+        load_row<NLD, WIDE>(rd.xprev + c * NLD, xp);
+        resid_correction<NLD>(rd, c, xp, yk);
+        store_row<NLD, WIDE>(y + c * NLD, yk);
+    }
+}
+
+template <int NLD>
+__global__ void __launch_bounds__(CB) cg_class_resid(const ClsDev cd, const __grid_constant__ ResidDev rd, const double *__restrict__ x,
+                                                     double *__restrict__ y) {
+    extern __shared__ __align__(16) double s_tab[];
+    load_class_tables(cd, s_tab, cd.n_self * cd.S);
+    const long nc = cd.n_cells;
+    for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
+        const double *As = s_tab + (int)cd.cls16[c] * cd.S;
+        int dof[NLD];
+        double xk[NLD], xp[NLD], yk[NLD];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) dof[i] = cd.dofmap[(long)i * nc + c];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            xk[i] = x[dof[i]];
+            xp[i] = rd.xprev[dof[i]];
+            yk[i] = 0.0;
+        }
+        smem_matvec_acc<NLD>(As, xk, yk);
+        resid_correction<NLD>(rd, c, xp, yk);
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) atomicAdd(&y[dof[i]], yk[i]);
+    }
+}
+
 // One step of the Chebyshev iteration for  (M^-1 J) z = M^-1 r  (M = block-diagonal element mass matrix), the
 // polynomial preconditioner of the DG solver (pcg.cu):
 //     d' = a d + b M^-1 (r - J z),   z' = z + d'
@@ -797,7 +859,7 @@ struct ChebDev {
 };
 
 template <int NLD, int NNB, int P, bool WIDE, bool BND, bool LAST>
-__global__ void __launch_bounds__(CB) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
+__global__ void __launch_bounds__(CB, 3) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
                                                    SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
@@ -874,7 +936,7 @@ struct sg_thermal_op {
     void *tab_host;      // Tab<D,P,DG> instance
     size_t tab_bytes;
     double *btab_dev, *bw_dev;
-    double mass_inv[100];
+    double mass_inv[100], mass[100], load[10];
     // local-matrix classes (fast apply path); cls.tab == nullptr when not available
     ClsDev cls;
     void *cls_words;       // cls64 / cls16 storage
@@ -942,6 +1004,24 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
             k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
         } else
             cg_class_apply<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+        SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
+    } else if (mode == MODE_RESID && op->cls.tab != nullptr && !(op->d.flags & SG_THERMAL_GENERAL_RESIDUAL)) {
+        ResidDev rd;
+        rd.xprev = xprev;
+        rd.detJ = op->d.geom + (int64_t)D * D * op->d.n_cells;
+        rd.dt_f = dv.dt_f;
+        memcpy(rd.mass, op->mass, sizeof(double) * NLD * NLD);
+        memcpy(rd.load, op->load, sizeof(double) * NLD);
+        if constexpr (DG) {
+            const bool wide = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)xprev) & 31) == 0;
+            auto k = wide ? dg_class_resid<NLD, D + 1, P, true> : dg_class_resid<NLD, D + 1, P, false>;
+            SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
+            k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, rd, x, y);
+        } else {
+            SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_resid<NLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
+            cg_class_resid<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, rd, x, y);
+        }
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
     } else if (ncell > 0) {
@@ -1282,6 +1362,8 @@ int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *d, sg_thermal_op **
         return rc;
     }
     invert_small(d->mass, d->n_ld, op->mass_inv);
+    memcpy(op->mass, d->mass, sizeof(double) * d->n_ld * d->n_ld);
+    memcpy(op->load, d->load, sizeof(double) * d->n_ld);
     OpDev &dv = op->dev;
     memset(&dv, 0, sizeof(dv));
     dv.n_cells = d->n_cells;

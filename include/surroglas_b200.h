@@ -174,7 +174,8 @@ typedef struct {
 } sg_thermal_desc;
 
 enum {
-    SG_THERMAL_NO_CLASSES = 1       /* never use the local-matrix class tables (general per-cell-geometry kernel only) */
+    SG_THERMAL_NO_CLASSES = 1,      /* never use the local-matrix class tables (general per-cell-geometry kernel only) */
+    SG_THERMAL_GENERAL_RESIDUAL = 2 /* evaluate the residual with the per-cell-geometry kernel even when the tables exist */
 };
 
 typedef struct sg_thermal_op sg_thermal_op;
