@@ -377,6 +377,14 @@ __global__ void __launch_bounds__(VB) k_hash_fill(long n, long global_offset, lo
     grid_reduce<1>(acc, red, out);
 }
 
+// The host reads solver scalars from a MAPPED pinned mirror that this kernel fills with plain stores: no
+// cudaMemcpy, so the reads never queue behind a large device->host output copy on the DMA engine
+// (output.HostMirror streams 2 GB per step on a side stream).
+__global__ void k_mirror(const double *S, const PcgCtrl *ctrl, double *S_host, PcgCtrl *ctrl_host) {
+    if (threadIdx.x < 8) S_host[threadIdx.x] = S[threadIdx.x];
+    if (threadIdx.x == 8) *ctrl_host = *ctrl;
+}
+
 inline unsigned vgrid(long n) {
     long g = (n + VB - 1) / VB;
     if (g < 1) g = 1;
@@ -430,7 +438,7 @@ struct sg_thermal_solver {
     // Chebyshev polynomial preconditioner (DG + class tables): degree = operator applications inside it
     int cheb_degree;            // 0 = off
     double cheb_lo, cheb_hi;    // spectrum bounds of M^-1 J in use (hi <= 0: estimate at first use)
-    double *zA, *zB, *dbuf;     // workspace views
+    double *zA, *zB;            // workspace views
     int cheb_failed;
 };
 
@@ -443,7 +451,10 @@ int allreduce(sg_thermal_solver *s, double *ptr, int count, cudaStream_t st) {
 }
 
 int read_scalars(sg_thermal_solver *s, int first, int count, cudaStream_t st) {
-    SG_CHECK_CUDA(cudaMemcpyAsync(s->S_host + first, s->S + first, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    (void)first;
+    (void)count;
+    k_mirror<<<1, 32, 0, st>>>(s->S, s->ctrl, s->S_host, s->ctrl_host);
+    SG_CHECK_CUDA(cudaGetLastError());
     SG_CHECK_CUDA(cudaStreamSynchronize(st));
     return SG_OK;
 }
@@ -586,15 +597,16 @@ int pcg_run_cheb(sg_thermal_solver *s, const double *T_lin, const double *b, dou
     // z = q_k(M^-1 J) M^-1 r from z1 (in zA); the result's address depends on the parity of k
     double *zfinal = (k % 2 == 0) ? s->zA : s->zB;
     auto precondition = [&](double *Srz) -> int {
-        double *zin = s->zA, *zout = s->zB;
+        double *zin = s->zA, *zother = s->zB;
         for (int j = 0; j < k; ++j) {
             int r2;
             if (s->halo && (r2 = sg_halo_forward(s->halo, zin, 1, st))) return r2;
-            SgChebStep cs{zin, s->r, j == 0 ? zin : s->dbuf, s->dbuf, zout, ca[j], cb[j], j == k - 1 ? 1 : 0};
+            // z_{j+1} overwrites z_{j-1} (which lives in `zother`; for j = 0 there is no z_0 and zother is free)
+            SgChebStep cs{zin, s->r, j == 0 ? nullptr : zother, zother, ca[j], cb[j], j == k - 1 ? 1 : 0};
             if ((r2 = sg_thermal_cheb_step(s->op, cs, s->red, Srz, skip, st))) return r2;
             double *t = zin;
-            zin = zout;
-            zout = t;
+            zin = zother;
+            zother = t;
         }
         return allreduce(s, Srz, 1, st);
     };
@@ -622,9 +634,7 @@ int pcg_run_cheb(sg_thermal_solver *s, const double *T_lin, const double *b, dou
             SG_CHECK_CUDA(cudaGetLastError());
             sg_count_launch(2);
         }
-        SG_CHECK_CUDA(cudaMemcpyAsync(s->ctrl_host, s->ctrl, sizeof(PcgCtrl), cudaMemcpyDeviceToHost, st));
-        SG_CHECK_CUDA(cudaMemcpyAsync(s->S_host + 2 * (it & 1), S + 2 * (it & 1), sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
-        SG_CHECK_CUDA(cudaStreamSynchronize(st));
+        if ((rc = read_scalars(s, 0, 8, st))) return rc;
         done = s->ctrl_host->done;
         rr = done ? s->ctrl_host->rr : s->S_host[2 * (it & 1) + 1];
         if (done) it = s->ctrl_host->iters;
@@ -728,7 +738,6 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     s->p = w + 3 * s->n;
     s->Ap = w + 4 * s->n;
     s->dinv = w + 5 * s->n;
-    s->dbuf = s->dinv;            // the DG solver has no Jacobi diagonal: the slot holds the Chebyshev direction
     s->zA = w + 6 * s->n;
     s->zB = w + 7 * s->n;
     s->cheb_degree = 0;
@@ -744,10 +753,10 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     if (e == cudaSuccess) e = cudaMemset(s->red.counter, 0, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&s->S, sizeof(double) * 8);
     if (e == cudaSuccess) e = cudaMemset(s->S, 0, sizeof(double) * 8);
-    if (e == cudaSuccess) e = cudaMallocHost(&s->S_host, sizeof(double) * 8);
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->S_host, sizeof(double) * 8, cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaMalloc(&s->ctrl, sizeof(PcgCtrl));
     if (e == cudaSuccess) e = cudaMemset(s->ctrl, 0, sizeof(PcgCtrl));
-    if (e == cudaSuccess) e = cudaMallocHost(&s->ctrl_host, sizeof(PcgCtrl));
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->ctrl_host, sizeof(PcgCtrl), cudaHostAllocMapped);
     if (e != cudaSuccess) {
         sg_set_error("sg_thermal_solver_create: %s", cudaGetErrorString(e));
         sg_thermal_solver_destroy(s);
@@ -859,9 +868,7 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
                 sg_count_launch();
             }
         }
-        SG_CHECK_CUDA(cudaMemcpyAsync(s->ctrl_host, s->ctrl, sizeof(PcgCtrl), cudaMemcpyDeviceToHost, st));
-        SG_CHECK_CUDA(cudaMemcpyAsync(s->S_host + 2 * (it & 1), S + 2 * (it & 1), sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
-        SG_CHECK_CUDA(cudaStreamSynchronize(st));
+        if ((rc = read_scalars(s, 0, 8, st))) return rc;
         done = s->ctrl_host->done;
         rr = done ? s->ctrl_host->rr : s->S_host[2 * (it & 1) + 1];
         if (done) it = s->ctrl_host->iters;

@@ -48,10 +48,11 @@ int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x
                          const int *skip, cudaStream_t st);
 
 // One fused Chebyshev step of the polynomial preconditioner (DG + class tables only, see dg_cheb_step):
-// d_out = a d_in + b M^-1 (r - J z_in), z_out = z_in + d_out; last: d_out is not stored, *dot_out = r.z_out.
+// z_out = z_in + a (z_in - z_prev) + b M^-1 (r - J z_in); z_prev == NULL means 0 (first step); z_out may alias
+// z_prev but not z_in; last: *dot_out = r.z_out.
 struct SgChebStep {
-    const double *z_in, *r, *d_in;
-    double *d_out, *z_out;
+    const double *z_in, *r, *z_prev;
+    double *z_out;
     double a, b;
     int last;
 };

@@ -847,30 +847,31 @@ __global__ void __launch_bounds__(CB) cg_class_resid(const ClsDev cd, const __gr
 }
 
 // One step of the Chebyshev iteration for  (M^-1 J) z = M^-1 r  (M = block-diagonal element mass matrix), the
-// polynomial preconditioner of the DG solver (pcg.cu):
-//     d' = a d + b M^-1 (r - J z),   z' = z + d'
-// fused into the operator apply: J z never goes to memory.  z' is written to a second buffer because the
-// neighbours still read z.  LAST: d' is not stored and r.z' is reduced into dot_out[0].
+// polynomial preconditioner of the DG solver (pcg.cu), in three-term form
+//     z_new = z + a (z - z_prev) + b M^-1 (r - J z)
+// fused into the operator apply: J z never goes to memory.  z_new overwrites z_prev (only the cell itself reads
+// z_prev, the neighbours read z), so two buffers alternate.  FIRST: z_prev = 0 is not read and z_new goes to the
+// other buffer.  LAST: r.z_new is reduced into dot_out[0].
 struct ChebDev {
-    const double *r, *d_in, *detJ;
-    double *d_out, *z_out;
+    const double *r, *z_prev, *detJ;
+    double *z_out;
     double a, b;
     double minv[100];   // Mhat^-1, row-major NLD x NLD
 };
 
-template <int NLD, int NNB, int P, bool WIDE, bool BND, bool LAST>
+template <int NLD, int NNB, int P, bool WIDE, bool BND, bool FIRST, bool LAST>
 __global__ void __launch_bounds__(CB, 3) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
-                                                   SgRed red, double *dot_out, const int *skip) {
+                                                      SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
     load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
     const double *s_nb = s_tab + cd.n_self * cd.S;
     double dsum[1] = {0.0};
     for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
-        double zk[NLD], Jz[NLD], rk[NLD], dk[NLD];
+        double zk[NLD], Jz[NLD], rk[NLD], zp[NLD];
         dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
         load_row<NLD, WIDE>(ch.r + c * NLD, rk);
-        load_row<NLD, WIDE>(ch.d_in + c * NLD, dk);
+        if (!FIRST) load_row<NLD, WIDE>(ch.z_prev + c * NLD, zp);
         const double idet = ch.b / ch.detJ[c];
 #pragma unroll
         for (int i = 0; i < NLD; ++i) Jz[i] = rk[i] - Jz[i];
@@ -879,14 +880,13 @@ __global__ void __launch_bounds__(CB, 3) dg_cheb_step(const ClsDev cd, const __g
             double m = 0.0;
 #pragma unroll
             for (int j = 0; j < NLD; ++j) m += ch.minv[i * NLD + j] * Jz[j];
-            dk[i] = ch.a * dk[i] + idet * m;
-            zk[i] += dk[i];
+            const double dprev = FIRST ? zk[i] : zk[i] - zp[i];
+            zp[i] = zk[i] + (ch.a * dprev + idet * m);
         }
-        if (!LAST) store_row<NLD, WIDE>(ch.d_out + c * NLD, dk);
-        store_row<NLD, WIDE>(ch.z_out + c * NLD, zk);
+        store_row<NLD, WIDE>(ch.z_out + c * NLD, zp);
         if (LAST) {
 #pragma unroll
-            for (int i = 0; i < NLD; ++i) dsum[0] += rk[i] * zk[i];
+            for (int i = 0; i < NLD; ++i) dsum[0] += rk[i] * zp[i];
         }
     }
     if (LAST) sg_grid_reduce<1>(dsum, red, dot_out);
@@ -1077,22 +1077,26 @@ int cheb_step_t(const sg_thermal_op *op, const SgChebStep &cs, SgRed red, double
         SG_REQUIRE(op->cls.tab, "Chebyshev step needs the class tables");
         ChebDev ch;
         ch.r = cs.r;
-        ch.d_in = cs.d_in;
-        ch.d_out = cs.d_out;
+        ch.z_prev = cs.z_prev;
         ch.z_out = cs.z_out;
         ch.detJ = op->d.geom + (int64_t)D * D * op->d.n_cells;
         ch.a = cs.a;
         ch.b = cs.b;
         for (int i = 0; i < NLD * NLD; ++i) ch.minv[i] = op->mass_inv[i];
-        const uintptr_t al = (uintptr_t)cs.z_in | (uintptr_t)cs.r | (uintptr_t)cs.d_in | (uintptr_t)cs.d_out | (uintptr_t)cs.z_out;
-        const bool wide = (al & 31) == 0, bnd = op->bmat != nullptr;
-        void (*k)(const ClsDev, const ChebDev, const double *, SgRed, double *, const int *);
-        if (cs.last)
-            k = bnd ? (wide ? dg_cheb_step<NLD, NNB, P, true, true, true> : dg_cheb_step<NLD, NNB, P, false, true, true>)
-                    : (wide ? dg_cheb_step<NLD, NNB, P, true, false, true> : dg_cheb_step<NLD, NNB, P, false, false, true>);
-        else
-            k = bnd ? (wide ? dg_cheb_step<NLD, NNB, P, true, true, false> : dg_cheb_step<NLD, NNB, P, false, true, false>)
-                    : (wide ? dg_cheb_step<NLD, NNB, P, true, false, false> : dg_cheb_step<NLD, NNB, P, false, false, false>);
+        const uintptr_t al = (uintptr_t)cs.z_in | (uintptr_t)cs.r | (uintptr_t)cs.z_prev | (uintptr_t)cs.z_out;
+        const bool wide = (al & 31) == 0, bnd = op->bmat != nullptr, first = cs.z_prev == nullptr, last = cs.last != 0;
+        using K = void (*)(const ClsDev, const ChebDev, const double *, SgRed, double *, const int *);
+        // [wide][bnd][first][last]
+        static const K table[2][2][2][2] = {
+            {{{dg_cheb_step<NLD, NNB, P, false, false, false, false>, dg_cheb_step<NLD, NNB, P, false, false, false, true>},
+              {dg_cheb_step<NLD, NNB, P, false, false, true, false>, dg_cheb_step<NLD, NNB, P, false, false, true, true>}},
+             {{dg_cheb_step<NLD, NNB, P, false, true, false, false>, dg_cheb_step<NLD, NNB, P, false, true, false, true>},
+              {dg_cheb_step<NLD, NNB, P, false, true, true, false>, dg_cheb_step<NLD, NNB, P, false, true, true, true>}}},
+            {{{dg_cheb_step<NLD, NNB, P, true, false, false, false>, dg_cheb_step<NLD, NNB, P, true, false, false, true>},
+              {dg_cheb_step<NLD, NNB, P, true, false, true, false>, dg_cheb_step<NLD, NNB, P, true, false, true, true>}},
+             {{dg_cheb_step<NLD, NNB, P, true, true, false, false>, dg_cheb_step<NLD, NNB, P, true, true, false, true>},
+              {dg_cheb_step<NLD, NNB, P, true, true, true, false>, dg_cheb_step<NLD, NNB, P, true, true, true, true>}}}};
+        const K k = table[wide][bnd][first][last];
         SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
         k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, ch, cs.z_in, red, dot_out, skip);
         SG_CHECK_CUDA(cudaGetLastError());

@@ -102,6 +102,8 @@ class ThermoViscoProblem:
                                               to_sigma=self._to_sigma)                            # TVP:48-54
         self._thermal_op = None
         self.output_dir = None
+        self.host_mirror = None           # output.HostMirror: per-step pinned host copies of T/phi/Tf/xi/sigma
+        self.last_mirror_slot = None
 
     # ------------------------------------------------------------------------------------------ mesh
     @staticmethod
@@ -270,6 +272,8 @@ class ThermoViscoProblem:
     def _write_output(self) -> None:
         if getattr(self, "_writer", None) is not None:
             self._writer.write(self.t)
+        if self.host_mirror is not None:
+            self.last_mirror_slot = self.host_mirror.capture()
 
     # ------------------------------------------------------------------------------------------ time loop
     def solve_timestep(self, t) -> None:
