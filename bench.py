@@ -190,7 +190,7 @@ def run_reference(args):
             "timesteps_per_s": 1.0 / dt_s,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -361,12 +361,36 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu_baseline:
         v, dt_s, cores, sample, _ = cpu_timestep_rate(args.workload, 2, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
 
 
+class StdoutToStderr:
+    """The contract is ONE JSON line on stdout: while the benchmark runs, file descriptor 1 points at stderr so that
+    native libraries (NCCL prints its version banner on stdout) cannot interleave; emit() writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self._saved, (text + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
+OUT = None
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -376,10 +400,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cheb", type=int, default=None, help="Chebyshev preconditioner degree of the DG solver (0 = off)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    with StdoutToStderr() as OUT:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_gpu(args)
 
 
 if __name__ == "__main__":
