@@ -334,6 +334,9 @@ def run_gpu(args):
         "config": {"workload": args.workload, "cells_per_gpu": int(mesh.n_cells if world == 1 else qp_local // (dim + 1)),
                    "qp_per_gpu": int(qp_local), "qp_total": int(qp_total), "fe_config": cfg, "dt": DT, "prony_terms": 6,
                    "plate_mm": list(lengths), "partition": f"x-slabs over {world} GPU(s)",
+                   "transport": ("single GPU" if world == 1 else
+                                 ("NVLink peer memory (IPC-mapped mailboxes + flags; no NCCL on the data path)" if op.peer_memory
+                                  else "NCCL send/recv + all-reduce")),
                    "cache": "state per GPU (>17 GB) is far larger than the 126 MB L2; no L2 flush needed",
                    "newton_its_per_step": newton_its / args.steps, "pcg_its_per_step": lin_its / args.steps,
                    "setup_s": round(t_setup, 1), "local_matrix_classes": cls,

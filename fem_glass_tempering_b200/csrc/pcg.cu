@@ -417,6 +417,7 @@ struct sg_halo_plan {
     sg_ctx *ctx;
     int n;
     sg_halo_segment *seg;
+    SgPeer *peer;      // NVLink peer-memory path (sg_halo_peer_alloc/open); NULL: NCCL send/recv
 };
 
 struct sg_thermal_solver {
@@ -446,6 +447,7 @@ namespace {
 
 int allreduce(sg_thermal_solver *s, double *ptr, int count, cudaStream_t st) {
     if (s->ctx->nranks == 1) return SG_OK;
+    if (s->halo && sg_peer_ready(s->halo->peer)) return sg_peer_allreduce(s->halo->peer, ptr, count, st);
     SG_CHECK_NCCL(sg_nccl()->AllReduce(ptr, ptr, (size_t)count, ncclDouble, ncclSum, s->ctx->comm, st));
     return SG_OK;
 }
@@ -456,6 +458,7 @@ int read_scalars(sg_thermal_solver *s, int first, int count, cudaStream_t st) {
     k_mirror<<<1, 32, 0, st>>>(s->S, s->ctrl, s->S_host, s->ctrl_host);
     SG_CHECK_CUDA(cudaGetLastError());
     SG_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (s->halo && s->halo->peer) return sg_peer_check(s->halo->peer);
     return SG_OK;
 }
 
@@ -674,20 +677,64 @@ int sg_halo_plan_create(sg_ctx *ctx, int32_t n_segments, const sg_halo_segment *
     p->n = n_segments;
     p->seg = new sg_halo_segment[n_segments > 0 ? n_segments : 1];
     for (int i = 0; i < n_segments; ++i) p->seg[i] = segments[i];
+    p->peer = nullptr;
     *out = p;
     return SG_OK;
 }
 
 int sg_halo_plan_destroy(sg_halo_plan *plan) {
     if (!plan) return SG_OK;
+    if (plan->peer) sg_peer_destroy(plan->peer);
     delete[] plan->seg;
     delete plan;
     return SG_OK;
 }
 
+// Peer-memory path: returns 1 and fills handle64 when this plan can use it (at most one neighbour below and one
+// above this rank), 0 otherwise.  The caller gathers the 64-byte handles of all ranks and calls sg_halo_peer_open.
+int sg_halo_peer_alloc(sg_halo_plan *plan, void *handle64) {
+    SG_REQUIRE(plan && handle64, "sg_halo_peer_alloc: NULL argument");
+    if (plan->ctx->nranks < 2 || plan->n > 2) return 0;
+    int below = 0, above = 0;
+    int64_t mx = 0;
+    for (int i = 0; i < plan->n; ++i) {
+        (plan->seg[i].peer < plan->ctx->rank ? below : above)++;
+        if (plan->seg[i].send_count > mx) mx = plan->seg[i].send_count;
+        if (plan->seg[i].recv_count > mx) mx = plan->seg[i].recv_count;
+    }
+    if (below > 1 || above > 1) return 0;
+    if (plan->peer) return 0;
+    const int rc = sg_peer_create(plan->ctx, (size_t)mx, &plan->peer, handle64);
+    if (rc != SG_OK) {
+        plan->peer = nullptr;
+        return rc;
+    }
+    return 1;
+}
+
+// handles == NULL: some rank could not allocate; drop the peer path everywhere (NCCL stays in use).
+int sg_halo_peer_open(sg_halo_plan *plan, const void *handles) {
+    SG_REQUIRE(plan, "sg_halo_peer_open: NULL plan");
+    if (!plan->peer) return SG_OK;
+    if (!handles) {
+        sg_peer_destroy(plan->peer);
+        plan->peer = nullptr;
+        return SG_OK;
+    }
+    const int rc = sg_peer_open(plan->peer, handles);
+    if (rc != SG_OK) {
+        sg_peer_destroy(plan->peer);
+        plan->peer = nullptr;
+    }
+    return rc;
+}
+
+int sg_halo_uses_peer_memory(const sg_halo_plan *plan) { return plan && sg_peer_ready(plan->peer) ? 1 : 0; }
+
 int sg_halo_forward(sg_halo_plan *plan, double *vec, int32_t bs, void *stream) {
     SG_REQUIRE(plan && vec && bs >= 1, "sg_halo_forward: bad argument");
     if (plan->n == 0) return SG_OK;
+    if (bs == 1 && sg_peer_ready(plan->peer)) return sg_peer_halo_forward(plan->peer, plan->n, plan->seg, vec, (cudaStream_t)stream);
     const SgNccl *n = sg_nccl();
     if (!n || !plan->ctx->comm) {
         sg_set_error("sg_halo_forward: context has no NCCL communicator");

@@ -59,6 +59,17 @@ struct SgChebStep {
 bool sg_thermal_has_cheb(const sg_thermal_op *op);
 int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
 
+// peer.cu: NVLink peer-memory halo exchange and small all-reduce (replaces NCCL on the solver's data path)
+struct SgPeer;
+int sg_peer_create(sg_ctx *ctx, size_t mailbox_doubles, SgPeer **out, void *handle64);
+int sg_peer_open(SgPeer *p, const void *handles /* nranks x 64 bytes */);
+int sg_peer_destroy(SgPeer *p);
+bool sg_peer_ready(const SgPeer *p);
+size_t sg_peer_mailbox_doubles(const SgPeer *p);
+int sg_peer_check(SgPeer *p);
+int sg_peer_halo_forward(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, cudaStream_t st);
+int sg_peer_allreduce(SgPeer *p, double *vals, int count, cudaStream_t st);
+
 // classify.cu: equivalence classes of 64-bit keys.  cls_out[i] = class of keys[i] in [0, *n_cls),
 // rep_out[k] = index of one member of class k; both are cudaMalloc'ed here and freed by the caller.
 int sg_classify_u64(const uint64_t *keys_dev, int64_t n, int32_t **cls_out, int32_t *n_cls, int32_t **rep_out);

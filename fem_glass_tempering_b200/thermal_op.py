@@ -100,6 +100,9 @@ class ThermalOperator:
             hh = C.c_void_p()
             _lib.check(L.sg_halo_plan_create(ctx.handle, len(segs), arr, C.byref(hh)))
             self.halo = hh
+        self.peer_memory = False
+        if ctx.nranks > 1:
+            self._setup_peer_memory(L)
         nws = L.sg_thermal_solver_workspace_doubles(self.handle)
         self.workspace = torch.zeros(max(int(nws), 1), dtype=torch.float64, device=dev)
         sh = C.c_void_p()
@@ -114,6 +117,33 @@ class ThermalOperator:
         if cheb_degree:
             self.set_chebyshev(cheb_degree)
         self.last_stats = None
+
+    def _setup_peer_memory(self, L) -> None:
+        """NVLink peer-memory transport of the halo / small all-reduces (sg_halo_peer_alloc/open): every rank exports one
+        communication block, the 64-byte IPC handles travel through torch.distributed.  Collective over all ranks;
+        SG_NO_PEER=1 keeps NCCL on the data path."""
+        import os
+        import torch.distributed as dist
+        handle = C.create_string_buffer(64)
+        rc = 0
+        if self.halo is not None and os.environ.get("SG_NO_PEER", "0") != "1":
+            rc = L.sg_halo_peer_alloc(self.halo, handle)
+        mine = handle.raw if rc == 1 else None
+        everyone = [None] * self.ctx.nranks
+        dist.all_gather_object(everyone, mine)
+        if self.halo is None:
+            return
+        if all(h is not None for h in everyone):
+            blob = C.create_string_buffer(b"".join(everyone), 64 * self.ctx.nranks)
+            ok = L.sg_halo_peer_open(self.halo, blob) == 0
+        else:
+            L.sg_halo_peer_open(self.halo, None)
+            ok = False
+        flags = [None] * self.ctx.nranks
+        dist.all_gather_object(flags, bool(ok and L.sg_halo_uses_peer_memory(self.halo)))
+        if not all(flags):                       # one rank could not map a neighbour: nobody uses the peer path
+            L.sg_halo_peer_open(self.halo, None)
+        self.peer_memory = bool(L.sg_halo_uses_peer_memory(self.halo))
 
     # -- raw operator calls (asynchronous on the current stream) ---------------------------------
     def residual(self, T, T_prev, out):

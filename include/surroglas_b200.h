@@ -210,6 +210,15 @@ typedef struct sg_halo_plan sg_halo_plan;
 int sg_halo_plan_create(sg_ctx *ctx, int32_t n_segments, const sg_halo_segment *segments, sg_halo_plan **out);
 int sg_halo_plan_destroy(sg_halo_plan *plan);
 int sg_halo_forward(sg_halo_plan *plan, double *vec, int32_t block_size, void *stream);
+/* Optional NVLink peer-memory transport for block_size 1 exchanges and the solver's 1-2 double all-reduces (one
+ * process per GPU, all on one NVSwitch domain): boundary rows are stored straight into the neighbour's memory and
+ * published with a sequence flag; no NCCL launch on the data path.  sg_halo_peer_alloc returns 1 and a 64-byte
+ * cudaIpcMemHandle_t when the plan qualifies (0 otherwise, <0 on error); the host gathers the handles of ALL ranks
+ * (rank order, 64 bytes each) and passes them to sg_halo_peer_open, or NULL if any rank returned 0.  Waits are
+ * bounded: a neighbour that never arrives turns into SG_E_NCCL at the next host synchronisation, not a hang. */
+int sg_halo_peer_alloc(sg_halo_plan *plan, void *handle64);
+int sg_halo_peer_open(sg_halo_plan *plan, const void *handles);
+int sg_halo_uses_peer_memory(const sg_halo_plan *plan);
 
 /* Newton + Jacobi-PCG time-step solver (NewtonSolver.solve, TVP:334-346,389). */
 typedef struct {

@@ -114,7 +114,7 @@ def main():
             ok = ok and good
             report.append(f"{fam}{deg} d={dim} n={n}: owned ranges tile={tiles} relerr T={worst['T']:.1e} Tf={worst['Tf']:.1e} "
                           f"sigma={worst['sigma']:.1e} its(ref)={ref.solver.last_stats.newton_its}/{ref.solver.last_stats.lin_its} "
-                          f"its(part)={gathered[0]['its']} {'ok' if good else 'FAIL'}")
+                          f"its(part)={gathered[0]['its']} peer_memory={prob._thermal_op.peer_memory} {'ok' if good else 'FAIL'}")
         dist.barrier()
     if rank == 0:
         for line in report:
