@@ -43,6 +43,9 @@ def bind(L) -> None:
     L.sg_thermal_class_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.sg_thermal_profile.argtypes = [vp, C.c_int32, C.c_int32]
     L.sg_thermal_profile_read.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.sg_thermal_profile_read_kind.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.sg_thermal_cheb_step_bytes.argtypes = [vp, C.c_int32]
+    L.sg_thermal_cheb_step_bytes.restype = C.c_int64
     L.sg_thermal_apply_bytes.argtypes = [vp]
     L.sg_thermal_apply_bytes.restype = C.c_int64
     L.sg_halo_plan_create.argtypes = [vp, C.c_int32, C.POINTER(HaloSegmentC), C.POINTER(vp)]

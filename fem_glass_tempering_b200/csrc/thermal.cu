@@ -17,6 +17,9 @@
 // small separate kernel.
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "sg_common.cuh"
 
 namespace {
@@ -625,6 +628,14 @@ __global__ void __launch_bounds__(TB) cg_bfacet_apply(const OpDev op, const doub
     sg_grid_reduce<1>(dsum, red, dot_out);
 }
 
+// fraction of the pairs (c, c + stride) of the paired work decomposition whose class words agree
+__global__ void k_pair_score(const uint64_t *cls, long lo, long groups, long stride, unsigned long long *matches) {
+    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= groups * stride) return;
+    const long g = q / stride, r = q - g * stride, c0 = lo + g * 2 * stride + r;
+    if (cls[c0] == cls[c0 + stride]) atomicAdd(matches, 1ull);
+}
+
 struct ClsDev {
     long n_cells, cell_lo, cell_hi, dot_lo, dot_hi;
     const int32_t *nbr;     // DG [NNB][n_cells]
@@ -636,6 +647,8 @@ struct ClsDev {
     // exterior facets handled inside the DG class kernel (P1): nbr holds -2 - b for exterior facet b and
     // bmat[b] the packed symmetric matrix  dt*0.001*int (4 sigma eps T^3 + htc) phi_k phi_l ds  over the facet's dofs
     const double *bmat;
+    // two cells per thread (dg_cell_apply2): c and c + pair_stride are processed together; 0 = off
+    long pair_stride, pair_groups;
 };
 
 constexpr int CB = 256;  // threads per block of the class kernels
@@ -708,6 +721,26 @@ __device__ __forceinline__ void smem_matvec_acc(const double *__restrict__ A, co
     }
 }
 
+// Exterior facet f of a DG cell: y_K += B_f x_K on the facet's dofs (nb = -2 - facet index, see ClsDev::bmat).
+template <int NLD, int NNB, int P>
+__device__ __forceinline__ void dg_exterior_facet(const ClsDev &cd, const int f, const int nb, const double (&xk)[NLD], double (&yk)[NLD]) {
+    constexpr int D = NNB - 1, NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
+    const double *Bp = cd.bmat + (long)(-2 - nb) * NFDP;
+    double B[NFDP];
+#pragma unroll
+    for (int k = 0; k < NFDP; ++k) B[k] = Bp[k];
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < NFD; ++k)
+#pragma unroll
+        for (int l = k; l < NFD; ++l) {
+            const int ik = facet_dof(D, P, f, k), il = facet_dof(D, P, f, l);
+            yk[ik] += B[m] * xk[il];
+            if (l != k) yk[il] += B[m] * xk[ik];
+            ++m;
+        }
+}
+
 // Element vector of DG cell c from the class tables: loads the class word, the neighbour ids, the cell's row
 // xk and the neighbours' rows of x, returns yk = A_self x_K + sum_f A_nb x_N (+ exterior-facet matrices).
 template <int NLD, int NNB, int P, bool WIDE, bool BND>
@@ -737,25 +770,97 @@ __device__ __forceinline__ void dg_cell_apply(const ClsDev &cd, const double *s_
         const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
         if (u) smem_matvec_acc<NLD>(s_nb + (u - 1) * cd.S, xn[f], yk);
         if constexpr (BND) {
-            if (nb[f] < -1) {   // exterior facet: y_K += B_f x_K on the facet's dofs
-                constexpr int D = NNB - 1, NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
-                const double *Bp = cd.bmat + (long)(-2 - nb[f]) * NFDP;
-                double B[NFDP];
-#pragma unroll
-                for (int k = 0; k < NFDP; ++k) B[k] = Bp[k];
-                int m = 0;
-#pragma unroll
-                for (int k = 0; k < NFD; ++k)
-#pragma unroll
-                    for (int l = k; l < NFD; ++l) {
-                        const int ik = facet_dof(D, P, f, k), il = facet_dof(D, P, f, l);
-                        yk[ik] += B[m] * xk[il];
-                        if (l != k) yk[il] += B[m] * xk[ik];
-                        ++m;
-                    }
-            }
+            if (nb[f] < -1) dg_exterior_facet<NLD, NNB, P>(cd, f, nb[f], xk, yk);
         }
     }
+}
+
+// Two right-hand sides against ONE table read: acc0 += A x0, acc1 += A x1.
+template <int NLD>
+__device__ __forceinline__ void smem_matvec_acc2(const double *__restrict__ A, const double (&x0)[NLD], const double (&x1)[NLD],
+                                                 double (&acc0)[NLD], double (&acc1)[NLD]) {
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        double a0 = acc0[i], a1 = acc1[i];
+        if constexpr (NLD % 2 == 0) {
+            const double2 *row = reinterpret_cast<const double2 *>(A + i * NLD);
+#pragma unroll
+            for (int j = 0; j < NLD / 2; ++j) {
+                const double2 t = row[j];
+                a0 += t.x * x0[2 * j];
+                a1 += t.x * x1[2 * j];
+                a0 += t.y * x0[2 * j + 1];
+                a1 += t.y * x1[2 * j + 1];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) {
+                const double t = A[i * NLD + j];
+                a0 += t * x0[j];
+                a1 += t * x1[j];
+            }
+        }
+        acc0[i] = a0;
+        acc1[i] = a1;
+    }
+}
+
+// Two cells per thread (c1 = c0 + pair stride: the same Kuhn type one tile-pair further, mesh.py): when their class
+// words agree — everywhere except next to some boundaries — every shared-memory table entry is read once and used
+// for both, which halves the shared-memory wavefronts that bound the single-cell kernel.
+template <int NLD, int NNB, int P, bool WIDE, bool BND>
+__device__ __forceinline__ void dg_cell_apply2(const ClsDev &cd, const double *s_tab, const double *s_nb, const long c0, const long c1,
+                                               const double *__restrict__ x, double (&xk0)[NLD], double (&yk0)[NLD],
+                                               double (&xk1)[NLD], double (&yk1)[NLD]) {
+    const long nc = cd.n_cells;
+    const uint64_t w = cd.cls64[c0];
+    if (w != cd.cls64[c1]) {
+        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, x, xk0, yk0);
+        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c1, x, xk1, yk1);
+        return;
+    }
+    int nb0[NNB], nb1[NNB];
+#pragma unroll
+    for (int f = 0; f < NNB; ++f) {
+        nb0[f] = cd.nbr[(long)f * nc + c0];
+        nb1[f] = cd.nbr[(long)f * nc + c1];
+    }
+    load_row<NLD, WIDE>(x + c0 * NLD, xk0);
+    load_row<NLD, WIDE>(x + c1 * NLD, xk1);
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) yk0[i] = yk1[i] = 0.0;
+    smem_matvec_acc2<NLD>(s_tab + (int)(w & 0xFFFFull) * cd.S, xk0, xk1, yk0, yk1);
+#pragma unroll
+    for (int f = 0; f < NNB; ++f) {
+        const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
+        if (u) {   // equal class words: facet f is interior for both cells
+            double xa[NLD], xb[NLD];
+            load_row<NLD, WIDE>(x + (long)nb0[f] * NLD, xa);
+            load_row<NLD, WIDE>(x + (long)nb1[f] * NLD, xb);
+            smem_matvec_acc2<NLD>(s_nb + (u - 1) * cd.S, xa, xb, yk0, yk1);
+        }
+        if constexpr (BND) {
+            if (nb0[f] < -1) dg_exterior_facet<NLD, NNB, P>(cd, f, nb0[f], xk0, yk0);
+            if (nb1[f] < -1) dg_exterior_facet<NLD, NNB, P>(cd, f, nb1[f], xk1, yk1);
+        }
+    }
+}
+
+// Work item -> cells of the paired kernels: groups of 2*stride cells, item (g, r) -> c0 = lo + g*2*stride + r and
+// c1 = c0 + stride; the cells behind the last full group are single items (c1 = -1).
+__device__ __forceinline__ void pair_cells(const ClsDev &cd, const long item, long &c0, long &c1) {
+    const long st = cd.pair_stride, paired = cd.pair_groups * st;
+    if (item < paired) {
+        const long g = item / st, r = item - g * st;
+        c0 = cd.cell_lo + g * 2 * st + r;
+        c1 = c0 + st;
+    } else {
+        c0 = cd.cell_lo + cd.pair_groups * 2 * st + (item - paired);
+        c1 = -1;
+    }
+}
+__device__ __forceinline__ long pair_items(const ClsDev &cd) {
+    return cd.pair_groups * cd.pair_stride + (cd.cell_hi - cd.cell_lo - cd.pair_groups * 2 * cd.pair_stride);
 }
 
 __device__ __forceinline__ void load_class_tables(const ClsDev &cd, double *s_tab, int ntab) {
@@ -765,21 +870,42 @@ __device__ __forceinline__ void load_class_tables(const ClsDev &cd, double *s_ta
 
 // DG fast apply: persistent grid-stride blocks, class tables in shared memory, fused x.y reduction.
 // A warp handles 32 consecutive cells; when these share their classes (the plate meshes number the cells
-// in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.
-template <int NLD, int NNB, int P, bool WIDE, bool BND>
-__global__ void __launch_bounds__(CB, 3) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
-                                                     SgRed red, double *dot_out, const int *skip) {
+// in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.  PAIR: two cells per
+// thread sharing the table reads (dg_cell_apply2).
+template <int NLD, int NNB, int P, bool WIDE, bool BND, bool PAIR = false>
+__global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
+                                                                   SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
     load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
     const double *s_nb = s_tab + cd.n_self * cd.S;
     double dsum[2] = {0.0, 0.0};   // [1] stays 0: slot of the separate exterior-facet kernel (overwritten by it when it runs)
-    for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
-        double xk[NLD], yk[NLD];
-        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
-        store_row<NLD, WIDE>(y + c * NLD, yk);
+    if constexpr (PAIR) {
+        const long items = pair_items(cd);
+        for (long it = (long)blockIdx.x * CB + threadIdx.x; it < items; it += (long)gridDim.x * CB) {
+            long c0, c1;
+            pair_cells(cd, it, c0, c1);
+            double xk0[NLD], yk0[NLD], xk1[NLD], yk1[NLD];
+            if (c1 >= 0) {
+                dg_cell_apply2<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, c1, x, xk0, yk0, xk1, yk1);
+                store_row<NLD, WIDE>(y + c1 * NLD, yk1);
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
+                for (int i = 0; i < NLD; ++i) dsum[0] += xk1[i] * yk1[i];
+            } else {
+                dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, x, xk0, yk0);
+            }
+            store_row<NLD, WIDE>(y + c0 * NLD, yk0);
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) dsum[0] += xk0[i] * yk0[i];
+        }
+    } else {
+        for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
+            double xk[NLD], yk[NLD];
+            dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
+            store_row<NLD, WIDE>(y + c * NLD, yk);
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
+        }
     }
     sg_grid_reduce<2>(dsum, red, dot_out);
 }
@@ -859,34 +985,56 @@ struct ChebDev {
     double minv[100];   // Mhat^-1, row-major NLD x NLD
 };
 
-template <int NLD, int NNB, int P, bool WIDE, bool BND, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(CB, 3) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
-                                                      SgRed red, double *dot_out, const int *skip) {
+template <int NLD, bool WIDE, bool FIRST, bool LAST>
+__device__ __forceinline__ void cheb_update(const ChebDev &ch, const long c, const double (&zk)[NLD], double (&Jz)[NLD], double &dsum) {
+    double rk[NLD], zp[NLD];
+    load_row<NLD, WIDE>(ch.r + c * NLD, rk);
+    if (!FIRST) load_row<NLD, WIDE>(ch.z_prev + c * NLD, zp);
+    const double idet = ch.b / ch.detJ[c];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) Jz[i] = rk[i] - Jz[i];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        double m = 0.0;
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) m += ch.minv[i * NLD + j] * Jz[j];
+        const double dprev = FIRST ? zk[i] : zk[i] - zp[i];
+        zp[i] = zk[i] + (ch.a * dprev + idet * m);
+    }
+    store_row<NLD, WIDE>(ch.z_out + c * NLD, zp);
+    if (LAST) {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) dsum += rk[i] * zp[i];
+    }
+}
+
+template <int NLD, int NNB, int P, bool WIDE, bool BND, bool FIRST, bool LAST, bool PAIR = false>
+__global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
+                                                                 SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
     load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
     const double *s_nb = s_tab + cd.n_self * cd.S;
     double dsum[1] = {0.0};
-    for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
-        double zk[NLD], Jz[NLD], rk[NLD], zp[NLD];
-        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
-        load_row<NLD, WIDE>(ch.r + c * NLD, rk);
-        if (!FIRST) load_row<NLD, WIDE>(ch.z_prev + c * NLD, zp);
-        const double idet = ch.b / ch.detJ[c];
-#pragma unroll
-        for (int i = 0; i < NLD; ++i) Jz[i] = rk[i] - Jz[i];
-#pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-            double m = 0.0;
-#pragma unroll
-            for (int j = 0; j < NLD; ++j) m += ch.minv[i * NLD + j] * Jz[j];
-            const double dprev = FIRST ? zk[i] : zk[i] - zp[i];
-            zp[i] = zk[i] + (ch.a * dprev + idet * m);
+    if constexpr (PAIR) {
+        const long items = pair_items(cd);
+        for (long it = (long)blockIdx.x * CB + threadIdx.x; it < items; it += (long)gridDim.x * CB) {
+            long c0, c1;
+            pair_cells(cd, it, c0, c1);
+            double zk0[NLD], Jz0[NLD], zk1[NLD], Jz1[NLD];
+            if (c1 >= 0) {
+                dg_cell_apply2<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, c1, z, zk0, Jz0, zk1, Jz1);
+                cheb_update<NLD, WIDE, FIRST, LAST>(ch, c1, zk1, Jz1, dsum[0]);
+            } else {
+                dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, z, zk0, Jz0);
+            }
+            cheb_update<NLD, WIDE, FIRST, LAST>(ch, c0, zk0, Jz0, dsum[0]);
         }
-        store_row<NLD, WIDE>(ch.z_out + c * NLD, zp);
-        if (LAST) {
-#pragma unroll
-            for (int i = 0; i < NLD; ++i) dsum[0] += rk[i] * zp[i];
+    } else {
+        for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
+            double zk[NLD], Jz[NLD];
+            dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
+            cheb_update<NLD, WIDE, FIRST, LAST>(ch, c, zk, Jz, dsum[0]);
         }
     }
     if (LAST) sg_grid_reduce<1>(dsum, red, dot_out);
@@ -941,7 +1089,7 @@ struct sg_thermal_op {
     ClsDev cls;
     void *cls_words;       // cls64 / cls16 storage
     double *cls_tab;
-    int cls_grid;
+    int cls_grid, cls_grid_pair;
     size_t cls_smem;
     int32_t n_geom_classes;
     SgRed own_red;         // reduction scratch of sg_thermal_jac_apply (solver-less use of the fast path)
@@ -952,6 +1100,7 @@ struct sg_thermal_op {
     // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
     int prof_on, prof_n, prof_cap;
     cudaEvent_t *prof_ev;
+    unsigned char *prof_kind;   // per recorded launch: 0 = Jacobian-apply cell kernel, 1 = fused Chebyshev step
     int (*launch)(const sg_thermal_op *, int mode, const double *T, const double *x, const double *xprev, double *y,
                   SgRed red, double *dot2, const int *skip, cudaStream_t st);
     int (*build_classes)(sg_thermal_op *);
@@ -969,9 +1118,12 @@ struct ProfScope {  // CUDA-event pair around the apply cell kernel when profili
     const sg_thermal_op *op;
     cudaStream_t st;
     bool on;
-    ProfScope(const sg_thermal_op *o, int mode, cudaStream_t s) : op(o), st(s) {
+    ProfScope(const sg_thermal_op *o, int mode, cudaStream_t s, int kind = 0) : op(o), st(s) {
         on = mode == MODE_APPLY && o->prof_on && o->prof_n < o->prof_cap;
-        if (on) cudaEventRecord(o->prof_ev[2 * o->prof_n], st);
+        if (on) {
+            o->prof_kind[o->prof_n] = (unsigned char)kind;
+            cudaEventRecord(o->prof_ev[2 * o->prof_n], st);
+        }
     }
     ~ProfScope() {
         if (on) {
@@ -999,9 +1151,13 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         ProfScope ps(op, mode, st);
         const bool wide = (((uintptr_t)x | (uintptr_t)y) & 31) == 0;
         if constexpr (DG) {
-            auto k = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true> : dg_class_apply<NLD, D + 1, P, false, true>)
-                              : (wide ? dg_class_apply<NLD, D + 1, P, true, false> : dg_class_apply<NLD, D + 1, P, false, false>);
-            k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+            if (op->cls.pair_stride > 0 && wide && op->bmat) {
+                dg_class_apply<NLD, D + 1, P, true, true, true><<<op->cls_grid_pair, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+            } else {
+                auto k = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true> : dg_class_apply<NLD, D + 1, P, false, true>)
+                                  : (wide ? dg_class_apply<NLD, D + 1, P, true, false> : dg_class_apply<NLD, D + 1, P, false, false>);
+                k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+            }
         } else
             cg_class_apply<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
         SG_CHECK_CUDA(cudaGetLastError());
@@ -1096,9 +1252,16 @@ int cheb_step_t(const sg_thermal_op *op, const SgChebStep &cs, SgRed red, double
               {dg_cheb_step<NLD, NNB, P, true, false, true, false>, dg_cheb_step<NLD, NNB, P, true, false, true, true>}},
              {{dg_cheb_step<NLD, NNB, P, true, true, false, false>, dg_cheb_step<NLD, NNB, P, true, true, false, true>},
               {dg_cheb_step<NLD, NNB, P, true, true, true, false>, dg_cheb_step<NLD, NNB, P, true, true, true, true>}}}};
-        const K k = table[wide][bnd][first][last];
+        static const K pair_table[2][2] = {
+            {dg_cheb_step<NLD, NNB, P, true, true, false, false, true>, dg_cheb_step<NLD, NNB, P, true, true, false, true, true>},
+            {dg_cheb_step<NLD, NNB, P, true, true, true, false, true>, dg_cheb_step<NLD, NNB, P, true, true, true, true, true>}};
+        const bool pair = op->cls.pair_stride > 0 && wide && bnd;
+        const K k = pair ? pair_table[first][last] : table[wide][bnd][first][last];
         SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
-        k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, ch, cs.z_in, red, dot_out, skip);
+        {
+            ProfScope ps(op, MODE_APPLY, st, 1);
+            k<<<pair ? op->cls_grid_pair : op->cls_grid, CB, op->cls_smem, st>>>(op->cls, ch, cs.z_in, red, dot_out, skip);
+        }
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
         return SG_OK;
@@ -1216,6 +1379,45 @@ int build_classes_t(sg_thermal_op *op) {
     cd.n_nb = NF;
     cd.S = S;
     cd.bmat = nullptr;
+    cd.pair_stride = cd.pair_groups = 0;
+    op->cls_grid_pair = 0;
+    if (DG && NLD % 4 == 0 && (op->d.flags & SG_THERMAL_PAIRS)) {
+        // two cells per thread: find the stride at which cells repeat their class word (tile-ordered plates: one
+        // tile-pair = 32 * n_types cells); needs a clear majority of matching pairs to pay off
+        const long ncell = dv.cell_hi - dv.cell_lo;
+        const long cand[] = {32, 64, 96, 128, 192, 256, 384, 512, 768};
+        DevBuf cnt;
+        SG_CHECK_CUDA(cudaMalloc(&cnt.p, sizeof(unsigned long long)));
+        double best = 0.0;
+        long best_stride = 0;
+        for (long stp : cand) {
+            const long groups = ncell / (2 * stp);
+            if (groups < 8) continue;
+            SG_CHECK_CUDA(cudaMemset(cnt.p, 0, sizeof(unsigned long long)));
+            k_pair_score<<<(unsigned)((groups * stp + 255) / 256), 256>>>((const uint64_t *)op->cls_words, dv.cell_lo, groups, stp,
+                                                                          cnt.as<unsigned long long>());
+            unsigned long long m = 0;
+            SG_CHECK_CUDA(cudaMemcpy(&m, cnt.p, sizeof(m), cudaMemcpyDeviceToHost));
+            const double score = (double)m / (double)(groups * stp);
+            if (score > best + 1e-9) {
+                best = score;
+                best_stride = stp;
+            }
+        }
+        if (best >= 0.75) {
+            cd.pair_stride = best_stride;
+            cd.pair_groups = ncell / (2 * best_stride);
+            int per_sm_pair = 0;
+            SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, D + 1, P, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pair, dg_class_apply<NLD, D + 1, P, true, true, true>, CB, smem));
+            const long items = cd.pair_groups * best_stride + (ncell - cd.pair_groups * 2 * best_stride);
+            long gp = (long)(per_sm_pair > 0 ? per_sm_pair : 1) * op->ctx->sm_count;
+            const long needp = (items + CB - 1) / CB;
+            if (gp > needp) gp = needp;
+            if (gp > SG_MAX_BLOCKS) gp = SG_MAX_BLOCKS;
+            op->cls_grid_pair = (int)gp;
+        }
+    }
     if (dv.n_bf > 0) {
         // exterior facets from per-facet linearised boundary matrices (sg_thermal_linearize); DG applies them inside
         // the class kernel through its own copy of the neighbour ids with the exterior facets encoded
@@ -1434,6 +1636,7 @@ int sg_thermal_op_destroy(sg_thermal_op *op) {
     if (op->own_red.counter) cudaFree(op->own_red.counter);
     for (int i = 0; i < 2 * op->prof_cap; ++i) cudaEventDestroy(op->prof_ev[i]);
     delete[] op->prof_ev;
+    delete[] op->prof_kind;
     ::operator delete(op->tab_host);
     delete op;
     return SG_OK;
@@ -1477,6 +1680,8 @@ int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity) {
     if (enable && op->prof_cap < capacity) {
         for (int i = 0; i < 2 * op->prof_cap; ++i) cudaEventDestroy(op->prof_ev[i]);
         delete[] op->prof_ev;
+        delete[] op->prof_kind;
+        op->prof_kind = new unsigned char[capacity];
         op->prof_ev = new cudaEvent_t[2 * capacity];
         for (int i = 0; i < 2 * capacity; ++i) SG_CHECK_CUDA(cudaEventCreate(&op->prof_ev[i]));
         op->prof_cap = capacity;
@@ -1486,18 +1691,46 @@ int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity) {
     return SG_OK;
 }
 
-int sg_thermal_profile_read(sg_thermal_op *op, int64_t *n_launches, double *ms_total) {
+// Launches of kind `kind` recorded since the last enable.  Launches that returned at once because the solve had
+// already converged (device-side skip flag) are recognised by their duration (< 1/4 of the median) and left out.
+int sg_thermal_profile_read_kind(sg_thermal_op *op, int32_t kind, int64_t *n_launches, double *ms_total) {
     SG_REQUIRE(op && n_launches && ms_total, "sg_thermal_profile_read: NULL argument");
-    double tot = 0.0;
+    std::vector<float> t;
     for (int i = 0; i < op->prof_n; ++i) {
+        if (op->prof_kind[i] != kind) continue;
         float ms = 0.f;
         SG_CHECK_CUDA(cudaEventSynchronize(op->prof_ev[2 * i + 1]));
         SG_CHECK_CUDA(cudaEventElapsedTime(&ms, op->prof_ev[2 * i], op->prof_ev[2 * i + 1]));
-        tot += ms;
+        t.push_back(ms);
     }
-    *n_launches = op->prof_n;
+    double tot = 0.0;
+    int64_t n = 0;
+    if (!t.empty()) {
+        std::vector<float> sorted(t);
+        std::sort(sorted.begin(), sorted.end());
+        const float cut = 0.25f * sorted[sorted.size() / 2];
+        for (float v : t)
+            if (v >= cut) {
+                tot += v;
+                ++n;
+            }
+    }
+    *n_launches = n;
     *ms_total = tot;
     return SG_OK;
+}
+
+int sg_thermal_profile_read(sg_thermal_op *op, int64_t *n_launches, double *ms_total) {
+    return sg_thermal_profile_read_kind(op, 0, n_launches, ms_total);
+}
+
+// Algorithmic HBM bytes of one fused Chebyshev step (dg_cheb_step): the apply's traffic + r, z_prev (not in the
+// first step), |detJ| per cell; z_out replaces y.
+int64_t sg_thermal_cheb_step_bytes(const sg_thermal_op *op, int32_t first) {
+    if (!op || !op->cls.tab || op->d.family != 1) return -1;
+    const sg_thermal_desc &d = op->d;
+    const int64_t ncell = d.cell_hi - d.cell_lo;
+    return sg_thermal_apply_bytes(op) + ncell * (8 + 8 * d.n_ld * (first ? 1 : 2));
 }
 
 // Algorithmic HBM bytes of the cell kernel of one Jacobian apply, for the layout actually in use.

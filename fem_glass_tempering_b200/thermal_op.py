@@ -30,7 +30,7 @@ class ThermalOperator:
     """
 
     def __init__(self, ctx: _lib.Context, space: fe.ScalarSpace, params: dict, dt: float, partition: dict | None = None,
-                 use_classes: bool = True, cheb_degree: int | None = None):
+                 use_classes: bool = True, cheb_degree: int | None = None, use_pairs: bool | None = None):
         import torch
         self.ctx, self.space, self.dt = ctx, space, float(dt)
         mesh, d = space.mesh, space.mesh.dim
@@ -71,7 +71,10 @@ class ThermalOperator:
         desc.n_cells, desc.cell_lo, desc.cell_hi = nc, part.get("cell_lo", 0), part.get("cell_hi", nc)
         desc.n_dofs, desc.own_lo, desc.own_hi = space.n_nodes, part.get("own_lo", 0), part.get("own_hi", space.n_nodes)
         desc.own_cell_lo, desc.own_cell_hi = part.get("own_cell_lo", desc.cell_lo), part.get("own_cell_hi", desc.cell_hi)
-        desc.flags = 0 if use_classes else 1     # SG_THERMAL_NO_CLASSES
+        if use_pairs is None:
+            import os
+            use_pairs = os.environ.get("SG_PAIRS", "0") == "1"      # two cells per thread: measured slower, opt-in
+        desc.flags = (0 if use_classes else 1) | (4 if use_pairs else 0)     # SG_THERMAL_NO_CLASSES, SG_THERMAL_PAIRS
         for name in ("dofmap", "geom", "nbr", "nbinfo", "bf_cell", "bf_facet", "bf_area"):
             setattr(desc, name, _lib.ptr(keep.get(name)))
         desc.n_bfacets = nbf

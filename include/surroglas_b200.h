@@ -175,7 +175,10 @@ typedef struct {
 
 enum {
     SG_THERMAL_NO_CLASSES = 1,      /* never use the local-matrix class tables (general per-cell-geometry kernel only) */
-    SG_THERMAL_GENERAL_RESIDUAL = 2 /* evaluate the residual with the per-cell-geometry kernel even when the tables exist */
+    SG_THERMAL_GENERAL_RESIDUAL = 2,/* evaluate the residual with the per-cell-geometry kernel even when the tables exist */
+    SG_THERMAL_PAIRS = 4            /* DG class kernels: two cells per thread sharing the shared-memory table reads.  Off by
+                                       default: measured SLOWER on B200 (Chebyshev step 211 vs 183 us on C3; 128 registers halve
+                                       the resident warps), kept for experiments */
 };
 
 typedef struct sg_thermal_op sg_thermal_op;
@@ -196,6 +199,10 @@ int sg_thermal_class_info(const sg_thermal_op *op, int32_t *n_geometry, int32_t 
  * (measurement harness only; at most `capacity` launches are recorded after each enable). */
 int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity);
 int sg_thermal_profile_read(sg_thermal_op *op, int64_t *n_launches, double *ms_total);
+/* kind 0 = Jacobian-apply cell kernel, 1 = fused Chebyshev step of the DG solver; launches that returned
+ * immediately (solve already converged) are excluded. */
+int sg_thermal_profile_read_kind(sg_thermal_op *op, int32_t kind, int64_t *n_launches, double *ms_total);
+int64_t sg_thermal_cheb_step_bytes(const sg_thermal_op *op, int32_t first);
 /* Algorithmic HBM bytes of one sg_thermal_jac_apply (roofline numerator). */
 int64_t sg_thermal_apply_bytes(const sg_thermal_op *op);
 

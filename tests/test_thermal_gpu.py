@@ -170,6 +170,34 @@ def test_chebyshev_is_not_offered_for_cg_spaces(sg_ctx):
     assert op.chebyshev_degree == 0 and not op.set_chebyshev(3)
 
 
+@pytest.mark.parametrize("dims", [(20, 16, 8), (9, 8, 8), (8, 8, 4)])
+def test_two_cells_per_thread_kernels_match_single(sg_ctx, dims):
+    """DG1 3-D class kernels with two cells per thread (pairs one tile-pair apart sharing the table reads, plus the
+    unpaired tail and pairs whose classes differ) against the one-cell-per-thread kernels and the oracle."""
+    m = msh.box_mesh(*dims, *(float(k) for k in dims))
+    space = fe.ScalarSpace(m, "DG", 1)
+    n = space.n_nodes
+    rng = np.random.default_rng(4)
+    T = 700 + 100 * rng.random(n)
+    x = rng.standard_normal(n)
+    b = rng.standard_normal(n)
+    out = {}
+    for pairs in (True, False):
+        op = ThermalOperator(sg_ctx, space, MAIN_PARAMS, 0.1, use_pairs=pairs, cheb_degree=3)
+        y = torch.empty(n, dtype=torch.float64, device="cuda:0")
+        op.jac_apply(dev(T), dev(x), y)
+        xd = torch.zeros(n, dtype=torch.float64, device="cuda:0")
+        its, res = op.pcg(dev(T), dev(b), xd, rtol=1e-12)
+        out[pairs] = (y.cpu().numpy(), xd.cpu().numpy(), its)
+    assert np.max(np.abs(out[True][0] - out[False][0])) <= 1e-13 * np.max(np.abs(out[False][0]))
+    assert np.max(np.abs(out[True][1] - out[False][1])) <= 1e-10 * np.max(np.abs(out[False][1]))
+    assert abs(out[True][2] - out[False][2]) <= 1
+    if dims == (8, 8, 4):
+        orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "DG", 1, MAIN_PARAMS, 0.1)
+        yo = orc.jacobian(T) @ x
+        assert np.max(np.abs(out[True][0] - yo)) <= 1e-12 * np.max(np.abs(yo))
+
+
 def test_many_shapes_fall_back_to_per_cell_geometry(sg_ctx):
     """A mesh whose cells all differ (randomly perturbed vertices) has too many classes for the shared-memory tables:
     the library must keep the general kernel and still match the oracle."""
