@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(VB) k_axpy_p(long n, const double *__restrict_
                                                const double *Snext, int first, const PcgCtrl *ctrl) {
     if (ctrl->done) return;
     const double beta = first ? 0.0 : Snext[0] / Scur[0];
-    const long n2 = n >> 1;
+    const long n2 = ((((uintptr_t)z | (uintptr_t)p) & 15) == 0) ? n >> 1 : 0;   // workspace slices start at odd dofs when n is odd
     const double2 *z2 = reinterpret_cast<const double2 *>(z);
     double2 *p2 = reinterpret_cast<double2 *>(p);
     for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n2; i += (long)gridDim.x * VB) {
@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(VB) k_axpy_p(long n, const double *__restrict_
         q.y = a.y + beta * q.y;
         p2[i] = q;
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = z[n - 1] + (first ? 0.0 : beta * p[n - 1]);
+    for (long i = 2 * n2 + (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB)
+        p[i] = z[i] + (first ? 0.0 : beta * p[i]);
 }
 
 // power iteration for the largest eigenvalue of M^-1 J:  v = scale * M^-1 w,  out = |v|^2 over owned cells
