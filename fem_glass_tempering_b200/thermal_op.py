@@ -13,7 +13,8 @@ import numpy as np
 from . import _lib, fe
 from ._lib_thermal import HaloSegmentC, NewtonOptsC, NewtonStatsC, ThermalDescC
 
-PENALTY = 5.0  # ThermoViscoProblem.py:313
+PENALTY = 5.0  # ThermoViscoProblem.py:313; model_params["sip_penalty"] overrides it (the reference's 5.0 is not coercive
+               # on tetrahedra: its 3-D DG time stepping is unstable, tests/test_fe_tables.py)
 
 
 def _np_ptr(a: np.ndarray):
@@ -84,7 +85,7 @@ class ThermalOperator:
             setattr(desc, name, _np_ptr(arr))
         desc.dt, desc.alpha, desc.f = self.dt, float(params["alpha"]), float(params["f"])
         desc.sigma, desc.epsilon = float(params["sigma"]), float(params["epsilon"])
-        desc.htc, desc.T_ambient, desc.penalty = float(params["htc"]), float(params["T_ambient"]), PENALTY
+        desc.htc, desc.T_ambient, desc.penalty = float(params["htc"]), float(params["T_ambient"]), float(params.get("sip_penalty", PENALTY))
         self.own_lo, self.own_hi = desc.own_lo, desc.own_hi
         self.cell_lo, self.cell_hi = desc.cell_lo, desc.cell_hi
         self.n_bfacets = nbf

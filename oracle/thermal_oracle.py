@@ -227,7 +227,7 @@ class ThermalOracle:
             # jump(w, n) = w+ n+ + w- n-  as [nf, q, d, 2nl] over the stacked (+,-) basis
             jump = np.concatenate([vp[:, :, None, :] * n_p[:, None, :, None], vm[:, :, None, :] * n_m[:, None, :, None]], axis=3)
             avg_g = 0.5 * np.concatenate([gp, gm], axis=3)
-            pen = self.PENALTY / self.h[cp]
+            pen = float(self.p.get("sip_penalty", self.PENALTY)) / self.h[cp]   # product knob for non-reference penalties
             wq = FW[None, :] * meas[:, None]
             out = pen[:, None, None] * np.einsum("nq,nqbi,nqbj->nij", wq, jump, jump)
             out -= np.einsum("nq,nqbi,nqbj->nij", wq, avg_g, jump)

@@ -65,7 +65,7 @@ def jac_apply(space, tabs, geo, topo, params, dt, x, T_lin=None, xm=None, residu
                 dnN = np.einsum("ci,ci->c", dphiN, xN)
                 jump = vK - vN
                 w = dt * a * tabs.fq_w[q] * area
-                contrib = w[:, None] * ((fe_penalty() / hplus * jump)[:, None] * tabs.fq_val[f, q][None, :]
+                contrib = w[:, None] * ((float(params.get("sip_penalty", fe_penalty())) / hplus * jump)[:, None] * tabs.fq_val[f, q][None, :]
                                         - 0.5 * dphiK * jump[:, None]
                                         - tabs.fq_val[f, q][None, :] * (0.5 * (dnK + dnN))[:, None])
                 np.add.at(yk, act, contrib)

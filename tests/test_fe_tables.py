@@ -163,12 +163,7 @@ def test_oracle_steady_state_and_newton():
 
 @pytest.mark.parametrize("dim,n", [(1, None), (2, (8, 4)), (3, (4, 4, 2))])
 def test_dg_operator_is_spd_on_the_benchmark_plates(dim, n):
-    """CG needs an SPD Jacobian (TVP:342); check the SIP-DG operator with the reference's penalty 5/h.
-
-    The reference's penalty (5.0 / CellDiameter, independent of degree and element shape, TVP:313-320) is
-    coercive on Kuhn tetrahedra only while the mass term dominates (dt*alpha/a^2 <~ 0.15 for cube edge a):
-    with a = 0.5 mm the Jacobian has negative eigenvalues.  The 3-D DG benchmark plate therefore uses
-    1 mm cubes (320 x 320 x 8 mm plate), see DESIGN.md."""
+    """CG needs an SPD Jacobian (TVP:342); check the SIP-DG operator with the reference's penalty 5/h."""
     if dim == 3:
         m = msh.box_mesh(*n, 4 * 1.0, 4 * 1.0, 2 * 1.0)
     elif dim == 2:
@@ -180,3 +175,29 @@ def test_dg_operator_is_spd_on_the_benchmark_plates(dim, n):
     J = orc.jacobian(np.full(space.n_nodes, 800.0)).toarray()
     ev = np.linalg.eigvalsh(0.5 * (J + J.T))
     assert ev.min() > 0, f"indefinite: min eigenvalue {ev.min()}"
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_stability_of_the_dg_time_stepping(dim):
+    """Implicit Euler amplifies a mode by 1/lambda(M^-1 J): the scheme is stable iff lambda_min(M^-1 J) >= 1, i.e. iff the
+    SIP form is coercive.  The reference's penalty 5.0/CellDiameter (TVP:313-320) is coercive on lines and on the
+    right triangles of the 2-D plate but NOT on Kuhn tetrahedra (lambda_min = 0.63 at 1 mm, dt = 0.1: a 3-D DG run with
+    the reference's own formulation grows by 1.6x per step and diverges after ~15 steps, whatever the mesh size —
+    coercivity is scale invariant).  model_params["sip_penalty"] = 6.0 restores coercivity; the 3-D DG benchmark plate
+    uses it (bench.py), every parity test keeps the reference's 5.0."""
+    import scipy.linalg as sla
+    m = {1: msh.graded_line_mesh(), 2: msh.rectangle_mesh(8, 4, 8.0, 4.0), 3: msh.box_mesh(4, 4, 2, 4.0, 4.0, 2.0)}[dim]
+    space = fe.ScalarSpace(m, "DG", 1)
+
+    def lam_min(params):
+        orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "DG", 1, params, 0.1)
+        J = orc.jacobian(np.full(space.n_nodes, 800.0)).toarray()
+        return sla.eigh(0.5 * (J + J.T), orc.M.toarray(), eigvals_only=True)[0]
+
+    ref = lam_min(MAIN_PARAMS)
+    if dim < 3:
+        assert ref >= 1.0 - 1e-9, ref
+    else:
+        assert ref < 0.9, f"expected the reference penalty to be non-coercive on tetrahedra, lambda_min = {ref}"
+        assert lam_min(dict(MAIN_PARAMS, sip_penalty=6.0)) >= 1.0 - 1e-9
+
