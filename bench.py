@@ -6,17 +6,20 @@
     python bench.py --impl reference ...        # the CPU restatement of the reference, timed on the host cores
 
 A "step" is ONE FULL TIMESTEP of ThermoViscoProblem.solve_timestep (TVP:367-381): the implicit-Euler heat solve
-(Newton + matrix-free Jacobi-PCG, hot path B), the fused viscoelastic update at every quadrature point (hot
-path A) and T_prev <- T_cur; file output is disabled.  Workload (config.workload): BASELINE configs[2], the
-3-D DG1 plate with radiative/convective Robin boundary, 320x320x8 hexahedra x 6 tetrahedra = 4 915 200 cells =
-19 660 800 quadrature points PER GPU (weak scaling: the plate grows along x with N; x-slab partition).
-configs[1] (~1 M points) is launch-latency bound on a B200 and configs[3] is the multi-GPU case, so configs[2]
-is the single-GPU configuration the metric is quoted on.
+(inexact Newton + matrix-free Chebyshev-preconditioned CG, hot path B), the fused viscoelastic update at every
+quadrature point (hot path A) and T_prev <- T_cur; file output is disabled.  Workload (config.workload): BASELINE
+configs[2], the 3-D DG1 plate with radiative/convective Robin boundary, 320x320x8 hexahedra x 6 tetrahedra =
+4 915 200 cells = 19 660 800 quadrature points PER GPU (weak scaling: the plate grows along x with N; x-slab
+partition; ghost-dof halo and the solver's 1-2 double all-reduces over NVLink peer memory).  configs[1] (~1 M
+points) is launch-latency bound on a B200 and configs[3] is the multi-GPU case, so configs[2] is the single-GPU
+configuration the metric is quoted on; --workload selects the others.
 
-Printed JSON (rank 0): metric = quadrature-point updates/s over all GPUs, plus timesteps/s, the e2e variant
-(host buffers: H2D of the step's temperature input, D2H of the five fields the reference writes every step,
-TVP:357-362), a roofline object for the dominant kernel (the DG Jacobian-apply cell kernel, timed live with
-CUDA events on its launch stream), the same for the fused viscoelastic kernel, and a CPU baseline.
+Printed JSON (rank 0, the only line on stdout): metric = quadrature-point updates/s over all GPUs, plus
+timesteps/s; e2e = the same through ThermoViscoProblem with host buffers (H2D of the step's temperature input, D2H
+of the five fields the reference writes every step, TVP:357-362, overlapped with the next step by
+output.HostMirror); "roofline" = the kernel with the largest share of the step (timed live with CUDA events on its
+launch stream, skipped launches excluded; algorithmic bytes from the library), with "roofline_cheb_step",
+"roofline_apply" and "roofline_visco" for the three hand-written hot kernels; and a CPU baseline.
 """
 from __future__ import annotations
 
@@ -392,6 +395,15 @@ def run_gpu(args):
             "bound": "hbm", "achieved": cheb_gbs, "peak": peak, "unit": "GB/s", "frac": cheb_gbs / peak, "traffic": None,
             "peak_source": peak_how, "algorithmic_bytes_per_launch": int(cheb_bytes), "launches_timed": int(n_cheb.value),
             "avg_launch_ms": cheb_ms, "share_of_step": ms_cheb.value / ms_total}
+    try:      # measured DRAM bytes per launch from the committed ncu captures (null when this workload was not captured)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            traffic = json.load(fh).get(args.workload, {}) 
+    except Exception:
+        traffic = {}
+    for key, kern in (("roofline_cheb_step", "dg_cheb_step"), ("roofline_apply", "dg_class_apply"), ("roofline_visco", "visco_fast_kernel")):
+        if line.get(key):
+            line[key]["traffic"] = traffic.get(kern) if kern in line[key]["kernel"] else None
+            line[key].setdefault("peak_source", peak_how)
     cands = [line[k] for k in ("roofline_cheb_step", "roofline_apply", "roofline_visco") if line.get(k)]
     line["roofline"] = max(cands, key=lambda r: r["share_of_step"])
     if world == 1 and not args.no_cpu_baseline:
