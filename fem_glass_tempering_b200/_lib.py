@@ -51,7 +51,8 @@ class ViscoGatherC(C.Structure):
 
 def build(verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    res = subprocess.run(["make", "-C", os.path.join(_PKG, "csrc")], capture_output=True, text=True)
+    res = subprocess.run(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", os.path.join(_PKG, "csrc")],
+                         capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("building libsurroglas_b200.so failed:\n" + res.stdout + res.stderr)
     if verbose:

@@ -95,12 +95,14 @@ __device__ __forceinline__ void pcg_check(PcgCtrl *ctrl, const double *Snext, do
 
 // beta = rz_new/rz ; p = dinv r + beta p ; flags convergence for the launches that follow
 __global__ void __launch_bounds__(VB) k_update_p(long n, const double *__restrict__ r, const double *__restrict__ dinv,
-                                                 double *__restrict__ p, const double *Scur, const double *Snext,
-                                                 PcgCtrl *ctrl, double tol2, int it) {
+                                                 double *__restrict__ p, double *__restrict__ Ap, const double *Scur,
+                                                 const double *Snext, PcgCtrl *ctrl, double tol2, int it) {
     if (ctrl->done) return;
     const double beta = Snext[0] / Scur[0];
-    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB)
+    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
         p[i] = dinv[i] * r[i] + beta * p[i];
+        Ap[i] = 0.0;     // the next operator apply scatters into Ap (RED.ADD): zero it here instead of a memset launch
+    }
     // every block has read `done` before block 0 can change it?  No ordering is needed: a block that
     // sees done != 0 set by THIS kernel merely skips a p update nobody will use.
     if (blockIdx.x == 0 && threadIdx.x == 0) pcg_check(ctrl, Snext, tol2, it);
@@ -896,7 +898,8 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
         for (int k = 0; k < nb; ++k, ++it) {
             double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
             if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
-            if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, &s->ctrl->done, st))) return rc;
+            // CG spaces: k_update_p of the previous iteration left Ap == 0 for the scatter
+            if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, &s->ctrl->done, st, !s->blk_nld && it > 0))) return rc;
             if ((rc = allreduce(s, S + 4, 2, st))) return rc;
             if (s->blk_nld) {
                 SG_BLK_DISPATCH(blk_update_xr, s, x, Scur, Snext, st);
@@ -911,7 +914,7 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
                 SG_BLK_DISPATCH(blk_update_p, s, Scur, Snext, tol2, it, st);
                 if (rc) return rc;
             } else {
-                k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, Scur, Snext, s->ctrl, tol2, it);
+                k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, s->Ap, Scur, Snext, s->ctrl, tol2, it);
                 SG_CHECK_CUDA(cudaGetLastError());
                 sg_count_launch();
             }

@@ -44,8 +44,9 @@ struct SgRed {
 // (cells + exterior facets).  When *skip != 0 (device flag, may be NULL) every kernel returns at once.
 // Must precede sg_thermal_apply_dot whenever T_lin changed (refreshes the linearised boundary matrices).
 int sg_thermal_linearize(sg_thermal_op *op, const double *T_lin, cudaStream_t st);
+// y_is_zero: the caller guarantees y == 0 on entry (CG spaces scatter into y; saves the memset launch).
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
-                         const int *skip, cudaStream_t st);
+                         const int *skip, cudaStream_t st, int y_is_zero = 0);
 
 // One fused Chebyshev step of the polynomial preconditioner (DG + class tables only, see dg_cheb_step):
 // z_out = z_in + a (z_in - z_prev) + b M^-1 (r - J z_in); z_prev == NULL means 0 (first step); z_out may alias

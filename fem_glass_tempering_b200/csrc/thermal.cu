@@ -649,6 +649,9 @@ struct ClsDev {
     const double *bmat;
     // two cells per thread (dg_cell_apply2): c and c + pair_stride are processed together; 0 = off
     long pair_stride, pair_groups;
+    // CG: exterior facets applied by the same kernel after the cells (bmat != NULL)
+    long n_bf;
+    const int32_t *bf_cell, *bf_facet;
 };
 
 constexpr int CB = 256;  // threads per block of the class kernels
@@ -1040,11 +1043,14 @@ __global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_cheb_step(const ClsDev cd
     if (LAST) sg_grid_reduce<1>(dsum, red, dot_out);
 }
 
-// CG fast apply: gather through the dofmap, class matrix from shared memory, scatter with RED.ADD.F64.
-// x.y is reduced cell-wise as x_K . (A_K x_K) over the cells [dot_lo, dot_hi) (each global cell on one rank).
-template <int NLD>
+// CG fast apply: gather through the dofmap, class matrix from shared memory, scatter with RED.ADD.F64; then, in the
+// same launch, the exterior facets from their linearised matrices (both parts only add into y, no ordering needed).
+// x.y is reduced cell-wise as x_K . (A_K x_K) over the cells [dot_lo, dot_hi) (each global cell on one rank) plus
+// x_F . (B_F x_F) over their exterior facets.
+template <int D, int P>
 __global__ void __launch_bounds__(CB) cg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
                                                      SgRed red, double *dot_out, const int *skip) {
+    constexpr int NLD = nld_of(D, P);
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
     const int ntab = cd.n_self * cd.S;
@@ -1071,6 +1077,43 @@ __global__ void __launch_bounds__(CB) cg_class_apply(const ClsDev cd, const doub
         }
         if (c >= cd.dot_lo && c < cd.dot_hi) dsum[0] += d;
     }
+    if (cd.bmat) {
+        constexpr int NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
+        for (long b = (long)blockIdx.x * CB + threadIdx.x; b < cd.n_bf; b += (long)gridDim.x * CB) {
+            const long c = cd.bf_cell[b];
+            if (c < cd.cell_lo || c >= cd.cell_hi) continue;
+            const int f = cd.bf_facet[b];
+            long dof[NFD];
+            double xk[NFD], yk[NFD], B[NFDP];
+#pragma unroll
+            for (int k = 0; k < NFD; ++k) {
+                int fd = 0;
+#pragma unroll
+                for (int ff = 0; ff < D + 1; ++ff)
+                    if (ff == f) fd = facet_dof(D, P, ff, k);
+                dof[k] = cd.dofmap[(long)fd * nc + c];
+                xk[k] = x[dof[k]];
+                yk[k] = 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < NFDP; ++k) B[k] = cd.bmat[b * NFDP + k];
+            int m = 0;
+#pragma unroll
+            for (int k = 0; k < NFD; ++k)
+#pragma unroll
+                for (int l = k; l < NFD; ++l) {
+                    yk[k] += B[m] * xk[l];
+                    if (l != k) yk[l] += B[m] * xk[k];
+                    ++m;
+                }
+            const bool counted = c >= cd.dot_lo && c < cd.dot_hi;
+#pragma unroll
+            for (int k = 0; k < NFD; ++k) {
+                atomicAdd(&y[dof[k]], yk[k]);
+                if (counted) dsum[1] += xk[k] * yk[k];
+            }
+        }
+    }
     sg_grid_reduce<2>(dsum, red, dot_out);
 }
 
@@ -1093,6 +1136,7 @@ struct sg_thermal_op {
     size_t cls_smem;
     int32_t n_geom_classes;
     SgRed own_red;         // reduction scratch of sg_thermal_jac_apply (solver-less use of the fast path)
+    int y_is_zero;         // set by sg_thermal_apply_dot: the caller guarantees y == 0 on entry (CG scatter needs no memset)
     int32_t *nbr_ext;      // DG P1: neighbour ids with exterior facets encoded (see ClsDev::bmat)
     double *bmat;
     int (*linearize)(const sg_thermal_op *, const double *T_lin, cudaStream_t st);
@@ -1144,7 +1188,7 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
     const long ncell = dv.cell_hi - dv.cell_lo;
     const unsigned gc = (unsigned)((ncell + TB - 1) / TB), gb = capped_grid(dv.n_bf, TB);
     const bool fast = mode == MODE_APPLY && op->cls.tab != nullptr;
-    if (!DG) SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
+    if (!DG && !(mode == MODE_APPLY && op->y_is_zero)) SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
     if (fast) {
         // the class kernels always reduce x.y; without a consumer it lands in a scratch slot
         double *dst = dot2 ? dot2 : red.partials + 2 * SG_MAX_BLOCKS;
@@ -1159,7 +1203,7 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
                 k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
             }
         } else
-            cg_class_apply<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+            cg_class_apply<D, P><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
     } else if (mode == MODE_RESID && op->cls.tab != nullptr && !(op->d.flags & SG_THERMAL_GENERAL_RESIDUAL)) {
@@ -1192,12 +1236,7 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
     if (fast && op->bmat && DG) {
         // exterior facets were applied inside the class kernel
     } else if (fast && op->bmat) {
-        if constexpr (!DG) {
-            double *dst = dot2 ? dot2 + 1 : red.partials + 2 * SG_MAX_BLOCKS;
-            cg_bfacet_apply<D, P><<<gb, TB, 0, st>>>(dv, op->bmat, x, y, red, dst, skip);
-            SG_CHECK_CUDA(cudaGetLastError());
-            sg_count_launch();
-        }
+        // CG: cg_class_apply applied the exterior facets in the same launch
     } else if (dv.n_bf > 0 || bdot) {
         if (mode == MODE_APPLY && bdot) bfacet_kernel<D, P, DG, MODE_APPLY, true><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, dot2 + 1, skip);
         if (mode == MODE_APPLY && !bdot) bfacet_kernel<D, P, DG, MODE_APPLY, false><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, nullptr, skip);
@@ -1349,8 +1388,8 @@ int build_classes_t(sg_thermal_op *op) {
         SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, NB, P, true, true>, CB, smem));
     } else {
-        SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_apply<NLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_class_apply<NLD>, CB, smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_apply<D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_class_apply<D, P>, CB, smem));
     }
     if (per_sm < 1) {
         cudaFree(op->cls_tab);
@@ -1379,6 +1418,9 @@ int build_classes_t(sg_thermal_op *op) {
     cd.n_nb = NF;
     cd.S = S;
     cd.bmat = nullptr;
+    cd.n_bf = dv.n_bf;
+    cd.bf_cell = dv.bf_cell;
+    cd.bf_facet = dv.bf_facet;
     cd.pair_stride = cd.pair_groups = 0;
     op->cls_grid_pair = 0;
     if (DG && NLD % 4 == 0 && (op->d.flags & SG_THERMAL_PAIRS)) {
@@ -1505,8 +1547,11 @@ int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, dou
 }
 
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
-                         const int *skip, cudaStream_t st) {
-    return op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, red, dot2, skip, st);
+                         const int *skip, cudaStream_t st, int y_is_zero) {
+    op->y_is_zero = y_is_zero;
+    const int rc = op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, red, dot2, skip, st);
+    op->y_is_zero = 0;
+    return rc;
 }
 
 // Gauss-Jordan inverse of the (SPD, n <= 10) reference mass matrix
