@@ -258,7 +258,12 @@ def run_gpu(args):
         one_step()
     barrier()
     import ctypes as C
-    _lib.check(L.sg_thermal_profile(op.handle, 1, 8192))
+    # Kernel timing with CUDA-event pairs runs inside the timed region, except when the solver replays its PCG batches as
+    # CUDA graphs (plain PCG on one GPU: small meshes, CG spaces) — event pairs cannot sit between graph nodes, so those
+    # workloads get a separate profiled pass of the same number of steps after the timed region.
+    prof_in_timed_region = bool(op.chebyshev_info()["degree"]) or world > 1
+    if prof_in_timed_region:
+        _lib.check(L.sg_thermal_profile(op.handle, 1, 8192))
     launches0 = L.sg_launch_count()
     lin_its = newton_its = 0
     visco_ev = []
@@ -281,6 +286,11 @@ def run_gpu(args):
         barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = L.sg_launch_count() - launches0
+    if not prof_in_timed_region:
+        _lib.check(L.sg_thermal_profile(op.handle, 1, 8192))
+        for _ in range(args.steps):
+            one_step()
+        barrier()
     n_apply, ms_apply = C.c_int64(0), C.c_double(0.0)
     n_cheb, ms_cheb = C.c_int64(0), C.c_double(0.0)
     _lib.check(L.sg_thermal_profile_read_kind(op.handle, 0, C.byref(n_apply), C.byref(ms_apply)))
@@ -359,6 +369,8 @@ def run_gpu(args):
                    "cache": "state per GPU (>17 GB) is far larger than the 126 MB L2; no L2 flush needed",
                    "newton_its_per_step": newton_its / args.steps, "pcg_its_per_step": lin_its / args.steps,
                    "setup_s": round(t_setup, 1), "local_matrix_classes": cls,
+                   "kernel_timing": ("CUDA events inside the timed region" if prof_in_timed_region else
+                                     "separate profiled pass after the timed region (the timed region replays CUDA graphs)"),
                    "preconditioner": (f"Chebyshev degree {op.chebyshev_info()['degree']} in M^-1 J on "
                                       f"[{op.chebyshev_info()['lo']:.3g}, {op.chebyshev_info()['hi']:.3g}] (pcg its = outer iterations)"
                                       if op.chebyshev_info()["degree"] else

@@ -10,6 +10,7 @@
 // GPUs the 1–2 doubles are combined with an in-place ncclAllReduce on the same stream; the ghost dofs
 // of the search direction are refreshed with grouped ncclSend/ncclRecv of contiguous ranges.
 #include <math.h>
+#include <stdlib.h>
 
 #include "sg_common.cuh"
 #include "sg_nccl.h"
@@ -27,6 +28,8 @@ struct PcgCtrl {
     int done;      // 0 running, 1 converged, 2 non-finite residual
     int iters;     // iterations completed when `done` was set
     double rr;     // |r|^2 at that point
+    double tol2;   // |r|^2 target of the running solve (k_pcg_begin); lives on the device so that a captured
+    int it_count;  // CUDA graph of a batch of iterations is valid for every solve; iterations executed so far
 };
 
 using Red = SgRed;
@@ -83,6 +86,23 @@ __global__ void __launch_bounds__(VB) k_update_xr(long n, long lo, long hi, cons
     grid_reduce<2>(acc, red, Snext);
 }
 
+// Convergence test by one thread with the target and the iteration count kept in the control block.
+__device__ __forceinline__ void pcg_check_counted(PcgCtrl *ctrl, const double *Snext) {
+    const int it = ctrl->it_count;
+    const double rr = Snext[1];
+    if (!(rr > ctrl->tol2) || !isfinite(rr)) {
+        ctrl->done = isfinite(rr) ? 1 : 2;
+        ctrl->iters = it + 1;
+        ctrl->rr = rr;
+    }
+    ctrl->it_count = it + 1;
+}
+
+__global__ void k_pcg_begin(PcgCtrl *ctrl, double tol2) {
+    ctrl->tol2 = tol2;
+    ctrl->it_count = 0;
+}
+
 // Convergence test of iteration `it` (0-based), by one thread, on the (all-reduced) new residual norm.
 __device__ __forceinline__ void pcg_check(PcgCtrl *ctrl, const double *Snext, double tol2, int it) {
     const double rr = Snext[1];
@@ -96,7 +116,7 @@ __device__ __forceinline__ void pcg_check(PcgCtrl *ctrl, const double *Snext, do
 // beta = rz_new/rz ; p = dinv r + beta p ; flags convergence for the launches that follow
 __global__ void __launch_bounds__(VB) k_update_p(long n, const double *__restrict__ r, const double *__restrict__ dinv,
                                                  double *__restrict__ p, double *__restrict__ Ap, const double *Scur,
-                                                 const double *Snext, PcgCtrl *ctrl, double tol2, int it) {
+                                                 const double *Snext, PcgCtrl *ctrl) {
     if (ctrl->done) return;
     const double beta = Snext[0] / Scur[0];
     for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
@@ -105,7 +125,7 @@ __global__ void __launch_bounds__(VB) k_update_p(long n, const double *__restric
     }
     // every block has read `done` before block 0 can change it?  No ordering is needed: a block that
     // sees done != 0 set by THIS kernel merely skips a p update nobody will use.
-    if (blockIdx.x == 0 && threadIdx.x == 0) pcg_check(ctrl, Snext, tol2, it);
+    if (blockIdx.x == 0 && threadIdx.x == 0) pcg_check_counted(ctrl, Snext);
 }
 
 __global__ void __launch_bounds__(VB) k_invert(long n, double *__restrict__ d) {
@@ -240,7 +260,7 @@ template <int NLD>
 __global__ void __launch_bounds__(VB) k_update_p_blk(const __grid_constant__ MassInv<NLD> mi, long n_cells,
                                                      const double *__restrict__ detJ, const double *__restrict__ r,
                                                      double *__restrict__ p, const double *Scur, const double *Snext,
-                                                     PcgCtrl *ctrl, double tol2, int it) {
+                                                     PcgCtrl *ctrl) {
     if (ctrl->done) return;
     const double beta = Snext[0] / Scur[0];
     for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
@@ -252,7 +272,7 @@ __global__ void __launch_bounds__(VB) k_update_p_blk(const __grid_constant__ Mas
         for (int i = 0; i < NLD; ++i) pk[i] = zk[i] + beta * pk[i];
         st_row<NLD>(p + c * NLD, pk);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) pcg_check(ctrl, Snext, tol2, it);
+    if (blockIdx.x == 0 && threadIdx.x == 0) pcg_check_counted(ctrl, Snext);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -444,6 +464,13 @@ struct sg_thermal_solver {
     double cheb_lo, cheb_hi;    // spectrum bounds of M^-1 J in use (hi <= 0: estimate at first use)
     double *zA, *zB;            // workspace views
     int cheb_failed;
+    // The solver runs on its own non-blocking stream (ordered against the caller's stream with events): batches of
+    // plain PCG iterations are replayed as a CUDA graph, which cannot be captured on the legacy default stream.
+    cudaStream_t own;
+    cudaEvent_t ev_in, ev_out;
+    cudaGraphExec_t batch_graph;
+    const double *graph_T, *graph_x;
+    int use_graphs;
 };
 
 namespace {
@@ -489,9 +516,9 @@ int blk_update_xr(sg_thermal_solver *s, double *x, const double *Scur, double *S
     return SG_OK;
 }
 template <int NLD>
-int blk_update_p(sg_thermal_solver *s, const double *Scur, const double *Snext, double tol2, int it, cudaStream_t st) {
+int blk_update_p(sg_thermal_solver *s, const double *Scur, const double *Snext, cudaStream_t st) {
     k_update_p_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->detJ, s->r, s->p, Scur, Snext,
-                                                         s->ctrl, tol2, it);
+                                                         s->ctrl);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;
@@ -563,6 +590,21 @@ int estimate_spectrum(sg_thermal_solver *s, const double *T_lin, cudaStream_t st
     s->cheb_lo = fmin(0.9, s->cheb_hi / 4.0);
     return SG_OK;
 }
+
+// Runs a solver entry point on the solver's own stream, ordered after everything the caller has enqueued on ITS
+// stream so far, and makes the caller's stream wait for the solver's work on exit (also on error paths).
+struct StreamScope {
+    sg_thermal_solver *s;
+    cudaStream_t caller;
+    StreamScope(sg_thermal_solver *sv, cudaStream_t c) : s(sv), caller(c) {
+        cudaEventRecord(s->ev_in, caller);
+        cudaStreamWaitEvent(s->own, s->ev_in, 0);
+    }
+    ~StreamScope() {
+        cudaEventRecord(s->ev_out, s->own);
+        cudaStreamWaitEvent(caller, s->ev_out, 0);
+    }
+};
 
 constexpr int CHEB_MAX = 8;
 constexpr int CHEB_BATCH = 4;
@@ -798,12 +840,23 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     s->S = nullptr;
     s->S_host = nullptr;
     s->ctrl = s->ctrl_host = nullptr;
+    s->own = nullptr;
+    s->ev_in = s->ev_out = nullptr;
+    s->batch_graph = nullptr;
+    s->graph_T = s->graph_x = nullptr;
+    {
+        const char *ng = getenv("SG_NO_GRAPHS");
+        s->use_graphs = !(ng && ng[0] == '1');
+    }
     cudaError_t e = cudaMalloc(&s->red.partials, sizeof(double) * (SG_MAX_BLOCKS * 2 + 2));
     if (e == cudaSuccess) e = cudaMalloc(&s->red.counter, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(s->red.counter, 0, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&s->S, sizeof(double) * 8);
     if (e == cudaSuccess) e = cudaMemset(s->S, 0, sizeof(double) * 8);
     if (e == cudaSuccess) e = cudaHostAlloc(&s->S_host, sizeof(double) * 8, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&s->ctrl, sizeof(PcgCtrl));
     if (e == cudaSuccess) e = cudaMemset(s->ctrl, 0, sizeof(PcgCtrl));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->ctrl_host, sizeof(PcgCtrl), cudaHostAllocMapped);
@@ -822,6 +875,13 @@ int sg_thermal_solver_destroy(sg_thermal_solver *s) {
     if (s->red.counter) cudaFree(s->red.counter);
     if (s->S) cudaFree(s->S);
     if (s->S_host) cudaFreeHost(s->S_host);
+    if (s->batch_graph) cudaGraphExecDestroy(s->batch_graph);
+    if (s->own) {
+        cudaStreamSynchronize(s->own);
+        cudaStreamDestroy(s->own);
+    }
+    if (s->ev_in) cudaEventDestroy(s->ev_in);
+    if (s->ev_out) cudaEventDestroy(s->ev_out);
     if (s->ctrl) cudaFree(s->ctrl);
     if (s->ctrl_host) cudaFreeHost(s->ctrl_host);
     delete s;
@@ -834,7 +894,8 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
 int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, double *x, double rtol, double atol,
                  int32_t max_it, int32_t *iters, double *rel_res, void *stream) {
     SG_REQUIRE(s && T_lin && b && x, "sg_pcg_solve: NULL argument");
-    return pcg_run(s, T_lin, b, x, PcgTol{rtol, atol, false, 0.0, 0.0, 0.0, 0.0}, max_it, iters, rel_res, (cudaStream_t)stream);
+    StreamScope scope(s, (cudaStream_t)stream);
+    return pcg_run(s, T_lin, b, x, PcgTol{rtol, atol, false, 0.0, 0.0, 0.0, 0.0}, max_it, iters, rel_res, s->own);
 }
 
 int sg_thermal_solver_set_chebyshev(sg_thermal_solver *s, int32_t degree, double lo, double hi) {
@@ -890,34 +951,81 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
     }
     int it = 0, done = rr0 > tol2 ? 0 : 1;
     double rr = rr0;
-    if (!done && (rc = sg_thermal_linearize(s->op, T_lin, st))) return rc;
-    // Iterations are enqueued BATCH at a time without host synchronisation: the kernels test convergence
-    // themselves (pcg_check) and the launches after the converged iteration return immediately.
+    if (!done) {
+        if ((rc = sg_thermal_linearize(s->op, T_lin, st))) return rc;
+        k_pcg_begin<<<1, 1, 0, st>>>(s->ctrl, tol2);
+        SG_CHECK_CUDA(cudaGetLastError());
+        // CG spaces scatter into Ap: zero it once, afterwards every p update leaves it zeroed
+        if (!s->blk_nld) SG_CHECK_CUDA(cudaMemsetAsync(s->Ap, 0, sizeof(double) * (size_t)n, st));
+    }
+    // One PCG iteration = 3 launches.  Iterations are enqueued BATCH at a time without host synchronisation: the
+    // kernels test convergence themselves and the launches after the converged iteration return immediately.
+    auto enqueue_iteration = [&](int parity) -> int {
+        double *Scur = S + 2 * parity, *Snext = S + 2 * (1 - parity);
+        int r2;
+        if (s->halo && (r2 = sg_halo_forward(s->halo, s->p, 1, st))) return r2;
+        if ((r2 = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, &s->ctrl->done, st, !s->blk_nld))) return r2;
+        if ((r2 = allreduce(s, S + 4, 2, st))) return r2;
+        if (s->blk_nld) {
+            int rc;
+            SG_BLK_DISPATCH(blk_update_xr, s, x, Scur, Snext, st);
+            if (rc) return rc;
+        } else {
+            k_update_xr<<<g, VB, 0, st>>>(n, lo, hi, s->p, s->Ap, s->dinv, x, s->r, s->red, Scur, S + 4, Snext, s->ctrl);
+            SG_CHECK_CUDA(cudaGetLastError());
+            sg_count_launch();
+        }
+        if ((r2 = allreduce(s, Snext, 2, st))) return r2;
+        if (s->blk_nld) {
+            int rc;
+            SG_BLK_DISPATCH(blk_update_p, s, Scur, Snext, st);
+            if (rc) return rc;
+        } else {
+            k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, s->Ap, Scur, Snext, s->ctrl);
+            SG_CHECK_CUDA(cudaGetLastError());
+            sg_count_launch();
+        }
+        return SG_OK;
+    };
+    // Single GPU: a full batch is captured once into a CUDA graph (every argument that changes between solves lives
+    // in device memory) and replayed — the kernels of small meshes take a few microseconds, less than their launches.
+    const bool graphs = s->use_graphs && s->ctx->nranks == 1 && !sg_thermal_profiling(s->op) && (BATCH % 2 == 0);
     while (!done && it < max_it) {
         const int nb = (max_it - it < BATCH) ? max_it - it : BATCH;
-        for (int k = 0; k < nb; ++k, ++it) {
-            double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
-            if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
-            // CG spaces: k_update_p of the previous iteration left Ap == 0 for the scatter
-            if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, &s->ctrl->done, st, !s->blk_nld && it > 0))) return rc;
-            if ((rc = allreduce(s, S + 4, 2, st))) return rc;
-            if (s->blk_nld) {
-                SG_BLK_DISPATCH(blk_update_xr, s, x, Scur, Snext, st);
-                if (rc) return rc;
-            } else {
-                k_update_xr<<<g, VB, 0, st>>>(n, lo, hi, s->p, s->Ap, s->dinv, x, s->r, s->red, Scur, S + 4, Snext, s->ctrl);
-                SG_CHECK_CUDA(cudaGetLastError());
-                sg_count_launch();
+        if (graphs && nb == BATCH) {
+            if (!s->batch_graph || s->graph_T != T_lin || s->graph_x != x) {
+                if (s->batch_graph) cudaGraphExecDestroy(s->batch_graph);
+                s->batch_graph = nullptr;
+                cudaGraph_t graph = nullptr;
+                SG_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                int rcap = SG_OK;
+                for (int k = 0; k < BATCH && rcap == SG_OK; ++k) rcap = enqueue_iteration(k & 1);
+                const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+                sg_count_launch(-3 * BATCH);   // the captured launches did not execute
+                if (rcap != SG_OK || ec != cudaSuccess || !graph) {
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                    s->use_graphs = 0;      // capture not possible here: plain launches from now on
+                    if (rcap != SG_OK) return rcap;
+                    continue;
+                }
+                const cudaError_t ei = cudaGraphInstantiate(&s->batch_graph, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ei != cudaSuccess) {
+                    cudaGetLastError();
+                    s->batch_graph = nullptr;
+                    s->use_graphs = 0;
+                    continue;
+                }
+                s->graph_T = T_lin;
+                s->graph_x = x;
             }
-            if ((rc = allreduce(s, Snext, 2, st))) return rc;
-            if (s->blk_nld) {
-                SG_BLK_DISPATCH(blk_update_p, s, Scur, Snext, tol2, it, st);
-                if (rc) return rc;
-            } else {
-                k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, s->Ap, Scur, Snext, s->ctrl, tol2, it);
-                SG_CHECK_CUDA(cudaGetLastError());
-                sg_count_launch();
-            }
+            SG_CHECK_CUDA(cudaGraphLaunch(s->batch_graph, st));
+            sg_count_launch(3 * BATCH);
+            it += BATCH;
+        } else {
+            for (int k = 0; k < nb; ++k, ++it)
+                if ((rc = enqueue_iteration(it & 1))) return rc;
         }
         if ((rc = read_scalars(s, 0, 8, st))) return rc;
         done = s->ctrl_host->done;
@@ -941,7 +1049,8 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
 int sg_thermal_timestep(sg_thermal_solver *s, double *T, const double *T_prev, const sg_newton_opts *o,
                         sg_newton_stats *stats, void *stream) {
     SG_REQUIRE(s && T && T_prev && o, "sg_thermal_timestep: NULL argument");
-    cudaStream_t st = (cudaStream_t)stream;
+    StreamScope scope(s, (cudaStream_t)stream);
+    cudaStream_t st = s->own;
     const long n = s->n;
     const unsigned g = vgrid(n);
     int rc, lin_total = 0;

@@ -58,6 +58,7 @@ struct SgChebStep {
     int last;
 };
 bool sg_thermal_has_cheb(const sg_thermal_op *op);
+bool sg_thermal_profiling(const sg_thermal_op *op);   // event pairs around the kernels are being recorded
 int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
 
 // peer.cu: NVLink peer-memory halo exchange and small all-reduce (replaces NCCL on the solver's data path)

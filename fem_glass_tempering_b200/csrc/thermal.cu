@@ -1537,6 +1537,8 @@ void sg_op_info(const sg_thermal_op *op, SgOpInfo *o) {
 
 int sg_thermal_linearize(sg_thermal_op *op, const double *T_lin, cudaStream_t st) { return op->linearize(op, T_lin, st); }
 
+bool sg_thermal_profiling(const sg_thermal_op *op) { return op->prof_on != 0; }
+
 bool sg_thermal_has_cheb(const sg_thermal_op *op) {
     // the exterior facets must be inside the class kernel (bmat) or absent, so that J z is complete per cell
     return op->d.family == 1 && op->cls.tab != nullptr && (op->bmat != nullptr || op->d.n_bfacets == 0);

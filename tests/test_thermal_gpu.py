@@ -198,6 +198,32 @@ def test_two_cells_per_thread_kernels_match_single(sg_ctx, dims):
         assert np.max(np.abs(out[True][0] - yo)) <= 1e-12 * np.max(np.abs(yo))
 
 
+@pytest.mark.parametrize("dim,family,degree", [(2, "CG", 2), (3, "CG", 2), (3, "DG", 1), (1, "DG", 1)])
+def test_cuda_graph_batches_match_plain_launches(sg_ctx, dim, family, degree, monkeypatch):
+    """The plain PCG replays batches of 8 iterations as a CUDA graph on the solver's own stream; SG_NO_GRAPHS=1 launches
+    the same kernels one by one.  Same iteration count, same solution; repeated solves reuse the graph."""
+    res = {}
+    for no_graphs in ("0", "1"):
+        monkeypatch.setenv("SG_NO_GRAPHS", no_graphs)
+        m, space, op, orc = setup(sg_ctx, dim, family, degree, cheb_degree=0)
+        n = space.n_nodes
+        rng = np.random.default_rng(21)
+        T = np.full(n, 790.0) - rng.random(n)
+        Td = dev(T)
+        op.prepare_preconditioner(Td)
+        sols = []
+        for rep in range(3):
+            b = rng.standard_normal(n)
+            xd = torch.zeros(n, dtype=torch.float64, device="cuda:0")
+            its, rr = op.pcg(Td, dev(b), xd, rtol=1e-12)
+            sols.append((its, xd.cpu().numpy()))
+        res[no_graphs] = sols
+    for (i0, x0), (i1, x1) in zip(res["0"], res["1"]):
+        assert i0 == i1
+        assert np.max(np.abs(x0 - x1)) <= 1e-12 * np.max(np.abs(x1))
+    assert res["0"][0][0] > 8          # more than one batch: the graph path was exercised
+
+
 def test_many_shapes_fall_back_to_per_cell_geometry(sg_ctx):
     """A mesh whose cells all differ (randomly perturbed vertices) has too many classes for the shared-memory tables:
     the library must keep the general kernel and still match the oracle."""
