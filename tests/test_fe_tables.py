@@ -201,3 +201,28 @@ def test_stability_of_the_dg_time_stepping(dim):
         assert ref < 0.9, f"expected the reference penalty to be non-coercive on tetrahedra, lambda_min = {ref}"
         assert lam_min(dict(MAIN_PARAMS, sip_penalty=6.0)) >= 1.0 - 1e-9
 
+
+
+@pytest.mark.parametrize("dims", [(3, 5, 9), (2, 8, 8), (4, 3, 2)])
+def test_class_uniform_cell_tiles(dims):
+    """mesh.py numbers the simplices of every x-column in tiles of 32 elements, Kuhn type by Kuhn type: the same set of
+    cells as the plain element-major order, x-columns stay contiguous (slab partition), and 32 consecutive cells of a
+    full tile share their shape (one warp of the operator kernels reads one class-table entry)."""
+    tiled, plain = msh.box_mesh(*dims), msh.box_mesh(*dims, tile=1)
+    assert {tuple(c) for c in tiled.cells.tolist()} == {tuple(c) for c in plain.cells.tolist()}
+    nx, ny, nz = dims
+    col = ny * nz * 6
+    for i in range(nx):
+        xs = tiled.x[tiled.cells[i * col:(i + 1) * col]][:, :, 0]
+        assert xs.min() >= tiled.x[:, 0].max() * i / nx - 1e-12 and xs.max() <= tiled.x[:, 0].max() * (i + 1) / nx + 1e-12
+    geo = fe.cell_geometry(tiled)
+    per_col = ny * nz
+    for i in range(nx):
+        for t0 in range(0, per_col, 32):
+            ts = min(32, per_col - t0)
+            for k in range(6):
+                a = i * col + t0 * 6 + k * ts
+                J = geo.Jinv[a:a + ts]
+                assert np.allclose(J, J[0], atol=1e-12), "cells of one tile row differ in shape"
+    r = msh.rectangle_mesh(5, 40)
+    assert r.n_cells == 400 and len({tuple(c) for c in r.cells.tolist()}) == 400
