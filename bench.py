@@ -153,13 +153,36 @@ def cpu_timestep_rate(workload_name: str, steps: int, warmup: int):
     except OSError:
         omp = False
 
+    import ctypes as C
+    pcg_lib = None
+    try:       # OpenMP Jacobi-PCG on the assembled CSR Jacobian (oracle/cpu_pcg.c); scipy's cg is single-threaded
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True)
+        pcg_lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libcpu_pcg_omp.so"))
+        pcg_lib.cpu_pcg_jacobi.restype = C.c_int
+    except OSError:
+        pcg_lib = None
+
+    def linear_solve(J, b):
+        dinv = 1.0 / J.diagonal()
+        if pcg_lib is None:
+            return spla.cg(J, b, rtol=1e-8, atol=0.0, M=sp.diags(dinv), maxiter=10000)[0]
+        J = J.tocsr()
+        J.sort_indices()
+        x = np.empty_like(b)
+        ptr = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        indptr, indices = J.indptr.astype(np.int32), J.indices.astype(np.int32)
+        its = pcg_lib.cpu_pcg_jacobi(C.c_long(b.size), ptr(indptr, C.c_int32), ptr(indices, C.c_int32), ptr(J.data, C.c_double),
+                                     ptr(dinv, C.c_double), ptr(np.ascontiguousarray(b), C.c_double), ptr(x, C.c_double),
+                                     C.c_double(1e-8), C.c_int(10000))
+        if its < 0:
+            raise RuntimeError("CPU PCG did not converge")
+        return x
+
     def newton(T0, Tp):
         T, r0 = T0.copy(), None
         for it in range(1, 51):
             b = orc.residual(T, Tp)
-            J = orc.jacobian(T)
-            dinv = 1.0 / J.diagonal()
-            dx, info = spla.cg(J, b, rtol=1e-8, atol=0.0, M=sp.diags(dinv), maxiter=10000)
+            dx = linear_solve(orc.jacobian(T), b)
             T = T - dx
             r = np.linalg.norm(dx)
             if it == 1:
@@ -184,8 +207,9 @@ def cpu_timestep_rate(workload_name: str, steps: int, warmup: int):
     qp = mesh.n_cells * space.n_ld
     cores = os.cpu_count() if omp else 1
     sample = (f"{'x'.join(map(str, n))} cells x {6 if dim == 3 else 2} simplices = {qp} points, {steps} steps; heat solve: "
-              f"assembled scipy.sparse Jacobian + Jacobi-CG Newton (1 thread); viscoelastic chain: 17-pass C port, "
-              f"OpenMP on {cores} threads; set-up {setup_s:.1f}s not timed")
+              f"assembled scipy.sparse Jacobian + Newton with Jacobi-PCG "
+              f"({'OpenMP C on ' + str(cores) + ' threads' if pcg_lib is not None else 'scipy, 1 thread'}); viscoelastic chain: "
+              f"17-pass C port, OpenMP on {cores} threads; set-up {setup_s:.1f}s not timed")
     return qp / dt_s, dt_s, cores, sample, n
 
 
