@@ -32,9 +32,11 @@ class ViscoParamsC(C.Structure):
                 ("H", C.c_double), ("Rg", C.c_double), ("Tb", C.c_double),
                 ("alpha_solid", C.c_double), ("alpha_liquid", C.c_double), ("dt", C.c_double),
                 ("m", _dbl16), ("lambda_m", _dbl16), ("g", _dbl16), ("lambda_g", _dbl16),
-                ("k", _dbl16), ("lambda_k", _dbl16)]
+                ("k", _dbl16), ("lambda_k", _dbl16),
+                ("mode", C.c_int32), ("chi", C.c_double)]
 
 
+VISCO_REFERENCE, VISCO_CORRECTED = 0, 1
 VISCO_FIELD_NAMES = ("T_cur", "T_prev", "Tf_partial", "Tf", "phi", "xi", "s_tilde", "sigma_tilde", "sigma",
                      "T_next", "phi_next", "thermal_strain", "total_strain", "deviatoric_strain",
                      "ds_partial", "dsigma_partial", "s_partial", "sigma_partial")
@@ -164,8 +166,9 @@ class ViscoPlan:
     """sg_visco_plan wrapper (constants of ViscoelasticModel.__init__, VM:9-84)."""
 
     def __init__(self, ctx: Context, *, dim: int, dt: float, H: float, Rg: float, Tb: float, alpha_solid: float,
-                 alpha_liquid: float, m, lambda_m, g, lambda_g, k, lambda_k):
+                 alpha_liquid: float, m, lambda_m, g, lambda_g, k, lambda_k, mode: int = VISCO_REFERENCE, chi: float = 0.5):
         p = ViscoParamsC()
+        p.mode, p.chi = int(mode), float(chi)
         p.dim, p.n_terms = dim, len(m)
         if not (len(m) == len(lambda_m) == len(g) == len(lambda_g) == len(k) == len(lambda_k)):
             raise ValueError("Prony tables must have equal lengths")

@@ -39,6 +39,8 @@ struct VKParams {
     double m[SG_MAX_TERMS], lm[SG_MAX_TERMS];
     double g2[SG_MAX_TERMS], lg[SG_MAX_TERMS];  // g2 = 2.0 * g_n (VM:178)
     double k[SG_MAX_TERMS], lk[SG_MAX_TERMS];
+    int mode;        // SG_VISCO_REFERENCE: the reference's expressions as executed; SG_VISCO_CORRECTED: see below
+    double chi;      // VM:15
 };
 
 struct VGather {
@@ -57,6 +59,24 @@ __device__ __forceinline__ double taylor3(double xi, double lambda) {
 // VM:156-161 / VM:162-167
 __device__ __forceinline__ double shift_phi(const VKParams &P, double T) {
     return exp(P.c_HRg * (P.inv_Tb - 1.0 / T));
+}
+
+// ---- SG_VISCO_CORRECTED: the scheme the reference's comments cite (Nielsen et al. 2010) without the quirks of the
+// executed code:
+//   phi      = exp(H/Rg (1/Tb - chi/T_cur  - (1-chi)/Tf_prev))          Eq. 25 as written at VM:100-108 (dead there)
+//   Tf_partial, Tf                                                      VM:111-125 unchanged, with this phi
+//   d eps_th = alpha_s (T_cur - T_prev) + (alpha_l - alpha_s)(Tf_cur - Tf_prev)     VM:128-133 with the OLD Tf_prev
+//   xi       = dt/2 (phi(T_prev, Tf_prev) + phi(T_cur, Tf_cur))         trapezoidal shifted-time increment (> 0)
+//   per term x = xi/lambda:  decay = exp(-x),  fac = (1 - exp(-x))/x = -expm1(-x)/x   (no cancellation, no 0/0)
+//   s_n      <- s_n decay + 2 g_n dev fac,   sigma_n <- sigma_n decay + k_n tr I fac       the history IS the partial stress
+__device__ __forceinline__ double phi_eq25(const VKParams &P, double T, double Tf) {
+    return exp(P.c_HRg * (P.inv_Tb - P.chi / T - (1.0 - P.chi) / Tf));
+}
+__device__ __forceinline__ void decay_fac(double xi, double lambda, double &decay, double &fac) {
+    const double x = xi / lambda;
+    const double em1 = expm1(-x);
+    decay = 1.0 + em1;
+    fac = (x != 0.0) ? (-em1) / x : 1.0;
 }
 
 __device__ __forceinline__ double gather_eval(const VGather &G, const double *__restrict__ arr, long node) {
@@ -138,101 +158,171 @@ visco_kernel(const VKParams P, const sg_visco_fields f, const VGather G, const l
         }
     }
 
-    // ---- stage 1a: per-node scalars (thread per node) ---------------------------------
-    if (tid < nn) {
-        const long node = tile0 + tid;
-        double Tc, Tp, xi, phi = 0.0;
-        if constexpr (GATHER) {
-            Tc = gather_eval(G, f.T_cur, node);
-            Tp = gather_eval(G, f.T_prev, node);
-            xi = gather_eval(G, f.xi, node);
-            s_tf[tid] = gather_eval(G, f.Tf, node);
-        } else {
-            Tc = f.T_cur[node];
-            Tp = f.T_prev[node];
-            phi = shift_phi(P, Tc);                     // VM:156
-            const double Tn = Tc + (Tc - Tp);           // VM:151
-            const double phin = shift_phi(P, Tn);       // VM:162
-            xi = P.half_dt * (phin - phi);              // VM:171
-            if (ph_tf || ph_shift) f.phi[node] = phi;   // TVP:456, TVP:531
-            if (ph_shift) {
-                f.xi[node] = xi;                        // TVP:541
-                if (f.T_next) f.T_next[node] = Tn;      // TVP:524
-                if (f.phi_next) f.phi_next[node] = phin;  // TVP:533
+    if (P.mode == SG_VISCO_CORRECTED) {
+        // Only the fused same-space call reaches here (sg_visco_update checks): all four phases at once.
+        if constexpr (SCALAR && TENSOR) {
+            // node scalars that do not need the new Tf
+            if (tid < nn) {
+                const long node = tile0 + tid;
+                const double Tc = f.T_cur[node], Tp = f.T_prev[node], Tfo = f.Tf[node];
+                const double phi = phi_eq25(P, Tc, Tfo);
+                f.phi[node] = phi;
+                if (f.T_next) f.T_next[node] = Tc + (Tc - Tp);
+                s_Tc[tid] = Tc;
+                s_dT[tid] = Tc - Tp;
+                s_phi[tid] = phi;
+                s_tf[tid] = Tfo;                                 // old Tf
+                s_xi[tid] = phi_eq25(P, Tp, Tfo);                // phi at t_n, completed to xi below
             }
-            if (!ph_tf) s_tf[tid] = f.Tf[node];
-        }
-        s_Tc[tid] = Tc;
-        s_dT[tid] = Tc - Tp;
-        s_xi[tid] = xi;
-        s_phi[tid] = phi;
-    }
-    __syncthreads();
-
-    // ---- stage 1b: (node, term) pairs: fictive-temperature relaxation + Taylor factors -
-    const int n_pairs = nn * N;
-    for (int it = tid; it < n_pairs; it += VTHREADS) {
-        const int t = it / N, i = it - t * N;
-        if (ph_tf) {
-            // VM:111-119  (lambda_m*Tfp_prev + T*dt*phi) / (lambda_m + dt*phi)
-            const double Tc = s_Tc[t], phi = s_phi[t];
-            const double num = P.lm[i] * f.Tf_partial[tile0 * N + it] + (Tc * P.dt) * phi;
-            const double den = P.lm[i] + P.dt * phi;
-            const double v = num / den;
-            f.Tf_partial[tile0 * N + it] = v;  // TVP:466 + copy TVP:469
-            s_tfp[it] = v;
-        }
-        if (ph_stress) {
-            const double xi = s_xi[t];
-            s_tg[it] = taylor3(xi, P.lg[i]);
-            s_tk[it] = taylor3(xi, P.lk[i]);
-        }
-    }
-    __syncthreads();
-
-    // ---- stage 1c: Tf, strains, Prony increment coefficients ---------------------------
-    for (int it = tid; it < n_pairs; it += VTHREADS) {
-        const int t = it / N, i = it - t * N;
-        const long node = tile0 + t;
-        double tf;
-        if (ph_tf) {
-            // VM:122-125  inner(m, Tf_partial), left-to-right
-            tf = P.m[0] * s_tfp[t * N];
-            for (int j = 1; j < N; ++j) tf = tf + P.m[j] * s_tfp[t * N + j];
-            if (i == 0) f.Tf[node] = tf;  // TVP:480 + copy TVP:481
-        } else {
-            tf = s_tf[t];
-        }
-        if constexpr (TENSOR) {
-            // VM:128-133; Tf_cur == Tf_prev bitwise after TVP:481, so the structural term is 0 (or NaN)
-            const double eth = P.alpha_s * s_dT[t] + P.d_alpha * (tf - tf);
-            const double tot_d = -1.0 * eth;   // VM:137
-            const double tot_o = -1.0 * 0.0;
-            double tr = tot_d;
+            __syncthreads();
+            const int n_pairs = nn * N;
+            for (int it = tid; it < n_pairs; it += VTHREADS) {
+                const int t = it / N, i = it - t * N;
+                const double Tc = s_Tc[t], phi = s_phi[t];
+                const double v = (P.lm[i] * f.Tf_partial[tile0 * N + it] + (Tc * P.dt) * phi) / (P.lm[i] + P.dt * phi);
+                f.Tf_partial[tile0 * N + it] = v;
+                s_tfp[it] = v;
+            }
+            __syncthreads();
+            if (tid < nn) {
+                const long node = tile0 + tid;
+                double tf = P.m[0] * s_tfp[tid * N];
+                for (int j = 1; j < N; ++j) tf = tf + P.m[j] * s_tfp[tid * N + j];
+                f.Tf[node] = tf;
+                const double Tfo = s_tf[tid];
+                const double phin = phi_eq25(P, s_Tc[tid], tf);
+                const double xi = P.half_dt * (s_xi[tid] + phin);
+                f.xi[node] = xi;
+                if (f.phi_next) f.phi_next[node] = phin;
+                s_xi[tid] = xi;
+                s_tf[tid] = tf - Tfo;                            // structural part of the strain increment
+            }
+            __syncthreads();
+            for (int it = tid; it < n_pairs; it += VTHREADS) {
+                const int t = it / N, i = it - t * N;
+                const long node = tile0 + t;
+                const double eth = P.alpha_s * s_dT[t] + P.d_alpha * s_tf[t];
+                const double tot_d = -1.0 * eth, tot_o = -1.0 * 0.0;
+                double tr = tot_d;
 #pragma unroll
-            for (int a = 1; a < D; ++a) tr = tr + tot_d;
-            const double dev_d = tot_d - P.inv_d * tr;  // VM:144
-            const double dev_o = tot_o;
-            if (ph_strain && i == 0) {
+                for (int a = 1; a < D; ++a) tr = tr + tot_d;
+                const double dev_d = tot_d - P.inv_d * tr, dev_o = tot_o;
+                if (i == 0) {
 #pragma unroll
-                for (int c = 0; c < DD; ++c) {
-                    const bool diag = (c % (D + 1)) == 0;
-                    if (f.thermal_strain) f.thermal_strain[node * DD + c] = diag ? eth : 0.0;  // TVP:492
-                    if (f.total_strain) f.total_strain[node * DD + c] = diag ? tot_d : tot_o;  // TVP:504
-                    if (f.deviatoric_strain) f.deviatoric_strain[node * DD + c] = diag ? dev_d : dev_o;  // TVP:516
+                    for (int c = 0; c < DD; ++c) {
+                        const bool diag = (c % (D + 1)) == 0;
+                        if (f.thermal_strain) f.thermal_strain[node * DD + c] = diag ? eth : 0.0;
+                        if (f.total_strain) f.total_strain[node * DD + c] = diag ? tot_d : tot_o;
+                        if (f.deviatoric_strain) f.deviatoric_strain[node * DD + c] = diag ? dev_d : dev_o;
+                    }
                 }
+                double dg, fg, dk, fk;
+                decay_fac(s_xi[t], P.lg[i], dg, fg);
+                decay_fac(s_xi[t], P.lk[i], dk, fk);
+                s_tg[it] = dg;
+                s_tk[it] = dk;
+                s_dsd[it] = (P.g2[i] * dev_d) * fg;
+                s_dso[it] = (P.g2[i] * dev_o) * fg;
+                s_dkd[it] = (P.k[i] * tr) * fk;
+            }
+        }
+    } else {
+    // ---- stage 1a: per-node scalars (thread per node) ---------------------------------
+        if (tid < nn) {
+            const long node = tile0 + tid;
+            double Tc, Tp, xi, phi = 0.0;
+            if constexpr (GATHER) {
+                Tc = gather_eval(G, f.T_cur, node);
+                Tp = gather_eval(G, f.T_prev, node);
+                xi = gather_eval(G, f.xi, node);
+                s_tf[tid] = gather_eval(G, f.Tf, node);
+            } else {
+                Tc = f.T_cur[node];
+                Tp = f.T_prev[node];
+                phi = shift_phi(P, Tc);                     // VM:156
+                const double Tn = Tc + (Tc - Tp);           // VM:151
+                const double phin = shift_phi(P, Tn);       // VM:162
+                xi = P.half_dt * (phin - phi);              // VM:171
+                if (ph_tf || ph_shift) f.phi[node] = phi;   // TVP:456, TVP:531
+                if (ph_shift) {
+                    f.xi[node] = xi;                        // TVP:541
+                    if (f.T_next) f.T_next[node] = Tn;      // TVP:524
+                    if (f.phi_next) f.phi_next[node] = phin;  // TVP:533
+                }
+                if (!ph_tf) s_tf[tid] = f.Tf[node];
+            }
+            s_Tc[tid] = Tc;
+            s_dT[tid] = Tc - Tp;
+            s_xi[tid] = xi;
+            s_phi[tid] = phi;
+        }
+        __syncthreads();
+    
+        // ---- stage 1b: (node, term) pairs: fictive-temperature relaxation + Taylor factors -
+        const int n_pairs = nn * N;
+        for (int it = tid; it < n_pairs; it += VTHREADS) {
+            const int t = it / N, i = it - t * N;
+            if (ph_tf) {
+                // VM:111-119  (lambda_m*Tfp_prev + T*dt*phi) / (lambda_m + dt*phi)
+                const double Tc = s_Tc[t], phi = s_phi[t];
+                const double num = P.lm[i] * f.Tf_partial[tile0 * N + it] + (Tc * P.dt) * phi;
+                const double den = P.lm[i] + P.dt * phi;
+                const double v = num / den;
+                f.Tf_partial[tile0 * N + it] = v;  // TVP:466 + copy TVP:469
+                s_tfp[it] = v;
             }
             if (ph_stress) {
                 const double xi = s_xi[t];
-                const double one_g = 1.0 - s_tg[it], one_k = 1.0 - s_tk[it];
-                // VM:176-182   2.0*g_n*dev/xi*lambda_g_n*(1.0 - taylor)
-                s_dsd[it] = ((P.g2[i] * dev_d) / xi) * P.lg[i] * one_g;
-                s_dso[it] = ((P.g2[i] * dev_o) / xi) * P.lg[i] * one_g;
-                // VM:185-191   k_n*(tr*I)/xi*lambda_k_n*(1.0 - taylor)
-                s_dkd[it] = ((P.k[i] * tr) / xi) * P.lk[i] * one_k;
+                s_tg[it] = taylor3(xi, P.lg[i]);
+                s_tk[it] = taylor3(xi, P.lk[i]);
             }
         }
-    }
+        __syncthreads();
+    
+        // ---- stage 1c: Tf, strains, Prony increment coefficients ---------------------------
+        for (int it = tid; it < n_pairs; it += VTHREADS) {
+            const int t = it / N, i = it - t * N;
+            const long node = tile0 + t;
+            double tf;
+            if (ph_tf) {
+                // VM:122-125  inner(m, Tf_partial), left-to-right
+                tf = P.m[0] * s_tfp[t * N];
+                for (int j = 1; j < N; ++j) tf = tf + P.m[j] * s_tfp[t * N + j];
+                if (i == 0) f.Tf[node] = tf;  // TVP:480 + copy TVP:481
+            } else {
+                tf = s_tf[t];
+            }
+            if constexpr (TENSOR) {
+                // VM:128-133; Tf_cur == Tf_prev bitwise after TVP:481, so the structural term is 0 (or NaN)
+                const double eth = P.alpha_s * s_dT[t] + P.d_alpha * (tf - tf);
+                const double tot_d = -1.0 * eth;   // VM:137
+                const double tot_o = -1.0 * 0.0;
+                double tr = tot_d;
+    #pragma unroll
+                for (int a = 1; a < D; ++a) tr = tr + tot_d;
+                const double dev_d = tot_d - P.inv_d * tr;  // VM:144
+                const double dev_o = tot_o;
+                if (ph_strain && i == 0) {
+    #pragma unroll
+                    for (int c = 0; c < DD; ++c) {
+                        const bool diag = (c % (D + 1)) == 0;
+                        if (f.thermal_strain) f.thermal_strain[node * DD + c] = diag ? eth : 0.0;  // TVP:492
+                        if (f.total_strain) f.total_strain[node * DD + c] = diag ? tot_d : tot_o;  // TVP:504
+                        if (f.deviatoric_strain) f.deviatoric_strain[node * DD + c] = diag ? dev_d : dev_o;  // TVP:516
+                    }
+                }
+                if (ph_stress) {
+                    const double xi = s_xi[t];
+                    const double one_g = 1.0 - s_tg[it], one_k = 1.0 - s_tk[it];
+                    // VM:176-182   2.0*g_n*dev/xi*lambda_g_n*(1.0 - taylor)
+                    s_dsd[it] = ((P.g2[i] * dev_d) / xi) * P.lg[i] * one_g;
+                    s_dso[it] = ((P.g2[i] * dev_o) / xi) * P.lg[i] * one_g;
+                    // VM:185-191   k_n*(tr*I)/xi*lambda_k_n*(1.0 - taylor)
+                    s_dkd[it] = ((P.k[i] * tr) / xi) * P.lk[i] * one_k;
+                }
+            }
+        }
+}
     if constexpr (TENSOR) {
         if (!ph_stress) return;
         if (use_bulk) sgptx::mbar_wait(bar, 0);
@@ -249,12 +339,13 @@ visco_kernel(const VKParams P, const sg_visco_fields f, const VGather G, const l
                 const int q = t * N + n;
                 const double st = buf_s[e] * s_tg[q];    // VM:194-200
                 const double sg = buf_k[e] * s_tk[q];    // VM:203-209
-                buf_s[e] = st;                           // TVP:552 + copy TVP:559
-                buf_k[e] = sg;                           // TVP:571 + copy TVP:578
                 const double ds = diag ? s_dsd[q] : s_dso[q];
                 const double dk = diag ? s_dkd[q] : 0.0;
                 const double sp = ds + st;               // VM:212-215
                 const double kp = dk + sg;               // VM:218-221
+                const bool corrected = P.mode == SG_VISCO_CORRECTED;
+                buf_s[e] = corrected ? sp : st;          // TVP:552 + copy TVP:559 (corrected: the history is the partial stress)
+                buf_k[e] = corrected ? kp : sg;          // TVP:571 + copy TVP:578
                 const double pn = sp + kp;               // VM:224-228
                 acc = (n == 0) ? pn : acc + pn;
                 if (f.ds_partial) f.ds_partial[gbase + e] = ds;          // TVP:549
@@ -314,7 +405,7 @@ struct FastCfg {
     static constexpr uint32_t SMEM = 2 * S_BYTES + TFP_BYTES + SIG_BYTES + 16;
 };
 
-template <int D, int N>
+template <int D, int N, bool CORR = false>
 __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const sg_visco_fields f, const long n_tiles) {
     using C = FastCfg<D, N>;
     constexpr int DD = C::DD, ROW = C::ROW, G = C::G;
@@ -343,12 +434,20 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
         }
         const long node = node0 + lane;
         const double Tc = f.T_cur[node], Tp = f.T_prev[node];
-        const double phi = shift_phi(P, Tc);               // VM:156
-        const double Tn = Tc + (Tc - Tp);                  // VM:151
-        const double phin = shift_phi(P, Tn);              // VM:162
-        const double xi = P.half_dt * (phin - phi);        // VM:171
+        double phi, xi, Tf_old = 0.0, phi_old = 0.0;
+        if constexpr (CORR) {
+            Tf_old = f.Tf[node];
+            phi = phi_eq25(P, Tc, Tf_old);                 // VM:100-108
+            phi_old = phi_eq25(P, Tp, Tf_old);
+            xi = 0.0;                                      // needs the new Tf, see below
+        } else {
+            phi = shift_phi(P, Tc);                        // VM:156
+            const double Tn = Tc + (Tc - Tp);              // VM:151
+            const double phin = shift_phi(P, Tn);          // VM:162
+            xi = P.half_dt * (phin - phi);                 // VM:171
+            f.xi[node] = xi;
+        }
         f.phi[node] = phi;
-        f.xi[node] = xi;
         const double Tdt_phi = (Tc * P.dt) * phi, dt_phi = P.dt * phi;
 
         sgptx::mbar_wait(bar, parity);
@@ -366,8 +465,12 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
             }
         }
         f.Tf[node] = tf;
+        if constexpr (CORR) {
+            xi = P.half_dt * (phi_old + phi_eq25(P, Tc, tf));
+            f.xi[node] = xi;
+        }
         // ---- strains (VM:128-146) ----
-        const double eth = P.alpha_s * (Tc - Tp) + P.d_alpha * (tf - tf);
+        const double eth = P.alpha_s * (Tc - Tp) + P.d_alpha * (CORR ? tf - Tf_old : tf - tf);
         const double tot_d = -1.0 * eth, tot_o = -1.0 * 0.0;
         double tr = tot_d;
 #pragma unroll
@@ -383,20 +486,34 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
 #pragma unroll
             for (int u = 0; u < G; ++u) {
                 const int n = n0 + u;
-                tg[u] = taylor3(xi, P.lg[n]);
-                tk[u] = taylor3(xi, P.lk[n]);
-                const double one_g = 1.0 - tg[u], one_k = 1.0 - tk[u];
-                dsd[u] = ((P.g2[n] * dev_d) / xi) * P.lg[n] * one_g;
-                dso[u] = ((P.g2[n] * dev_o) / xi) * P.lg[n] * one_g;
-                dkd[u] = ((P.k[n] * tr) / xi) * P.lk[n] * one_k;
+                if constexpr (CORR) {
+                    double fg, fk;
+                    decay_fac(xi, P.lg[n], tg[u], fg);
+                    decay_fac(xi, P.lk[n], tk[u], fk);
+                    dsd[u] = (P.g2[n] * dev_d) * fg;
+                    dso[u] = (P.g2[n] * dev_o) * fg;
+                    dkd[u] = (P.k[n] * tr) * fk;
+                } else {
+                    tg[u] = taylor3(xi, P.lg[n]);
+                    tk[u] = taylor3(xi, P.lk[n]);
+                    const double one_g = 1.0 - tg[u], one_k = 1.0 - tk[u];
+                    dsd[u] = ((P.g2[n] * dev_d) / xi) * P.lg[n] * one_g;
+                    dso[u] = ((P.g2[n] * dev_o) / xi) * P.lg[n] * one_g;
+                    dkd[u] = ((P.k[n] * tr) / xi) * P.lk[n] * one_k;
+                }
             }
             auto item = [&](double &s, double &k, const int e) {  // e: element within the group
                 const int u = e / DD, c = e % DD;
                 const bool diag = (c % (D + 1)) == 0;
                 s = s * tg[u];
                 k = k * tk[u];
-                const double pn = ((diag ? dsd[u] : dso[u]) + s) + ((diag ? dkd[u] : 0.0) + k);
+                const double sp = (diag ? dsd[u] : dso[u]) + s, kp = (diag ? dkd[u] : 0.0) + k;
+                const double pn = sp + kp;
                 acc[c] = (n0 + u == 0) ? pn : acc[c] + pn;
+                if constexpr (CORR) {   // the history is the partial stress itself
+                    s = sp;
+                    k = kp;
+                }
             };
             if constexpr (C::VEC) {
                 double2 *vs = reinterpret_cast<double2 *>(rs + n0 * DD);
@@ -486,7 +603,7 @@ int launch_visco(const sg_visco_plan *plan, int64_t n, const sg_visco_fields &f,
 
 template <int D, int N>
 int setup_fast(sg_visco_plan *pl) {
-    auto kern = visco_fast_kernel<D, N>;
+    auto kern = pl->k.mode == SG_VISCO_CORRECTED ? visco_fast_kernel<D, N, true> : visco_fast_kernel<D, N, false>;
     const uint32_t smem = FastCfg<D, N>::SMEM;
     if (smem > 227u * 1024u) return SG_OK;
     SG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -551,6 +668,9 @@ int sg_visco_plan_create(sg_ctx *ctx, const sg_visco_params *p, sg_visco_plan **
     k.inv_d = 1.0 / (double)p->dim;
     k.alpha_s = p->alpha_solid;
     k.d_alpha = p->alpha_liquid - p->alpha_solid;
+    SG_REQUIRE(p->mode == SG_VISCO_REFERENCE || p->mode == SG_VISCO_CORRECTED, "sg_visco_plan_create: unknown mode %d", p->mode);
+    k.mode = p->mode;
+    k.chi = p->chi;
     for (int i = 0; i < p->n_terms; ++i) {
         k.m[i] = p->m[i];
         k.lm[i] = p->lambda_m[i];
@@ -581,6 +701,8 @@ int sg_visco_plan_destroy(sg_visco_plan *plan) {
 
 int sg_visco_update(sg_visco_plan *plan, int64_t n_nodes, const sg_visco_fields *f, uint32_t phases, void *stream) {
     SG_REQUIRE(plan, "sg_visco_update: plan is NULL");
+    SG_REQUIRE(plan->k.mode == SG_VISCO_REFERENCE || phases == SG_PHASE_ALL,
+               "sg_visco_update: the corrected scheme updates Tf and reads its old value in one pass; call it with SG_PHASE_ALL");
     int rc = check_fields(f, phases, true, true, n_nodes);
     if (rc) return rc;
     VGather G{0, nullptr, nullptr, nullptr};
@@ -619,6 +741,7 @@ int sg_visco_update(sg_visco_plan *plan, int64_t n_nodes, const sg_visco_fields 
 
 int sg_visco_update_scalar(sg_visco_plan *plan, int64_t n, const sg_visco_fields *f, uint32_t phases, void *stream) {
     SG_REQUIRE(plan, "sg_visco_update_scalar: plan is NULL");
+    SG_REQUIRE(plan->k.mode == SG_VISCO_REFERENCE, "the corrected scheme needs equal T and sigma spaces (sg_visco_update)");
     int rc = check_fields(f, phases, true, false, n);
     if (rc) return rc;
     VGather G{0, nullptr, nullptr, nullptr};
@@ -628,6 +751,7 @@ int sg_visco_update_scalar(sg_visco_plan *plan, int64_t n, const sg_visco_fields
 int sg_visco_update_tensor(sg_visco_plan *plan, int64_t n, const sg_visco_fields *f, const sg_visco_gather *g,
                            uint32_t phases, void *stream) {
     SG_REQUIRE(plan, "sg_visco_update_tensor: plan is NULL");
+    SG_REQUIRE(plan->k.mode == SG_VISCO_REFERENCE, "the corrected scheme needs equal T and sigma spaces (sg_visco_update)");
     SG_REQUIRE(g && g->dofs && g->local_point && g->weights && g->n_ld > 0, "sg_visco_update_tensor: bad gather map");
     int rc = check_fields(f, phases, false, true, n);
     if (rc) return rc;
@@ -639,6 +763,7 @@ int64_t sg_visco_bytes_per_node(const sg_visco_params *p, const sg_visco_fields 
     if (!p || !f) return -1;
     const int64_t N = p->n_terms, dd = (int64_t)p->dim * p->dim;
     int64_t w = 2;  // read T_cur, T_prev
+    if (p->mode == SG_VISCO_CORRECTED) w += 1;                    // reads the old Tf
     if (phases & SG_PHASE_TF) w += 2 * N + 1;                    // Tf_partial r+w, Tf w
     if (phases & (SG_PHASE_TF | SG_PHASE_SHIFT)) w += 1;          // phi
     if (phases & SG_PHASE_SHIFT) w += 1 + (f->T_next ? 1 : 0) + (f->phi_next ? 1 : 0);

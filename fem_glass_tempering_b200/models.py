@@ -65,10 +65,18 @@ class PointwiseExpression:
 
 
 class ViscoelasticModel:
-    """ViscoelasticModel.py:9-84; optional model_parameters["prony"] = dict of six tables or an int N."""
+    """ViscoelasticModel.py:9-84; optional model_parameters["prony"] = dict of six tables or an int N, and
+    model_parameters["physics"] = "reference" (default: the reference's expressions exactly as it executes them, quirks
+    Q1-Q5 of SURVEY 3.5 included) | "corrected" (the scheme its comments cite: Eq. 25 shift function with chi and the
+    old fictive temperature, structural strain term, trapezoidal shifted time, exact exponentials, history = partial
+    stress; csrc/visco.cu).  The corrected scheme is an extension: it needs equal T and sigma spaces and runs only as
+    the fused update of solve_timestep."""
 
     def __init__(self, mesh, model_parameters: dict) -> None:
-        self.chi = 0.5                                   # VM:15 (unused at run time, SURVEY Q1)
+        self.chi = float(model_parameters.get("chi", 0.5))   # VM:15 (unused by the reference at run time, SURVEY Q1)
+        self.physics = model_parameters.get("physics", "reference")
+        if self.physics not in ("reference", "corrected"):
+            raise ValueError('model_parameters["physics"] must be "reference" or "corrected"')
         self.dim = mesh.topology.dim
         tabs = model_parameters.get("prony", 6)
         if isinstance(tabs, int):
@@ -97,7 +105,8 @@ class ViscoelasticModel:
             ctx, dim=self.dim, dt=dt, H=float(self.H), Rg=float(self.Rg), Tb=float(self.Tb),
             alpha_solid=float(self.alpha_solid), alpha_liquid=float(self.alpha_liquid),
             m=list(self.m_n_tableau), lambda_m=list(self.lambda_m_n_tableau), g=list(self.g_n_tableau),
-            lambda_g=list(self.lambda_g_n_tableau), k=list(self.k_n_tableau), lambda_k=list(self.lambda_k_n_tableau))
+            lambda_g=list(self.lambda_g_n_tableau), k=list(self.k_n_tableau), lambda_k=list(self.lambda_k_n_tableau),
+            mode=_lib.VISCO_CORRECTED if self.physics == "corrected" else _lib.VISCO_REFERENCE, chi=self.chi)
         return self.plan
 
     # -- reference-shaped expressions -------------------------------------------------------------

@@ -289,6 +289,12 @@ class ThermoViscoProblem:
         assert (converged), "Newton solver did not converge: " + _lib.lib().sg_last_error().decode()   # TVP:390
 
     def _run_phases(self, phases: int) -> None:
+        if self.material_model.physics == "corrected":
+            if not self._same_space:
+                raise NotImplementedError('physics="corrected" needs fe_config["T"] == fe_config["sigma"]')
+            if phases != _lib.PHASE_ALL:
+                raise NotImplementedError('physics="corrected" runs as one fused update (solve_timestep / _solve_viscoelastic): '
+                                          "it reads the old fictive temperature while writing the new one")
         plan, t = self.material_model.plan, self._visco_tensors()
         nT, nS = self.functionSpaces["T"].n_nodes, self.functionSpaces["sigma"].n_nodes
         if self._same_space:

@@ -66,7 +66,12 @@ typedef struct {
     double m[SG_MAX_TERMS], lambda_m[SG_MAX_TERMS];   /* VM:19-34 */
     double g[SG_MAX_TERMS], lambda_g[SG_MAX_TERMS];   /* VM:35-50 */
     double k[SG_MAX_TERMS], lambda_k[SG_MAX_TERMS];   /* VM:51-68 */
+    int32_t mode;     /* SG_VISCO_REFERENCE (0): the reference's expressions exactly as executed, quirks included;
+                         SG_VISCO_CORRECTED (1): the scheme its comments cite (csrc/visco.cu), fused call only */
+    double chi;       /* VM:15; only the corrected scheme reads it */
 } sg_visco_params;
+
+enum { SG_VISCO_REFERENCE = 0, SG_VISCO_CORRECTED = 1 };
 
 /* Phases = the four reference methods; a phase only controls which outputs are
  * WRITTEN, every input it needs is recomputed from T_cur/T_prev/Tf. */

@@ -335,3 +335,68 @@ void vo_step_fused(const vo_params *p, long n, const double *T_cur, const double
 
 int vo_sizeof_params(void) { return (int)sizeof(vo_params); }
 int vo_sizeof_state(void) { return (int)sizeof(vo_state); }
+
+/* ------------------------------------------------------------------------------------------------
+ * SPECIFICATION of the product's OPTIONAL "corrected" scheme (model_params["physics"] = "corrected").
+ * This is NOT a restatement of reference behaviour: the reference executes the quirky chain above.  It states, in
+ * plain C, the scheme the reference's comments cite (Nielsen et al. 2010) with SURVEY quirks Q1-Q4 and Q14 removed,
+ * so that the CUDA kernels of that mode have an independent CPU statement to be tested against:
+ *   phi      = exp(H/Rg (1/Tb - chi/T_cur - (1-chi)/Tf_prev))      (VM:100-108, dead in the reference)
+ *   Tf_partial, Tf as VM:111-125 with this phi
+ *   d eps_th = alpha_s (T_cur - T_prev) + (alpha_l - alpha_s)(Tf_cur - Tf_prev)   (VM:128-133 with the old Tf_prev)
+ *   xi       = dt/2 (phi(T_prev, Tf_prev) + phi(T_cur, Tf_cur))
+ *   x = xi/lambda: decay = 1 + expm1(-x), fac = -expm1(-x)/x (1 if x == 0)
+ *   s_n <- s_n decay + 2 g_n dev fac ; sigma_n <- sigma_n decay + k_n tr I fac ; sigma = sum_n (s_n + sigma_n)
+ * s_hist / k_hist hold the partial stresses themselves. */
+void vo_step_corrected(const vo_params *p, double chi, long n, const double *T_cur, const double *T_prev,
+                       double *Tf_partial, double *Tf, double *phi_out, double *xi_out,
+                       double *s_hist, double *k_hist, double *sigma)
+{
+    const int N = p->N, d = p->dim;
+    const long dd = (long)d * d;
+    const double c = p->H / p->Rg, inv_Tb = 1.0 / p->Tb, inv_d = 1.0 / (double)d;
+    const double da = p->alpha_liquid - p->alpha_solid, half_dt = p->dt / 2;
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < n; ++q) {
+        const double Tc = T_cur[q], Tp = T_prev[q], Tfo = Tf[q];
+        const double phi = exp(c * (inv_Tb - chi / Tc - (1.0 - chi) / Tfo));
+        const double phi_old = exp(c * (inv_Tb - chi / Tp - (1.0 - chi) / Tfo));
+        double tf = 0.0;
+        for (int i = 0; i < N; ++i) {
+            double v = (p->lambda_m[i] * Tf_partial[q * N + i] + (Tc * p->dt) * phi) / (p->lambda_m[i] + p->dt * phi);
+            Tf_partial[q * N + i] = v;
+            tf = (i == 0) ? p->m[0] * v : tf + p->m[i] * v;
+        }
+        Tf[q] = tf;
+        const double xi = half_dt * (phi_old + exp(c * (inv_Tb - chi / Tc - (1.0 - chi) / tf)));
+        phi_out[q] = phi;
+        xi_out[q] = xi;
+        const double eth = p->alpha_solid * (Tc - Tp) + da * (tf - Tfo);
+        const double tot_d = -1.0 * eth, tot_o = -1.0 * 0.0;
+        double tr = tot_d;
+        for (int i = 1; i < d; ++i)
+            tr = tr + tot_d;
+        const double dev_d = tot_d - inv_d * tr, dev_o = tot_o;
+        double acc[9];
+        for (int t = 0; t < N; ++t) {
+            const double xg = xi / p->lambda_g[t], xk = xi / p->lambda_k[t];
+            const double eg = expm1(-xg), ek = expm1(-xk);
+            const double dg = 1.0 + eg, dk = 1.0 + ek;
+            const double fg = (xg != 0.0) ? (-eg) / xg : 1.0, fk = (xk != 0.0) ? (-ek) / xk : 1.0;
+            const double two_g = 2.0 * p->g[t];
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) {
+                    const long e = (q * N + t) * dd + (long)i * d + j;
+                    const double ds = (two_g * (i == j ? dev_d : dev_o)) * fg;
+                    const double dks = (i == j) ? (p->k[t] * tr) * fk : 0.0;
+                    const double sp = ds + s_hist[e] * dg, kp = dks + k_hist[e] * dk;
+                    s_hist[e] = sp;
+                    k_hist[e] = kp;
+                    const double pn = sp + kp;
+                    acc[i * d + j] = (t == 0) ? pn : acc[i * d + j] + pn;
+                }
+        }
+        for (long e = 0; e < dd; ++e)
+            sigma[q * dd + e] = acc[e];
+    }
+}

@@ -264,3 +264,11 @@ def step_fused(p: ViscoParams, T_cur, T_prev, Tf_partial_, Tf_, phi_, xi_, s_til
     cp = p.c()
     _lib(omp).vo_step_fused(C.byref(cp), C.c_long(T_cur.size), _p(T_cur), _p(T_prev), _p(Tf_partial_), _p(Tf_),
                             _p(phi_), _p(xi_), _p(s_tilde), _p(sigma_tilde), _p(sigma))
+
+
+def step_corrected(p: ViscoParams, chi, T_cur, T_prev, Tf_partial_, Tf_, phi_, xi_, s_hist, k_hist, sigma, omp=False) -> None:
+    """CPU statement of the product's OPTIONAL corrected scheme (visco_oracle.c: vo_step_corrected).  Not reference
+    behaviour — the specification the CUDA kernels of model_params["physics"] = "corrected" are tested against."""
+    cp = p.c()
+    _lib(omp).vo_step_corrected(C.byref(cp), C.c_double(chi), C.c_long(T_cur.size), _p(T_cur), _p(T_prev), _p(Tf_partial_),
+                                _p(Tf_), _p(phi_), _p(xi_), _p(s_hist), _p(k_hist), _p(sigma))

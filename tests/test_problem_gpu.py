@@ -264,3 +264,30 @@ def test_chebyshev_solver_gives_the_same_histories(sg_ctx):
         assert rel_err(cpu(prob.functions_current["Tf"]), orc.f["Tf_cur"]) <= 1e-10
         orc.end_step()
     assert prob._thermal_op.chebyshev_info()["degree"] == 3
+
+
+def test_corrected_physics_through_the_problem_api(sg_ctx):
+    """model_params["physics"] = "corrected" (an extension, see ViscoelasticModel): the problem-level run equals the CPU
+    statement of that scheme fed with the GPU's own temperature history; stresses carry memory and stay finite."""
+    from oracle import visco_oracle as vo
+    cfg = {"T": {"element": "CG", "degree": 1}, "sigma": {"element": "CG", "degree": 1}}
+    params = dict(MAIN_PARAMS, physics="corrected")
+    prob = ThermoViscoProblem(mesh_path="", time=(0.0, 50.0), dt=0.1, config=cfg, model_parameters=params,
+                              mesh=msh.graded_line_mesh(), ctx=sg_ctx, verbose=False, materialize="minimal")
+    prob.setup(dirichlet_bc=False)
+    n = prob.functionSpaces["T"].n_nodes
+    p = vo.ViscoParams(dim=1, dt=0.1)
+    o = dict(Tfp=cpu(prob.functions_current["Tf_partial"]).copy(), Tf=cpu(prob.functions_current["Tf"]).copy(),
+             s=np.zeros(n * 6), k=np.zeros(n * 6), phi=np.zeros(n), xi=np.zeros(n), sig=np.zeros(n))
+    for step in range(12):
+        T_prev = cpu(prob.functions_previous["T"]).copy()
+        prob.solve_timestep(t=0.0)
+        T_cur = cpu(prob.functions_current["T"]).copy()
+        vo.step_corrected(p, 0.5, T_cur, T_prev, o["Tfp"], o["Tf"], o["phi"], o["xi"], o["s"], o["k"], o["sig"])
+        assert rel_err(cpu(prob.functions_current["Tf"]), o["Tf"]) <= 1e-12
+        assert rel_err(cpu(prob.functions["xi"]), o["xi"]) <= 1e-12
+        sig = cpu(prob.functions_next["sigma"])
+        assert np.isfinite(sig).all()
+        assert rel_err(sig, o["sig"]) <= 1e-11
+    with pytest.raises(NotImplementedError):
+        prob._solve_Tf()

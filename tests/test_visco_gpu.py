@@ -197,3 +197,62 @@ def test_errors_are_raised_not_swallowed(sg_ctx):
     with pytest.raises(_lib.SgError):
         _lib.ViscoPlan(sg_ctx, dim=4, dt=0.1, H=1, Rg=1, Tb=1, alpha_solid=0, alpha_liquid=0, m=[1], lambda_m=[1],
                        g=[1], lambda_g=[1], k=[1], lambda_k=[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Optional corrected scheme (model_params["physics"] = "corrected"): an extension, specified by oracle.vo_step_corrected
+@pytest.mark.parametrize("d,N,n", [(3, 6, 2000 + 17), (2, 6, 777), (1, 6, 4096), (3, 4, 96), (3, 6, 9)])
+def test_corrected_scheme_matches_its_cpu_statement(sg_ctx, d, N, n):
+    """Fast kernel (full tiles) + general kernel (tail): three steps so that the history (= partial stresses) matters.
+    exp/expm1 differ between libm and CUDA by an ulp or two: 1e-12 relative on every output."""
+    from fem_glass_tempering_b200 import _lib
+    p = vo.ViscoParams(dim=d, dt=0.1) if N == 6 else vo.ViscoParams(dim=d, dt=0.1, **{
+        k: getattr(vo.ViscoParams(dim=d, dt=0.1), k)[:N] for k in ("m", "lambda_m", "g", "lambda_g", "k", "lambda_k")})
+    chi = 0.5
+    plan = _lib.ViscoPlan(sg_ctx, dim=p.dim, dt=p.dt, H=p.H, Rg=p.Rg, Tb=p.Tb, alpha_solid=p.alpha_solid,
+                          alpha_liquid=p.alpha_liquid, m=p.m, lambda_m=p.lambda_m, g=p.g, lambda_g=p.lambda_g, k=p.k,
+                          lambda_k=p.lambda_k, mode=_lib.VISCO_CORRECTED, chi=chi)
+    T_cur, T_prev, Tfp, s, k = random_visco_state(n, d, N=p.N)
+    T_cur[:3] = T_prev[:3]                       # stationary nodes: the reference scheme gives 0/0 here, this one must not
+    Tf = T_prev + 1.0
+    t = gpu_state(p, T_cur, T_prev, Tfp, s, k, materialize=False)
+    t["Tf"] = torch.from_numpy(Tf.copy()).to("cuda:0")
+    o = dict(Tfp=Tfp.copy(), Tf=Tf.copy(), s=s.copy(), k=k.copy(), phi=np.zeros(n), xi=np.zeros(n), sig=np.zeros(n * d * d))
+    rng = np.random.default_rng(1)
+    for step in range(3):
+        plan.update(n, t)
+        vo.step_corrected(p, chi, T_cur, T_prev, o["Tfp"], o["Tf"], o["phi"], o["xi"], o["s"], o["k"], o["sig"])
+        g = {name: t[name].cpu().numpy() for name in ("Tf_partial", "Tf", "phi", "xi", "s_tilde", "sigma_tilde", "sigma")}
+        assert np.isfinite(g["sigma"]).all() and (g["xi"] > 0).all()
+        for name, ref in (("Tf_partial", o["Tfp"]), ("Tf", o["Tf"]), ("phi", o["phi"]), ("xi", o["xi"]),
+                          ("s_tilde", o["s"]), ("sigma_tilde", o["k"]), ("sigma", o["sig"])):
+            assert rel_err(g[name], ref) <= 1e-12, (name, step, rel_err(g[name], ref))
+        # next step: cool further
+        T_prev = T_cur.copy()
+        T_cur = T_cur - rng.uniform(0.05, 1.0, n)
+        t["T_cur"].copy_(torch.from_numpy(T_cur))
+        t["T_prev"].copy_(torch.from_numpy(T_prev))
+
+
+def test_corrected_scheme_full_materialisation_and_phase_rule(sg_ctx):
+    from fem_glass_tempering_b200 import _lib
+    d, n = 2, 130
+    p = vo.ViscoParams(dim=d, dt=0.1)
+    plan = _lib.ViscoPlan(sg_ctx, dim=p.dim, dt=p.dt, H=p.H, Rg=p.Rg, Tb=p.Tb, alpha_solid=p.alpha_solid,
+                          alpha_liquid=p.alpha_liquid, m=p.m, lambda_m=p.lambda_m, g=p.g, lambda_g=p.lambda_g, k=p.k,
+                          lambda_k=p.lambda_k, mode=_lib.VISCO_CORRECTED, chi=0.5)
+    T_cur, T_prev, Tfp, s, k = random_visco_state(n, d)
+    Tf = T_prev + 0.5
+    t = gpu_state(p, T_cur, T_prev, Tfp, s, k, materialize=True)
+    t["Tf"] = torch.from_numpy(Tf.copy()).to("cuda:0")
+    plan.update(n, t)
+    o = dict(Tfp=Tfp.copy(), Tf=Tf.copy(), s=s.copy(), k=k.copy(), phi=np.zeros(n), xi=np.zeros(n), sig=np.zeros(n * d * d))
+    vo.step_corrected(p, 0.5, T_cur, T_prev, o["Tfp"], o["Tf"], o["phi"], o["xi"], o["s"], o["k"], o["sig"])
+    assert rel_err(t["sigma"].cpu().numpy(), o["sig"]) <= 1e-12
+    assert_same(t["s_partial"].cpu().numpy(), t["s_tilde"].cpu().numpy(), "history == partial stress")
+    assert_same(t["sigma_partial"].cpu().numpy(), t["sigma_tilde"].cpu().numpy(), "history == partial stress")
+    eth = t["thermal_strain"].cpu().numpy().reshape(n, d, d)[:, 0, 0]
+    expect = p.alpha_solid * (T_cur - T_prev) + (p.alpha_liquid - p.alpha_solid) * (o["Tf"] - Tf)
+    assert np.max(np.abs(eth - expect)) <= 1e-15
+    with pytest.raises(_lib.SgError):
+        plan.update(n, t, _lib.PHASE_TF)            # the corrected scheme only runs as the fused update
