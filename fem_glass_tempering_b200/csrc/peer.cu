@@ -253,46 +253,69 @@ int sg_peer_check(SgPeer *p) {
 }
 
 // segments: at most one neighbour below and one above this rank (x-slab partition)
-int sg_peer_halo_forward(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, cudaStream_t st) {
+static dim3 halo_grid(int n_seg, const sg_halo_segment *seg) {
+    long maxcount = 0;
+    for (int i = 0; i < n_seg && i < 2; ++i) {
+        if (seg[i].send_count > maxcount) maxcount = seg[i].send_count;
+        if (seg[i].recv_count > maxcount) maxcount = seg[i].recv_count;
+    }
+    long gx = (maxcount / 2 + 255) / 256;
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    return dim3((unsigned)gx, (unsigned)(n_seg < 2 ? (n_seg < 1 ? 1 : n_seg) : 2));
+}
+
+int sg_peer_halo_push(SgPeer *p, int n_seg, const sg_halo_segment *seg, const double *vec, cudaStream_t st) {
     const int rank = p->ctx->rank;
     const unsigned long long seq = ++p->halo_seq;
     const int par = (int)(seq & 1ull);
     PushArgs pa;
-    PullArgs pl;
     memset(&pa, 0, sizeof(pa));
-    memset(&pl, 0, sizeof(pl));
-    long maxcount = 0;
     for (int i = 0; i < n_seg && i < 2; ++i) {
         const sg_halo_segment &g = seg[i];
         const int side_there = rank < g.peer ? 0 : 1;   // how the neighbour sees me: I am below it -> its side 0
-        const int side_here = g.peer < rank ? 0 : 1;
         SG_REQUIRE((size_t)g.send_count <= p->mailbox_doubles && (size_t)g.recv_count <= p->mailbox_doubles,
-                   "sg_peer_halo_forward: segment larger than the mailbox");
+                   "sg_peer_halo: segment larger than the mailbox");
         char *rb = p->remote[g.peer];
         pa.seg[i].src = vec + g.send_offset;
         pa.seg[i].dst = reinterpret_cast<double *>(rb + p->lay.mailbox) + ((size_t)side_there * 2 + par) * p->mailbox_doubles;
         pa.seg[i].flag = reinterpret_cast<unsigned long long *>(rb + p->lay.flags) + side_there * 2 + par;
         pa.seg[i].count = g.send_count;
+    }
+    pa.counters = p->counters;
+    pa.seq = seq;
+    k_halo_push<<<halo_grid(n_seg, seg), 256, 0, st>>>(pa);
+    SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
+    return SG_OK;
+}
+
+// completes the exchange started by the LAST sg_peer_halo_push
+int sg_peer_halo_pull(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, cudaStream_t st) {
+    const int rank = p->ctx->rank;
+    const unsigned long long seq = p->halo_seq;
+    const int par = (int)(seq & 1ull);
+    PullArgs pl;
+    memset(&pl, 0, sizeof(pl));
+    for (int i = 0; i < n_seg && i < 2; ++i) {
+        const sg_halo_segment &g = seg[i];
+        const int side_here = g.peer < rank ? 0 : 1;
         pl.seg[i].dst = vec + g.recv_offset;
         pl.seg[i].src = reinterpret_cast<const double *>(p->local + p->lay.mailbox) + ((size_t)side_here * 2 + par) * p->mailbox_doubles;
         pl.seg[i].flag = reinterpret_cast<const unsigned long long *>(p->local + p->lay.flags) + side_here * 2 + par;
         pl.seg[i].count = g.recv_count;
-        if (g.send_count > maxcount) maxcount = g.send_count;
-        if (g.recv_count > maxcount) maxcount = g.recv_count;
     }
-    pa.counters = p->counters;
-    pa.seq = seq;
     pl.seq = seq;
     pl.err = p->err_host;
-    long gx = (maxcount / 2 + 255) / 256;
-    if (gx < 1) gx = 1;
-    if (gx > 64) gx = 64;
-    const dim3 grid((unsigned)gx, (unsigned)(n_seg < 2 ? (n_seg < 1 ? 1 : n_seg) : 2));
-    k_halo_push<<<grid, 256, 0, st>>>(pa);
-    k_halo_pull<<<grid, 256, 0, st>>>(pl);
+    k_halo_pull<<<halo_grid(n_seg, seg), 256, 0, st>>>(pl);
     SG_CHECK_CUDA(cudaGetLastError());
-    sg_count_launch(2);
+    sg_count_launch();
     return SG_OK;
+}
+
+int sg_peer_halo_forward(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, cudaStream_t st) {
+    const int rc = sg_peer_halo_push(p, n_seg, seg, vec, st);
+    return rc ? rc : sg_peer_halo_pull(p, n_seg, seg, vec, st);
 }
 
 int sg_peer_allreduce(SgPeer *p, double *vals, int count, cudaStream_t st) {

@@ -45,8 +45,13 @@ struct SgRed {
 // Must precede sg_thermal_apply_dot whenever T_lin changed (refreshes the linearised boundary matrices).
 int sg_thermal_linearize(sg_thermal_op *op, const double *T_lin, cudaStream_t st);
 // y_is_zero: the caller guarantees y == 0 on entry (CG spaces scatter into y; saves the memset launch).
+// part (DG class kernels on a partitioned mesh, see sg_thermal_can_split): SG_PART_ALL, or SG_PART_INTERIOR (cells
+// without ghost neighbours: may run before the halo has arrived) followed by SG_PART_BOUNDARY (the rest; ADDS its share
+// of the reduction to dot2).
+enum { SG_PART_ALL = 0, SG_PART_INTERIOR = 1, SG_PART_BOUNDARY = 2 };
+bool sg_thermal_can_split(const sg_thermal_op *op);
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
-                         const int *skip, cudaStream_t st, int y_is_zero = 0);
+                         const int *skip, cudaStream_t st, int y_is_zero = 0, int part = SG_PART_ALL);
 
 // One fused Chebyshev step of the polynomial preconditioner (DG + class tables only, see dg_cheb_step):
 // z_out = z_in + a (z_in - z_prev) + b M^-1 (r - J z_in); z_prev == NULL means 0 (first step); z_out may alias
@@ -56,6 +61,7 @@ struct SgChebStep {
     double *z_out;
     double a, b;
     int last;
+    int part;   // SG_PART_*
 };
 bool sg_thermal_has_cheb(const sg_thermal_op *op);
 bool sg_thermal_profiling(const sg_thermal_op *op);   // event pairs around the kernels are being recorded
@@ -70,6 +76,9 @@ bool sg_peer_ready(const SgPeer *p);
 size_t sg_peer_mailbox_doubles(const SgPeer *p);
 int sg_peer_check(SgPeer *p);
 int sg_peer_halo_forward(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, cudaStream_t st);
+// the two halves of a forward exchange, so that work that needs no ghost values can run between them
+int sg_peer_halo_push(SgPeer *p, int n_seg, const sg_halo_segment *seg, const double *vec, cudaStream_t st);
+int sg_peer_halo_pull(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, cudaStream_t st);
 int sg_peer_allreduce(SgPeer *p, double *vals, int count, cudaStream_t st);
 
 // classify.cu: equivalence classes of 64-bit keys.  cls_out[i] = class of keys[i] in [0, *n_cls),
@@ -175,7 +184,7 @@ __device__ __forceinline__ double sg_block_sum(double v, double *scratch) {
 // order (deterministic) and stores the totals in out[0..NR).  Must be reached by every thread of every
 // block; gridDim.x <= SG_MAX_BLOCKS.
 template <int NR>
-__device__ __forceinline__ void sg_grid_reduce(double (&v)[NR], const SgRed red, double *out) {
+__device__ __forceinline__ void sg_grid_reduce(double (&v)[NR], const SgRed red, double *out, const bool accumulate = false) {
     __shared__ double scratch[32];
     __shared__ bool is_last;
 #pragma unroll
@@ -196,7 +205,7 @@ __device__ __forceinline__ void sg_grid_reduce(double (&v)[NR], const SgRed red,
             double s = 0.0;
             for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += red.partials[b * NR + k];
             s = sg_block_sum(s, scratch);
-            if (threadIdx.x == 0) out[k] = s;
+            if (threadIdx.x == 0) out[k] = accumulate ? out[k] + s : s;   // accumulate: second launch over another cell range
         }
         if (threadIdx.x == 0) *red.counter = 0u;
     }

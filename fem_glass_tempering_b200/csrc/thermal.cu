@@ -636,6 +636,23 @@ __global__ void k_pair_score(const uint64_t *cls, long lo, long groups, long str
     if (cls[c0] == cls[c0 + stride]) atomicAdd(matches, 1ull);
 }
 
+// DG partition: owned cells with a neighbour outside [lo, hi) (a ghost cell).  They sit at the two ends of the owned
+// range (x-slabs): lowB = one past the last such cell of the lower half, highB = the first one of the upper half.
+__global__ void k_split_range(int nnb, long nc, long lo, long hi, const int32_t *nbr, unsigned long long *lowB, unsigned long long *highB) {
+    const long c = lo + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= hi) return;
+    bool ghost = false;
+    for (int f = 0; f < nnb; ++f) {
+        const long nb = nbr[(long)f * nc + c];
+        ghost = ghost || (nb >= 0 && (nb < lo || nb >= hi));
+    }
+    if (!ghost) return;
+    if (c < lo + (hi - lo) / 2)
+        atomicMax(lowB, (unsigned long long)(c + 1));
+    else
+        atomicMin(highB, (unsigned long long)c);
+}
+
 struct ClsDev {
     long n_cells, cell_lo, cell_hi, dot_lo, dot_hi;
     const int32_t *nbr;     // DG [NNB][n_cells]
@@ -652,6 +669,10 @@ struct ClsDev {
     // CG: exterior facets applied by the same kernel after the cells (bmat != NULL)
     long n_bf;
     const int32_t *bf_cell, *bf_facet;
+    // DG, partitioned mesh: a launch may cover a second cell range (the two boundary strips) and add its share of the
+    // reduction to what an earlier launch over the interior cells left in dot_out
+    long cell_lo2, cell_hi2;
+    int accumulate;
 };
 
 constexpr int CB = 256;  // threads per block of the class kernels
@@ -902,15 +923,19 @@ __global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_class_apply(const ClsDev 
             for (int i = 0; i < NLD; ++i) dsum[0] += xk0[i] * yk0[i];
         }
     } else {
-        for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
-            double xk[NLD], yk[NLD];
-            dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
-            store_row<NLD, WIDE>(y + c * NLD, yk);
+#pragma unroll 1
+        for (int rg = 0; rg < 2; ++rg) {
+            const long lo = rg ? cd.cell_lo2 : cd.cell_lo, hi = rg ? cd.cell_hi2 : cd.cell_hi;
+            for (long c = lo + (long)blockIdx.x * CB + threadIdx.x; c < hi; c += (long)gridDim.x * CB) {
+                double xk[NLD], yk[NLD];
+                dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
+                store_row<NLD, WIDE>(y + c * NLD, yk);
 #pragma unroll
-            for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
+                for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
+            }
         }
     }
-    sg_grid_reduce<2>(dsum, red, dot_out);
+    sg_grid_reduce<2>(dsum, red, dot_out, cd.accumulate != 0);
 }
 
 // Residual from the class tables: F_K = (cell + interior-facet part of J) T  -  |detJ| Mhat T_prev  -  dt f |detJ| load.
@@ -1034,13 +1059,17 @@ __global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_cheb_step(const ClsDev cd
             cheb_update<NLD, WIDE, FIRST, LAST>(ch, c0, zk0, Jz0, dsum[0]);
         }
     } else {
-        for (long c = cd.cell_lo + (long)blockIdx.x * CB + threadIdx.x; c < cd.cell_hi; c += (long)gridDim.x * CB) {
-            double zk[NLD], Jz[NLD];
-            dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
-            cheb_update<NLD, WIDE, FIRST, LAST>(ch, c, zk, Jz, dsum[0]);
+#pragma unroll 1
+        for (int rg = 0; rg < 2; ++rg) {
+            const long lo = rg ? cd.cell_lo2 : cd.cell_lo, hi = rg ? cd.cell_hi2 : cd.cell_hi;
+            for (long c = lo + (long)blockIdx.x * CB + threadIdx.x; c < hi; c += (long)gridDim.x * CB) {
+                double zk[NLD], Jz[NLD];
+                dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
+                cheb_update<NLD, WIDE, FIRST, LAST>(ch, c, zk, Jz, dsum[0]);
+            }
         }
     }
-    if (LAST) sg_grid_reduce<1>(dsum, red, dot_out);
+    if (LAST) sg_grid_reduce<1>(dsum, red, dot_out, cd.accumulate != 0);
 }
 
 // CG fast apply: gather through the dofmap, class matrix from shared memory, scatter with RED.ADD.F64; then, in the
@@ -1136,6 +1165,8 @@ struct sg_thermal_op {
     size_t cls_smem;
     int32_t n_geom_classes;
     SgRed own_red;         // reduction scratch of sg_thermal_jac_apply (solver-less use of the fast path)
+    long split_lo, split_hi;   // DG: owned cells [split_lo, split_hi) have no ghost neighbour (split_lo >= split_hi: no split)
+    int part;              // set by sg_thermal_apply_dot: SG_PART_*
     int y_is_zero;         // set by sg_thermal_apply_dot: the caller guarantees y == 0 on entry (CG scatter needs no memset)
     int32_t *nbr_ext;      // DG P1: neighbour ids with exterior facets encoded (see ClsDev::bmat)
     double *bmat;
@@ -1177,6 +1208,31 @@ struct ProfScope {  // CUDA-event pair around the apply cell kernel when profili
     }
 };
 
+// ClsDev and grid of one part of a split launch (SG_PART_*)
+inline ClsDev part_view(const sg_thermal_op *op, int part, int *grid) {
+    ClsDev cd = op->cls;
+    cd.cell_lo2 = cd.cell_hi2 = 0;
+    cd.accumulate = 0;
+    long ncell = cd.cell_hi - cd.cell_lo;
+    if (part == SG_PART_INTERIOR) {
+        cd.cell_lo = op->split_lo;
+        cd.cell_hi = op->split_hi;
+        ncell = cd.cell_hi - cd.cell_lo;
+    } else if (part == SG_PART_BOUNDARY) {
+        cd.cell_lo2 = op->split_hi;
+        cd.cell_hi2 = cd.cell_hi;
+        cd.cell_hi = op->split_lo;
+        cd.accumulate = 1;
+        const long n1 = cd.cell_hi - cd.cell_lo, n2 = cd.cell_hi2 - cd.cell_lo2;
+        ncell = n1 > n2 ? n1 : n2;
+    }
+    long g = (ncell + CB - 1) / CB;
+    if (g < 1) g = 1;
+    if (g > op->cls_grid) g = op->cls_grid;
+    *grid = (int)g;
+    return cd;
+}
+
 // dot2 != nullptr (MODE_APPLY only): also produce dot2[0] + dot2[1] = x.y over the owned dofs.
 template <int D, int P, bool DG>
 int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const double *x, const double *xprev, double *y,
@@ -1195,12 +1251,14 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         ProfScope ps(op, mode, st);
         const bool wide = (((uintptr_t)x | (uintptr_t)y) & 31) == 0;
         if constexpr (DG) {
-            if (op->cls.pair_stride > 0 && wide && op->bmat) {
+            if (op->cls.pair_stride > 0 && wide && op->bmat && op->part == SG_PART_ALL) {
                 dg_class_apply<NLD, D + 1, P, true, true, true><<<op->cls_grid_pair, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
             } else {
                 auto k = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true> : dg_class_apply<NLD, D + 1, P, false, true>)
                                   : (wide ? dg_class_apply<NLD, D + 1, P, true, false> : dg_class_apply<NLD, D + 1, P, false, false>);
-                k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+                int grid = op->cls_grid;
+                const ClsDev cdv = part_view(op, op->part, &grid);
+                k<<<grid, CB, op->cls_smem, st>>>(cdv, x, y, red, dst, skip);
             }
         } else
             cg_class_apply<D, P><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
@@ -1294,12 +1352,14 @@ int cheb_step_t(const sg_thermal_op *op, const SgChebStep &cs, SgRed red, double
         static const K pair_table[2][2] = {
             {dg_cheb_step<NLD, NNB, P, true, true, false, false, true>, dg_cheb_step<NLD, NNB, P, true, true, false, true, true>},
             {dg_cheb_step<NLD, NNB, P, true, true, true, false, true>, dg_cheb_step<NLD, NNB, P, true, true, true, true, true>}};
-        const bool pair = op->cls.pair_stride > 0 && wide && bnd;
+        const bool pair = op->cls.pair_stride > 0 && wide && bnd && cs.part == SG_PART_ALL;
         const K k = pair ? pair_table[first][last] : table[wide][bnd][first][last];
         SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
+        int grid = op->cls_grid;
+        const ClsDev cd = part_view(op, cs.part, &grid);
         {
             ProfScope ps(op, MODE_APPLY, st, 1);
-            k<<<pair ? op->cls_grid_pair : op->cls_grid, CB, op->cls_smem, st>>>(op->cls, ch, cs.z_in, red, dot_out, skip);
+            k<<<pair ? op->cls_grid_pair : grid, CB, op->cls_smem, st>>>(cd, ch, cs.z_in, red, dot_out, skip);
         }
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
@@ -1417,6 +1477,25 @@ int build_classes_t(sg_thermal_op *op) {
     cd.n_self = NS;
     cd.n_nb = NF;
     cd.S = S;
+    cd.cell_lo2 = cd.cell_hi2 = 0;
+    cd.accumulate = 0;
+    op->split_lo = op->split_hi = 0;
+    if (DG && (dv.cell_lo > 0 || dv.cell_hi < nc)) {
+        DevBuf b2;
+        SG_CHECK_CUDA(cudaMalloc(&b2.p, 2 * sizeof(unsigned long long)));
+        const unsigned long long init[2] = {(unsigned long long)dv.cell_lo, (unsigned long long)dv.cell_hi};
+        SG_CHECK_CUDA(cudaMemcpy(b2.p, init, sizeof(init), cudaMemcpyHostToDevice));
+        const long nown = dv.cell_hi - dv.cell_lo;
+        k_split_range<<<(unsigned)((nown + 255) / 256), 256>>>(NNB, nc, dv.cell_lo, dv.cell_hi, dv.nbr, b2.as<unsigned long long>(),
+                                                               b2.as<unsigned long long>() + 1);
+        unsigned long long res[2];
+        SG_CHECK_CUDA(cudaMemcpy(res, b2.p, sizeof(res), cudaMemcpyDeviceToHost));
+        // worth splitting only if the interior is the bulk of the work
+        if ((long)res[1] - (long)res[0] > nown / 2) {
+            op->split_lo = (long)res[0];
+            op->split_hi = (long)res[1];
+        }
+    }
     cd.bmat = nullptr;
     cd.n_bf = dv.n_bf;
     cd.bf_cell = dv.bf_cell;
@@ -1548,11 +1627,19 @@ int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, dou
     return op->cheb_step(op, cs, red, dot_out, skip, st);
 }
 
+bool sg_thermal_can_split(const sg_thermal_op *op) {
+    return op->d.family == 1 && op->cls.tab != nullptr && op->cls.pair_stride == 0 && op->split_hi > op->split_lo &&
+           (op->bmat != nullptr || op->d.n_bfacets == 0);
+}
+
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
-                         const int *skip, cudaStream_t st, int y_is_zero) {
+                         const int *skip, cudaStream_t st, int y_is_zero, int part) {
+    SG_REQUIRE(part == SG_PART_ALL || sg_thermal_can_split(op), "sg_thermal_apply_dot: this operator cannot be split");
     op->y_is_zero = y_is_zero;
+    op->part = part;
     const int rc = op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, red, dot2, skip, st);
     op->y_is_zero = 0;
+    op->part = SG_PART_ALL;
     return rc;
 }
 
