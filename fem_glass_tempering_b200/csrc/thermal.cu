@@ -976,7 +976,7 @@ __global__ void __launch_bounds__(CB, 3) dg_class_resid(const ClsDev cd, const _
 }
 
 template <int NLD>
-__global__ void __launch_bounds__(CB) cg_class_resid(const ClsDev cd, const __grid_constant__ ResidDev rd, const double *__restrict__ x,
+__global__ void __launch_bounds__(CB, 4) cg_class_resid(const ClsDev cd, const __grid_constant__ ResidDev rd, const double *__restrict__ x,
                                                      double *__restrict__ y) {
     extern __shared__ __align__(16) double s_tab[];
     load_class_tables(cd, s_tab, cd.n_self * cd.S);
@@ -1077,7 +1077,7 @@ __global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_cheb_step(const ClsDev cd
 // x.y is reduced cell-wise as x_K . (A_K x_K) over the cells [dot_lo, dot_hi) (each global cell on one rank) plus
 // x_F . (B_F x_F) over their exterior facets.
 template <int D, int P>
-__global__ void __launch_bounds__(CB) cg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
+__global__ void __launch_bounds__(CB, 4) cg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
                                                      SgRed red, double *dot_out, const int *skip) {
     constexpr int NLD = nld_of(D, P);
     extern __shared__ __align__(16) double s_tab[];
