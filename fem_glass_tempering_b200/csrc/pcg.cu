@@ -365,25 +365,6 @@ __global__ void __launch_bounds__(VB) k_axpy_p(long n, const double *__restrict_
         p[i] = z[i] + (first ? 0.0 : beta * p[i]);
 }
 
-// power iteration for the largest eigenvalue of M^-1 J:  v = scale * M^-1 w,  out = |v|^2 over owned cells
-template <int NLD>
-__global__ void __launch_bounds__(VB) k_precond_scale(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
-                                                      const double *__restrict__ detJ, const double *__restrict__ w,
-                                                      double scale, double *__restrict__ v, Red red, double *out) {
-    double acc[1] = {0.0};
-    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
-        double wk[NLD], vk[NLD];
-        ld_row<NLD>(w + c * NLD, wk);
-        mass_solve<NLD>(mi, scale / detJ[c], wk, vk);
-        st_row<NLD>(v + c * NLD, vk);
-        if (c >= clo && c < chi) {
-#pragma unroll
-            for (int i = 0; i < NLD; ++i) acc[0] += vk[i] * vk[i];
-        }
-    }
-    grid_reduce<1>(acc, red, out);
-}
-
 // deterministic pseudo-random start vector in (-1, 1) from the GLOBAL dof index (same field for every partition)
 __global__ void __launch_bounds__(VB) k_hash_fill(long n, long global_offset, long lo, long hi, double *__restrict__ v, Red red,
                                                   double *out) {
@@ -553,44 +534,94 @@ int blk_update_xr_cheb(sg_thermal_solver *s, double *x, double inv_theta, const 
     sg_count_launch();
     return SG_OK;
 }
-template <int NLD>
-int blk_precond_scale(sg_thermal_solver *s, const double *w, double scale, double *v, double *out, cudaStream_t st) {
-    k_precond_scale<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, w, scale, v,
-                                                          s->red, out);
-    SG_CHECK_CUDA(cudaGetLastError());
-    sg_count_launch();
-    return SG_OK;
+// Number of eigenvalues of the symmetric tridiagonal matrix (diagonal a, off-diagonal o) below x (Sturm sequence).
+static int sturm_count(const double *a, const double *o, int m, double x) {
+    int cnt = 0;
+    double d = 1.0;
+    for (int i = 0; i < m; ++i) {
+        const double off2 = i ? o[i - 1] * o[i - 1] : 0.0;
+        d = a[i] - x - (i ? off2 / (d != 0.0 ? d : 1e-300) : 0.0);
+        if (d < 0.0) ++cnt;
+    }
+    return cnt;
 }
 
-// Largest eigenvalue of M^-1 J(T_lin) by 20 power iterations (v in s->p, J v in s->Ap); sets cheb_lo/hi.
-// An UNDER-estimated upper bound makes the polynomial preconditioner indefinite, so the estimate (which
-// approaches lambda_max from below) gets a 25 % margin; an over-estimate only costs a few per cent.
+// Extreme eigenvalues of M^-1 J(T_lin) from the Lanczos tridiagonal matrix that CG builds implicitly: LANCZOS steps of
+// the element-mass preconditioned iteration on a pseudo-random right-hand side, alpha/beta read back every step
+// (set-up only), largest/smallest Ritz value by bisection.  Ritz values converge to the extreme eigenvalues from
+// inside within a fraction of a per cent in ~20 steps (20 power iterations are still 4 % short), so the Chebyshev
+// interval can be tight: hi = 1.05 * ritz_max.  An UNDER-estimated upper bound makes the polynomial preconditioner
+// indefinite; pcg_run widens the interval and retries when that is detected.
 int estimate_spectrum(sg_thermal_solver *s, const double *T_lin, cudaStream_t st) {
+    constexpr int LANCZOS = 24;
     int rc;
-    double *S7 = s->S + 7;
-    k_hash_fill<<<vgrid(s->n), VB, 0, st>>>(s->n, 0, s->lo, s->hi, s->p, s->red, S7);
+    double *S = s->S;
+    double *rhs = s->zA, *xs = s->zB;
+    k_hash_fill<<<vgrid(s->n), VB, 0, st>>>(s->n, 0, s->lo, s->hi, rhs, s->red, S + 7);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
-    if ((rc = allreduce(s, S7, 1, st))) return rc;
-    if ((rc = read_scalars(s, 7, 1, st))) return rc;
-    double nrm = sqrt(s->S_host[7]), lam = 0.0;
+    SG_BLK_DISPATCH(blk_init, s, rhs, xs, st);
+    if (rc) return rc;
+    if ((rc = allreduce(s, S, 2, st))) return rc;
+    k_pcg_begin<<<1, 1, 0, st>>>(s->ctrl, 0.0);     // target 0: the iteration never stops by itself
+    SG_CHECK_CUDA(cudaGetLastError());
     if ((rc = sg_thermal_linearize(s->op, T_lin, st))) return rc;
-    for (int i = 0; i < 20; ++i) {
+    if ((rc = read_scalars(s, 0, 8, st))) return rc;
+    double rz = s->S_host[0], alpha_prev = 0.0, beta_prev = 0.0;
+    double diag[LANCZOS], off[LANCZOS];
+    int m = 0;
+    for (int it = 0; it < LANCZOS; ++it) {
+        double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
         if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
-        if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, s->S + 4, nullptr, st))) return rc;
-        SG_BLK_DISPATCH(blk_precond_scale, s, s->Ap, 1.0 / nrm, s->p, S7, st);
+        if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, nullptr, st))) return rc;
+        if ((rc = allreduce(s, S + 4, 2, st))) return rc;
+        SG_BLK_DISPATCH(blk_update_xr, s, xs, Scur, Snext, st);
         if (rc) return rc;
-        if ((rc = allreduce(s, S7, 1, st))) return rc;
-        if ((rc = read_scalars(s, 7, 1, st))) return rc;
-        lam = sqrt(s->S_host[7]);
-        if (!(lam > 0.0) || !isfinite(lam)) {
-            sg_set_error("estimate_spectrum: power iteration broke down (|M^-1 J v| = %g)", lam);
-            return SG_E_NOCONV;
-        }
-        nrm = lam;
+        if ((rc = allreduce(s, Snext, 2, st))) return rc;
+        SG_BLK_DISPATCH(blk_update_p, s, Scur, Snext, st);
+        if (rc) return rc;
+        if ((rc = read_scalars(s, 0, 8, st))) return rc;
+        const double pAp = s->S_host[4] + s->S_host[5], rz_next = s->S_host[2 * ((it + 1) & 1)];
+        if (!(pAp > 0.0) || !(rz > 0.0) || !isfinite(rz_next)) break;
+        const double alpha = rz / pAp, beta = rz_next / rz;
+        diag[m] = 1.0 / alpha + (m ? beta_prev / alpha_prev : 0.0);
+        if (m) off[m - 1] = sqrt(beta_prev) / alpha_prev;
+        ++m;
+        alpha_prev = alpha;
+        beta_prev = beta;
+        rz = rz_next;
+        if (!(rz_next > 0.0)) break;
     }
-    s->cheb_hi = 1.25 * lam;
-    s->cheb_lo = fmin(0.9, s->cheb_hi / 4.0);
+    if (m < 3) {
+        sg_set_error("estimate_spectrum: the Lanczos iteration broke down after %d steps", m);
+        return SG_E_NOCONV;
+    }
+    double glo = diag[0], ghi = diag[0];   // Gershgorin bracket
+    for (int i = 0; i < m; ++i) {
+        const double rad = (i ? fabs(off[i - 1]) : 0.0) + (i + 1 < m ? fabs(off[i]) : 0.0);
+        glo = fmin(glo, diag[i] - rad);
+        ghi = fmax(ghi, diag[i] + rad);
+    }
+    double lo = glo, hi = ghi;             // largest eigenvalue: smallest x with count(x) == m
+    for (int i = 0; i < 80; ++i) {
+        const double mid = 0.5 * (lo + hi);
+        if (sturm_count(diag, off, m, mid) >= m) hi = mid; else lo = mid;
+    }
+    const double ritz_max = hi;
+    lo = glo;
+    hi = ghi;                              // smallest eigenvalue: largest x with count(x) == 0
+    for (int i = 0; i < 80; ++i) {
+        const double mid = 0.5 * (lo + hi);
+        if (sturm_count(diag, off, m, mid) >= 1) hi = mid; else lo = mid;
+    }
+    const double ritz_min = lo;
+    if (!(ritz_max > 0.0) || !isfinite(ritz_max)) {
+        sg_set_error("estimate_spectrum: bad Ritz value %g", ritz_max);
+        return SG_E_NOCONV;
+    }
+    s->cheb_hi = 1.05 * ritz_max;
+    s->cheb_lo = fmin(0.9 * fmax(ritz_min, 0.0) + 0.0, s->cheb_hi / 4.0);
+    if (!(s->cheb_lo > 0.0)) s->cheb_lo = s->cheb_hi / 30.0;
     return SG_OK;
 }
 
@@ -947,9 +978,13 @@ int sg_thermal_solver_get_chebyshev(const sg_thermal_solver *s, int32_t *degree,
 static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, double *x, const PcgTol &tp,
                    int32_t max_it, int32_t *iters, double *rel_res, cudaStream_t st) {
     if (s->cheb_degree > 0 && !s->cheb_failed) {
-        const int rc_c = pcg_run_cheb(s, T_lin, b, x, tp, max_it, iters, rel_res, st);
+        int rc_c = pcg_run_cheb(s, T_lin, b, x, tp, max_it, iters, rel_res, st);
+        for (int retry = 0; rc_c == SG_E_NOCONV && retry < 2 && s->cheb_hi > 0.0; ++retry) {
+            s->cheb_hi *= 1.3;   // the upper bound was too small (r.z <= 0 or no convergence): widen the interval
+            rc_c = pcg_run_cheb(s, T_lin, b, x, tp, max_it, iters, rel_res, st);
+        }
         if (rc_c != SG_E_NOCONV) return rc_c;
-        s->cheb_failed = 1;   // eigenvalue bound too small or breakdown: fall back to the block-Jacobi iteration for good
+        s->cheb_failed = 1;   // still failing: fall back to the block-Jacobi iteration for good
     }
     const long n = s->n, lo = s->lo, hi = s->hi;
     const unsigned g = vgrid(n);

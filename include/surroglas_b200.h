@@ -256,9 +256,10 @@ int sg_thermal_solver_destroy(sg_thermal_solver *s);
 /* DG spaces with the class tables in use: precondition CG with the degree-`degree` Chebyshev polynomial in
  * M^-1 J (M = element mass blocks) instead of M^-1 alone: one CG iteration then does degree + 1 operator
  * applications (fused with the polynomial recurrence, J z never goes to memory) but only one set of CG vector
- * updates and reductions.  [lo, hi] bounds the spectrum of M^-1 J; hi <= 0: estimated by power iteration at
- * first use (+25 %).  Returns 1 when enabled, 0 when not available (CG spaces, general kernel) or degree == 0.
- * If the polynomial turns out not to be positive definite the solver falls back to M^-1 for good. */
+ * updates and reductions.  [lo, hi] bounds the spectrum of M^-1 J; hi <= 0: estimated at first use from the Ritz
+ * values of 24 Lanczos (CG) steps (hi = 1.05 theta_max).  Returns 1 when enabled, 0 when not available (CG spaces,
+ * general kernel) or degree == 0.  If the polynomial turns out not to be positive definite the interval is widened
+ * (x1.3, twice) and the solve retried; after that the solver falls back to M^-1 for good. */
 int sg_thermal_solver_set_chebyshev(sg_thermal_solver *s, int32_t degree, double lo, double hi);
 int sg_thermal_solver_get_chebyshev(const sg_thermal_solver *s, int32_t *degree, double *lo, double *hi);
 /* Solve J(T_lin) x = b with Jacobi-PCG from x = 0; blocks until converged (KSP 'cg', TVP:343). */

@@ -123,7 +123,7 @@ def test_fused_dot_product_of_the_solver(sg_ctx, dim, family, degree):
 @pytest.mark.parametrize("dim,degree", [(3, 1), (2, 1), (1, 1), (1, 2), (3, 2)])
 def test_chebyshev_preconditioned_pcg(sg_ctx, dim, degree):
     """DG: CG preconditioned with the Chebyshev polynomial in M^-1 J reaches the same solution as the element-mass
-    preconditioner in fewer (outer) iterations; the spectrum bound comes from the library's power iteration."""
+    preconditioner in fewer (outer) iterations; the spectrum interval comes from the library's Lanczos estimate."""
     import scipy.sparse.linalg as spla
     m = make_mesh(dim) if degree == 1 else (msh.graded_line_mesh() if dim == 1 else msh.box_mesh(4, 3, 2, 12.0, 9.0, 6.0))
     space = fe.ScalarSpace(m, "DG", degree)
