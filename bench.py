@@ -264,6 +264,8 @@ def run_gpu(args):
     op = prob._thermal_op
     if args.cheb is not None:
         op.set_chebyshev(args.cheb)
+    if args.eta is not None:
+        prob.solver.forcing_eta = args.eta
     L = _lib.lib()
     nT = prob.functionSpaces["T"].n_nodes
     nS = prob.functionSpaces["sigma"].n_nodes
@@ -483,6 +485,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cheb", type=int, default=None, help="Chebyshev preconditioner degree of the DG solver (0 = off)")
+    ap.add_argument("--eta", type=float, default=None, help="first forcing term of the inexact Newton iteration (0 = fixed tolerance)")
     args = ap.parse_args()
     with StdoutToStderr() as OUT:
         if args.impl == "reference":
