@@ -46,7 +46,7 @@ class NewtonSolverGPU:
         self.report = False
         self.krylov_solver = _KrylovStub()
         self.linear_rtol = 1e-12   # final linear-residual target of a step, relative to the first Newton residual
-        self.forcing_eta = 3e-3    # inexact Newton: first forcing term (0 = every PCG solve runs to the target)
+        self.forcing_eta = 1e-3    # inexact Newton: first forcing term (0 = every PCG solve runs to the target)
         self.last_stats = None
 
     def solve(self, u: Function):

@@ -112,7 +112,7 @@ class ThermalOperator:
         sh = C.c_void_p()
         _lib.check(L.sg_thermal_solver_create(self.handle, self.workspace.data_ptr(), self.halo, C.byref(sh)))
         self.solver = sh
-        self.opts = NewtonOptsC(1e-12, 1e-10, 50, 1e-12, 0.0, 10000, 3e-3)
+        self.opts = NewtonOptsC(1e-12, 1e-10, 50, 1e-12, 0.0, 10000, 1e-3)
         self.chebyshev_degree = 0
         if cheb_degree is None:
             # polynomial preconditioning trades CG vector updates for operator applications: worth it on large DG
