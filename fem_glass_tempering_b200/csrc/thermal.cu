@@ -583,51 +583,6 @@ __global__ void __launch_bounds__(TB) k_bfacet_mats(const OpDev op, const double
     for (int k = 0; k < NFDP; ++k) bmat[b * NFDP + k] = B[k];
 }
 
-// CG: y += B_f x on the facet's dofs from the precomputed matrices (the DG class kernel does this inline);
-// reduces x.(B_f x) over facets of the cells [dot_lo, dot_hi).
-template <int D, int P>
-__global__ void __launch_bounds__(TB) cg_bfacet_apply(const OpDev op, const double *__restrict__ bmat, const double *__restrict__ x,
-                                                      double *__restrict__ y, SgRed red, double *dot_out, const int *skip) {
-    constexpr int NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
-    if (skip && *skip) return;
-    double dsum[1] = {0.0};
-    for (long b = (long)blockIdx.x * TB + threadIdx.x; b < op.n_bf; b += (long)gridDim.x * TB) {
-        const long c = op.bf_cell[b];
-        if (c < op.cell_lo || c >= op.cell_hi) continue;
-        const int f = op.bf_facet[b];
-        long dof[NFD];
-        double xk[NFD], yk[NFD], B[NFDP];
-#pragma unroll
-        for (int k = 0; k < NFD; ++k) {
-            int fd = 0;
-#pragma unroll
-            for (int ff = 0; ff < D + 1; ++ff)
-                if (ff == f) fd = facet_dof(D, P, ff, k);
-            dof[k] = op.dofmap[(long)fd * op.n_cells + c];
-            xk[k] = x[dof[k]];
-            yk[k] = 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < NFDP; ++k) B[k] = bmat[b * NFDP + k];
-        int m = 0;
-#pragma unroll
-        for (int k = 0; k < NFD; ++k)
-#pragma unroll
-            for (int l = k; l < NFD; ++l) {
-                yk[k] += B[m] * xk[l];
-                if (l != k) yk[l] += B[m] * xk[k];
-                ++m;
-            }
-        const bool counted = c >= op.dot_lo && c < op.dot_hi;
-#pragma unroll
-        for (int k = 0; k < NFD; ++k) {
-            atomicAdd(&y[dof[k]], yk[k]);
-            if (counted) dsum[0] += xk[k] * yk[k];
-        }
-    }
-    sg_grid_reduce<1>(dsum, red, dot_out);
-}
-
 // fraction of the pairs (c, c + stride) of the paired work decomposition whose class words agree
 __global__ void k_pair_score(const uint64_t *cls, long lo, long groups, long stride, unsigned long long *matches) {
     const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
