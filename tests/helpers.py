@@ -58,3 +58,14 @@ def random_visco_state(n, d, N=6, seed=1234):
     s = rng.normal(0.0, 1e-3, n * N * d * d)
     k = rng.normal(0.0, 1e-3, n * N * d * d)
     return T_cur, T_prev, Tfp, s, k
+
+
+def load_thermal_kat():
+    """tests/golden/thermal_kat.json: hand-evaluated residual / Jacobian-vector product of the heat equation on the
+    reference's graded 1-D line (generator: tests/golden/make_thermal_kat.py)."""
+    with open(os.path.join(GOLDEN, "thermal_kat.json")) as fh:
+        data = json.load(fh)
+    arr = lambda v: np.array(unhex(v))
+    cases = [dict(family=c["family"], degree=c["degree"], T=arr(c["T"]), T_prev=arr(c["T_prev"]), x=arr(c["x"]),
+                  residual=arr(c["residual"]), jac_x=arr(c["jac_x"])) for c in data["cases"]]
+    return dict(dt=data["dt"], points=arr(data["points"]), cases=cases)

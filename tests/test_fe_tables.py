@@ -226,3 +226,20 @@ def test_class_uniform_cell_tiles(dims):
                 assert np.allclose(J, J[0], atol=1e-12), "cells of one tile row differ in shape"
     r = msh.rectangle_mesh(5, 40)
     assert r.n_cells == 400 and len({tuple(c) for c in r.cells.tolist()}) == 400
+
+
+def test_oracle_and_mesher_against_the_hand_evaluated_1d_vectors():
+    """The assembled oracle (and the graded-line mesher) against tests/golden/thermal_kat.json: residual and Jacobian-vector
+    product of TVP:293-325 on the reference's own mesh, hand-evaluated with closed-form P1 element matrices in plain
+    Python (tests/golden/make_thermal_kat.py).  1e-12 relative: the summation orders differ."""
+    from helpers import load_thermal_kat
+    kat = load_thermal_kat()
+    m = msh.graded_line_mesh()
+    assert m.n_cells == 48 and np.max(np.abs(m.x[:, 0] - kat["points"])) <= 1e-13
+    for c in kat["cases"]:
+        space = fe.ScalarSpace(m, c["family"], c["degree"])
+        orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, c["family"], c["degree"], MAIN_PARAMS, kat["dt"])
+        F = orc.residual(c["T"], c["T_prev"])
+        Jx = orc.jacobian(c["T"]) @ c["x"]
+        assert np.max(np.abs(F - c["residual"])) <= 1e-12 * np.max(np.abs(c["residual"])), c["family"]
+        assert np.max(np.abs(Jx - c["jac_x"])) <= 1e-12 * np.max(np.abs(c["jac_x"])), c["family"]
