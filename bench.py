@@ -47,8 +47,11 @@ MAIN_PARAMS = {  # main.py:29-55
 PARAM_OVERRIDES = {"C3_plate3d_DG1_robin_19.7M_qp": {"sip_penalty": 6.0}, "small_plate3d_DG1": {"sip_penalty": 6.0}}
 
 
+REFERENCE_PENALTY = False    # --reference-penalty: run the 3-D DG plates with the reference's 5.0 (diverges after ~15 steps)
+
+
 def params_of(workload: str) -> dict:
-    return dict(MAIN_PARAMS, **PARAM_OVERRIDES.get(workload, {}))
+    return dict(MAIN_PARAMS, **({} if REFERENCE_PENALTY else PARAM_OVERRIDES.get(workload, {})))
 
 
 WORKLOADS = {
@@ -387,7 +390,8 @@ def run_gpu(args):
         "config": {"workload": args.workload, "cells_per_gpu": int(mesh.n_cells if world == 1 else qp_local // (dim + 1)),
                    "qp_per_gpu": int(qp_local), "qp_total": int(qp_total), "fe_config": cfg, "dt": DT, "prony_terms": 6,
                    "model_params": "main.py:29-55" + ("".join(f", {k} = {v} (reference: 5.0 at TVP:313 is not coercive on tetrahedra; its "
-                                                              "run diverges after ~15 steps)" for k, v in PARAM_OVERRIDES.get(args.workload, {}).items())),
+                                                              "run diverges after ~15 steps)" for k, v in
+                                                              ({} if REFERENCE_PENALTY else PARAM_OVERRIDES.get(args.workload, {})).items())),
                    "plate_mm": list(lengths), "partition": f"x-slabs over {world} GPU(s)",
                    "transport": ("single GPU" if world == 1 else
                                  ("NVLink peer memory (IPC-mapped mailboxes + flags; no NCCL on the data path)" if op.peer_memory
@@ -485,8 +489,12 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cheb", type=int, default=None, help="Chebyshev preconditioner degree of the DG solver (0 = off)")
+    ap.add_argument("--reference-penalty", action="store_true",
+                    help="3-D DG plates with the reference's SIP penalty 5.0 instead of the coercive 6.0 (keep the run under 15 steps)")
     ap.add_argument("--eta", type=float, default=None, help="first forcing term of the inexact Newton iteration (0 = fixed tolerance)")
     args = ap.parse_args()
+    global REFERENCE_PENALTY
+    REFERENCE_PENALTY = args.reference_penalty
     with StdoutToStderr() as OUT:
         if args.impl == "reference":
             run_reference(args)
