@@ -69,3 +69,15 @@ def load_thermal_kat():
     cases = [dict(family=c["family"], degree=c["degree"], T=arr(c["T"]), T_prev=arr(c["T_prev"]), x=arr(c["x"]),
                   residual=arr(c["residual"]), jac_x=arr(c["jac_x"])) for c in data["cases"]]
     return dict(dt=data["dt"], points=arr(data["points"]), cases=cases)
+
+
+def load_thermal_kat_simplex():
+    """tests/golden/thermal_kat_2d3d.json: hand-evaluated residual / Jacobian-vector product on small perturbed 2-D and 3-D
+    meshes, DG1 and CG1 (generator: tests/golden/make_thermal_kat_simplex.py).  The meshes come from the file."""
+    with open(os.path.join(GOLDEN, "thermal_kat_2d3d.json")) as fh:
+        data = json.load(fh)
+    arr = lambda v: np.array(unhex(v))
+    cases = [dict(dim=c["dim"], family=c["family"], degree=c["degree"], x=np.array([unhex(p) for p in c["x"]]),
+                  cells=np.array(c["cells"]), T=arr(c["T"]), T_prev=arr(c["T_prev"]), v=arr(c["v"]),
+                  residual=arr(c["residual"]), jac_x=arr(c["jac_x"])) for c in data["cases"]]
+    return dict(dt=data["dt"], cases=cases)

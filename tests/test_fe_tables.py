@@ -243,3 +243,21 @@ def test_oracle_and_mesher_against_the_hand_evaluated_1d_vectors():
         Jx = orc.jacobian(c["T"]) @ c["x"]
         assert np.max(np.abs(F - c["residual"])) <= 1e-12 * np.max(np.abs(c["residual"])), c["family"]
         assert np.max(np.abs(Jx - c["jac_x"])) <= 1e-12 * np.max(np.abs(c["jac_x"])), c["family"]
+
+
+def test_oracle_against_the_hand_evaluated_2d_3d_vectors():
+    """The assembled oracle against tests/golden/thermal_kat_2d3d.json: the weak form of TVP:293-325 (mass, stiffness,
+    Robin + radiation, SIP with the '+' = lower-cell-index convention and h = CellDiameter('+')) hand-evaluated in plain
+    Python on small PERTURBED triangle / tetrahedron meshes, DG1 and CG1.  1e-12 relative (summation orders differ)."""
+    from helpers import load_thermal_kat_simplex
+    from fem_glass_tempering_b200.mesh import Mesh
+    kat = load_thermal_kat_simplex()
+    assert {(c["dim"], c["family"]) for c in kat["cases"]} == {(2, "DG"), (2, "CG"), (3, "DG"), (3, "CG")}
+    for c in kat["cases"]:
+        m = Mesh(c["x"], c["cells"])
+        space = fe.ScalarSpace(m, c["family"], c["degree"])
+        orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, c["family"], c["degree"], MAIN_PARAMS, kat["dt"])
+        F = orc.residual(c["T"], c["T_prev"])
+        Jx = orc.jacobian(c["T"]) @ c["v"]
+        assert np.max(np.abs(F - c["residual"])) <= 1e-12 * np.max(np.abs(c["residual"])), (c["dim"], c["family"])
+        assert np.max(np.abs(Jx - c["jac_x"])) <= 1e-12 * np.max(np.abs(c["jac_x"])), (c["dim"], c["family"])
