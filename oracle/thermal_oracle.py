@@ -10,8 +10,10 @@ dolfinx.fem.petsc.NonlinearProblem + dolfinx.nls.petsc.NewtonSolver + PETSc KSP
 The linear solves use a sparse direct factorisation, i.e. the exact discrete Newton step that the
 reference's CG+GAMG (TVP:343-344) approximates.
 
-PARITY UNPINNED: the reference has no tests/golden vectors and dolfinx/PETSc are un-vendored and not
-installable here.  Independence from the product: basis functions come from a Vandermonde inversion on
+PARITY UNPINNED against a reference RUN: the reference has no tests/golden vectors and dolfinx/PETSc are un-vendored
+and not installable here.  What pins this module instead: tests/golden/thermal_kat.json (the reference's graded 1-D
+line) and tests/golden/thermal_kat_2d3d.json (perturbed triangle / tetrahedron meshes), hand-evaluated from the weak
+form TVP:293-325 in plain Python by the committed generators; tests/test_fe_tables.py holds this module to them at 1e-12.  Independence from the product: basis functions come from a Vandermonde inversion on
 monomials (not the product's barycentric formulas), the '-' side of an interior facet is evaluated by
 inverting the affine map at the physical quadrature point (no permutation tables), normals and measures
 come from vertex coordinates.  Only the node numbering (dofmap + reference node order) is shared so that
