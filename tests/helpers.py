@@ -81,3 +81,13 @@ def load_thermal_kat_simplex():
                   cells=np.array(c["cells"]), T=arr(c["T"]), T_prev=arr(c["T_prev"]), v=arr(c["v"]),
                   residual=arr(c["residual"]), jac_x=arr(c["jac_x"])) for c in data["cases"]]
     return dict(dt=data["dt"], cases=cases)
+
+
+def load_main_py_history():
+    """tests/golden/main_py_history.json: hand-evaluated first time steps of the reference's default run
+    (generator: tests/golden/make_main_py_history.py)."""
+    with open(os.path.join(GOLDEN, "main_py_history.json")) as fh:
+        data = json.load(fh)
+    arr = lambda v: np.array([float("nan") if q == "nan" else float.fromhex(q) for q in v])
+    steps = [{k: (arr(v) if isinstance(v, list) else v) for k, v in s.items()} for s in data["steps"]]
+    return dict(dt=data["dt"], T_0=data["T_0"], points=arr(data["points"]), winner_dof=np.array(data["winner_dof"]), steps=steps)

@@ -118,3 +118,26 @@ def test_nan_where_T_unchanged():
     assert st["xi"][0] == 0.0
     assert np.isnan(st["sigma_next"][:4]).all()
     assert np.isfinite(st["sigma_next"][4:]).all()
+
+
+def test_whole_step_oracle_against_the_hand_evaluated_default_run():
+    """oracle/reference_problem.py (assembled heat solve + 17-pass replay + last-cell-wins DG1 -> CG1 interpolation) against
+    tests/golden/main_py_history.json: the first five steps of main.py's default run evaluated by hand in plain Python.
+    T and Tf 1e-12; stress 1e-9 where the node's temperature moved (its formula cancels)."""
+    from fem_glass_tempering_b200 import fe
+    from fem_glass_tempering_b200 import mesh as msh
+    from helpers import load_main_py_history
+    from oracle.reference_problem import OracleProblem
+    g = load_main_py_history()
+    m = msh.graded_line_mesh()
+    T, S = fe.ScalarSpace(m, "DG", 1), fe.ScalarSpace(m, "CG", 1)
+    sp = lambda s: dict(dofmap=s.dofmap, ref_nodes=s.element.nodes, family=s.family, degree=s.degree)
+    orc = OracleProblem(m.x, m.cells, sp(T), sp(S), vo.MAIN_PARAMS, g["dt"])
+    for st in g["steps"]:
+        orc.step()
+        assert np.max(np.abs(orc.f["T_cur"] - st["T"])) <= 1e-12 * 800
+        assert np.max(np.abs(orc.f["Tf_cur"] - st["Tf"])) <= 1e-12 * 800
+        moved = np.abs(st["T"] - st["T_prev"])[g["winner_dof"]] > 1e-6
+        so, sg = orc.f["sigma_next"].reshape(-1), st["sigma"]
+        assert moved.sum() >= 20 and np.max(np.abs(so[moved] - sg[moved])) <= 1e-9 * np.max(np.abs(sg[moved]))
+        orc.end_step()

@@ -291,3 +291,22 @@ def test_corrected_physics_through_the_problem_api(sg_ctx):
         assert rel_err(sig, o["sig"]) <= 1e-11
     with pytest.raises(NotImplementedError):
         prob._solve_Tf()
+
+
+def test_default_run_against_the_hand_evaluated_history(sg_ctx):
+    """ThermoViscoProblem with main.py's configuration against tests/golden/main_py_history.json (first five steps of the
+    reference's default run, hand-evaluated in plain Python: closed-form P1 matrices, dense Newton solves, the 16
+    expressions, last-cell-wins DG1 -> CG1).  T, Tf: 1e-10 relative; stress where the temperature moved: 1e-7 with the
+    default solver settings (same bound as test_main_py_default_run)."""
+    from helpers import load_main_py_history
+    g = load_main_py_history()
+    prob = ThermoViscoProblem(mesh_path="", time=(0.0, 50.0), dt=g["dt"], config=MAIN_CONFIG, model_parameters=MAIN_PARAMS,
+                              mesh=msh.graded_line_mesh(), ctx=sg_ctx, verbose=False)
+    prob.setup(dirichlet_bc=False)
+    for st in g["steps"]:
+        prob.solve_timestep(t=0.0)
+        assert rel_err(cpu(prob.functions_current["T"]), st["T"]) <= 1e-10
+        assert rel_err(cpu(prob.functions_current["Tf"]), st["Tf"]) <= 1e-10
+        moved = np.abs(st["T"] - st["T_prev"])[g["winner_dof"]] > 1e-6
+        sig = cpu(prob.functions_next["sigma"])
+        assert np.max(np.abs(sig[moved] - st["sigma"][moved])) <= 1e-7 * np.max(np.abs(st["sigma"][moved]))
