@@ -1,14 +1,20 @@
-// Jacobi-preconditioned conjugate gradients + Newton time-step driver + ghost-dof halo for hot path (B).
+// Preconditioned conjugate gradients + inexact-Newton time-step driver + ghost-dof halo for hot path (B).
 //
-// Replaces dolfinx.nls.petsc.NewtonSolver (incremental criterion, TVP:334-337) and its PETSc KSP
-// 'cg' (TVP:343) — GAMG is not reproduced: the Jacobian M + dt*(alpha*K + boundary) is mass-dominated
-// and Jacobi-PCG converges in a few tens of iterations.
+// Replaces dolfinx.nls.petsc.NewtonSolver (incremental criterion, TVP:334-337) and its PETSc KSP 'cg'
+// (TVP:343) — GAMG is not reproduced: the Jacobian M + dt*(alpha*K + boundary) is mass-dominated.
 //
-// All CG scalars (r.z, p.Ap, |r|^2) live on the device: each fused vector kernel finishes its
-// reduction with warp shuffles -> per-block partials -> the last block to finish sums the partials in
-// fixed order (deterministic), and the next kernel reads alpha/beta from that device buffer.  Across
-// GPUs the 1–2 doubles are combined with an in-place ncclAllReduce on the same stream; the ghost dofs
-// of the search direction are refreshed with grouped ncclSend/ncclRecv of contiguous ranges.
+//   * plain iteration (CG spaces: point Jacobi; DG: element-mass blocks): 3 kernels per iteration, batches of 8
+//     replayed as a CUDA graph on one GPU;
+//   * DG with class tables: CG preconditioned by a Chebyshev polynomial in M^-1 J whose steps are fused with the
+//     operator apply (thermal.cu dg_cheb_step), interval from Lanczos Ritz values (estimate_spectrum);
+//   * all CG scalars (r.z, p.Ap, |r|^2), the tolerance and the iteration count live on the device: every fused vector
+//     kernel ends with warp shuffles -> per-block partials -> "last block sums in fixed order" (deterministic), the
+//     kernels test convergence themselves and later launches of a converged solve return at once; the host reads
+//     the scalars through a mapped pinned mirror (k_mirror), never with a D2H memcpy;
+//   * Newton: dolfinx's incremental criterion with Eisenstat-Walker forcing terms for the linear solves;
+//   * the solver runs on its own stream, ordered against the caller's stream with events (StreamScope);
+//   * across GPUs the 1-2 doubles are all-reduced and the ghost dofs refreshed over NVLink peer memory (peer.cu),
+//     with NCCL (in-place ncclAllReduce, grouped ncclSend/ncclRecv of contiguous ranges) as the fallback.
 #include <math.h>
 #include <stdlib.h>
 

@@ -8,7 +8,12 @@
 //   Jacobian  J(T)[x,v] = same with T -> x in the linear terms and
 //                         dt*0.001*<(4 sigma eps T^3 + htc) x, v>_ds on the boundary.
 //
-// Design: one thread per cell, element tables passed BY VALUE in the kernel parameter block so that
+// Two families of kernels:
+//   (i)  class kernels (dg_class_apply, dg_cheb_step, dg_class_resid, cg_class_apply, cg_class_resid): the mesh's cells
+//        fall into a handful of (shape, neighbourhood) classes found at operator creation; the per-class local matrices
+//        sit in shared memory and a cell reads only its class word, neighbour ids and rows of x (further down);
+//   (ii) the general kernel below, used for meshes with too many classes and for the diagonal:
+// one thread per cell, element tables passed BY VALUE in the kernel parameter block so that
 // every table entry is a constant-bank operand of a fully unrolled DFMA (no shared-memory or LDS
 // traffic for the tables).  Cell geometry is SoA ([component][cell]) so a warp reads 32 consecutive
 // doubles per component.  DG: cell-centric interior facets (each cell visits its d+1 neighbours, no
