@@ -393,13 +393,33 @@ visco_kernel(const VKParams P, const sg_visco_fields f, const VGather G, const l
 // =====================================================================================
 constexpr int WT = 32;  // nodes per warp tile
 
+#ifndef SG_VISCO_CHUNK
+#define SG_VISCO_CHUNK 4
+#endif
+// Terms per shared-memory chunk.  Up to 6 Prony terms the whole history row of a node is staged at once; beyond that
+// (the 12-term end of the sweep of BASELINE config 5) a row of 12 x 9 doubles would cost 60 KB of shared memory per warp
+// and leave 3 warps per SM, so the terms are staged SG_VISCO_CHUNK = 4 at a time (every lane bulk-copies its own row segment): the
+// shared-memory footprint — and with it the number of resident warps — stays below that of the 6-term kernel.
+__host__ __device__ constexpr int fast_chunk_terms(int D, int N) {
+    // measured on B200 (d = 3): 8 and 10 terms are as fast or faster unchunked (80 % / 77 % of the HBM peak against
+    // 71-76 %: the per-lane segment copies cost what the occupancy gains), 12 terms are faster chunked: 58 % unchunked,
+    // 74 % in chunks of 6, 81 % in chunks of 4
+    if (N < 12) return N;
+    const int DD = D * D;
+    // segments must be multiples of 16 bytes and start 16-byte aligned: even number of doubles per segment
+    if ((DD % 2) == 0) return SG_VISCO_CHUNK;
+    return (N % 2 == 0 && SG_VISCO_CHUNK % 2 == 0) ? SG_VISCO_CHUNK : N;
+}
+
 template <int D, int N>
 struct FastCfg {
     static constexpr int DD = D * D;
     static constexpr int ROW = N * DD;             // doubles per node in a history tensor
-    static constexpr bool VEC = (ROW % 2) == 0;    // rows 16-B aligned -> LDS.128 / STS.128
+    static constexpr int CH = fast_chunk_terms(D, N);   // terms staged at a time
+    static constexpr int CROW = CH * DD;           // doubles per node in a staged chunk
+    static constexpr bool VEC = (ROW % 2) == 0 && (CROW % 2) == 0;    // rows 16-B aligned -> LDS.128 / STS.128
     static constexpr int G = VEC ? ((DD % 2) == 0 ? 1 : 2) : 1;  // terms per register group
-    static constexpr uint32_t S_BYTES = WT * ROW * 8;
+    static constexpr uint32_t S_BYTES = WT * CROW * 8;
     static constexpr uint32_t TFP_BYTES = WT * N * 8;
     static constexpr uint32_t SIG_BYTES = WT * DD * 8;
     static constexpr uint32_t SMEM = 2 * S_BYTES + TFP_BYTES + SIG_BYTES + 16;
@@ -408,11 +428,12 @@ struct FastCfg {
 template <int D, int N, bool CORR = false>
 __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const sg_visco_fields f, const long n_tiles) {
     using C = FastCfg<D, N>;
-    constexpr int DD = C::DD, ROW = C::ROW, G = C::G;
+    constexpr int DD = C::DD, ROW = C::ROW, G = C::G, CH = C::CH, CROW = C::CROW;
+    constexpr bool CHUNKED = CH < N;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *buf_s = reinterpret_cast<double *>(smem_raw);
-    double *buf_k = buf_s + WT * ROW;
-    double *buf_t = buf_k + WT * ROW;
+    double *buf_k = buf_s + WT * CROW;
+    double *buf_t = buf_k + WT * CROW;
     double *buf_o = buf_t + WT * N;
     uint64_t *bar = reinterpret_cast<uint64_t *>(buf_o + WT * DD);
     const int lane = threadIdx.x;
@@ -426,13 +447,23 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
 
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long node0 = tile * WT;
-        if (lane == 0) {
-            sgptx::mbar_expect_tx(bar, 2u * C::S_BYTES + C::TFP_BYTES);
-            sgptx::bulk_g2s(buf_s, f.s_tilde + node0 * ROW, C::S_BYTES, bar);
-            sgptx::bulk_g2s(buf_k, f.sigma_tilde + node0 * ROW, C::S_BYTES, bar);
-            sgptx::bulk_g2s(buf_t, f.Tf_partial + node0 * N, C::TFP_BYTES, bar);
-        }
         const long node = node0 + lane;
+        if constexpr (!CHUNKED) {
+            if (lane == 0) {
+                sgptx::mbar_expect_tx(bar, 2u * C::S_BYTES + C::TFP_BYTES);
+                sgptx::bulk_g2s(buf_s, f.s_tilde + node0 * ROW, C::S_BYTES, bar);
+                sgptx::bulk_g2s(buf_k, f.sigma_tilde + node0 * ROW, C::S_BYTES, bar);
+                sgptx::bulk_g2s(buf_t, f.Tf_partial + node0 * N, C::TFP_BYTES, bar);
+            }
+        } else {   // first chunk of terms: every lane copies the segment of its own row
+            if (lane == 0) {
+                sgptx::mbar_expect_tx(bar, 2u * C::S_BYTES + C::TFP_BYTES);
+                sgptx::bulk_g2s(buf_t, f.Tf_partial + node0 * N, C::TFP_BYTES, bar);
+            }
+            __syncwarp();
+            sgptx::bulk_g2s(buf_s + lane * CROW, f.s_tilde + node * ROW, CROW * 8u, bar);
+            sgptx::bulk_g2s(buf_k + lane * CROW, f.sigma_tilde + node * ROW, CROW * 8u, bar);
+        }
         const double Tc = f.T_cur[node], Tp = f.T_prev[node];
         double phi, xi, Tf_old = 0.0, phi_old = 0.0;
         if constexpr (CORR) {
@@ -477,63 +508,86 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
         for (int a = 1; a < D; ++a) tr = tr + tot_d;
         const double dev_d = tot_d - P.inv_d * tr, dev_o = tot_o;
 
-        // ---- Prony recursions (VM:176-228), G terms at a time out of registers ----
+        // ---- Prony recursions (VM:176-228), G terms at a time out of registers, CH terms per staged chunk ----
         double acc[DD];
-        double *rs = buf_s + lane * ROW, *rk = buf_k + lane * ROW;
+        double *rs = buf_s + lane * CROW, *rk = buf_k + lane * CROW;
 #pragma unroll
-        for (int n0 = 0; n0 < N; n0 += G) {
-            double tg[G], tk[G], dsd[G], dso[G], dkd[G];
+        for (int c0 = 0; c0 < N; c0 += CH) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int len = (N - c0 < CH) ? N - c0 : CH;      // compile-time after unrolling
+            if (CHUNKED && c0 > 0) {                          // stage the next chunk (the previous one has been written back)
+                if (lane == 0) sgptx::mbar_expect_tx(bar, 2u * (uint32_t)(WT * len * DD * 8));
+                __syncwarp();
+                sgptx::bulk_g2s(buf_s + lane * CROW, f.s_tilde + node * ROW + c0 * DD, (uint32_t)(len * DD * 8), bar);
+                sgptx::bulk_g2s(buf_k + lane * CROW, f.sigma_tilde + node * ROW + c0 * DD, (uint32_t)(len * DD * 8), bar);
+                sgptx::mbar_wait(bar, parity);
+                parity ^= 1u;
+            }
 #pragma unroll
-            for (int u = 0; u < G; ++u) {
-                const int n = n0 + u;
-                if constexpr (CORR) {
-                    double fg, fk;
-                    decay_fac(xi, P.lg[n], tg[u], fg);
-                    decay_fac(xi, P.lk[n], tk[u], fk);
-                    dsd[u] = (P.g2[n] * dev_d) * fg;
-                    dso[u] = (P.g2[n] * dev_o) * fg;
-                    dkd[u] = (P.k[n] * tr) * fk;
+            for (int n0 = c0; n0 < c0 + len; n0 += G) {
+                double tg[G], tk[G], dsd[G], dso[G], dkd[G];
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const int n = n0 + u;
+                    if constexpr (CORR) {
+                        double fg, fk;
+                        decay_fac(xi, P.lg[n], tg[u], fg);
+                        decay_fac(xi, P.lk[n], tk[u], fk);
+                        dsd[u] = (P.g2[n] * dev_d) * fg;
+                        dso[u] = (P.g2[n] * dev_o) * fg;
+                        dkd[u] = (P.k[n] * tr) * fk;
+                    } else {
+                        tg[u] = taylor3(xi, P.lg[n]);
+                        tk[u] = taylor3(xi, P.lk[n]);
+                        const double one_g = 1.0 - tg[u], one_k = 1.0 - tk[u];
+                        dsd[u] = ((P.g2[n] * dev_d) / xi) * P.lg[n] * one_g;
+                        dso[u] = ((P.g2[n] * dev_o) / xi) * P.lg[n] * one_g;
+                        dkd[u] = ((P.k[n] * tr) / xi) * P.lk[n] * one_k;
+                    }
+                }
+                auto item = [&](double &s, double &k, const int e) {  // e: element within the group
+                    const int u = e / DD, c = e % DD;
+                    const bool diag = (c % (D + 1)) == 0;
+                    s = s * tg[u];
+                    k = k * tk[u];
+                    const double sp = (diag ? dsd[u] : dso[u]) + s, kp = (diag ? dkd[u] : 0.0) + k;
+                    const double pn = sp + kp;
+                    acc[c] = (n0 + u == 0) ? pn : acc[c] + pn;
+                    if constexpr (CORR) {   // the history is the partial stress itself
+                        s = sp;
+                        k = kp;
+                    }
+                };
+                const int off = (n0 - c0) * DD;               // position inside the staged chunk
+                if constexpr (C::VEC) {
+                    double2 *vs = reinterpret_cast<double2 *>(rs + off);
+                    double2 *vk = reinterpret_cast<double2 *>(rk + off);
+#pragma unroll
+                    for (int j = 0; j < G * DD / 2; ++j) {
+                        double2 s = vs[j], k = vk[j];
+                        item(s.x, k.x, 2 * j);
+                        item(s.y, k.y, 2 * j + 1);
+                        vs[j] = s;
+                        vk[j] = k;
+                    }
                 } else {
-                    tg[u] = taylor3(xi, P.lg[n]);
-                    tk[u] = taylor3(xi, P.lk[n]);
-                    const double one_g = 1.0 - tg[u], one_k = 1.0 - tk[u];
-                    dsd[u] = ((P.g2[n] * dev_d) / xi) * P.lg[n] * one_g;
-                    dso[u] = ((P.g2[n] * dev_o) / xi) * P.lg[n] * one_g;
-                    dkd[u] = ((P.k[n] * tr) / xi) * P.lk[n] * one_k;
+#pragma unroll
+                    for (int e = 0; e < G * DD; ++e) {
+                        double s = rs[off + e], k = rk[off + e];
+                        item(s, k, e);
+                        rs[off + e] = s;
+                        rk[off + e] = k;
+                    }
                 }
             }
-            auto item = [&](double &s, double &k, const int e) {  // e: element within the group
-                const int u = e / DD, c = e % DD;
-                const bool diag = (c % (D + 1)) == 0;
-                s = s * tg[u];
-                k = k * tk[u];
-                const double sp = (diag ? dsd[u] : dso[u]) + s, kp = (diag ? dkd[u] : 0.0) + k;
-                const double pn = sp + kp;
-                acc[c] = (n0 + u == 0) ? pn : acc[c] + pn;
-                if constexpr (CORR) {   // the history is the partial stress itself
-                    s = sp;
-                    k = kp;
-                }
-            };
-            if constexpr (C::VEC) {
-                double2 *vs = reinterpret_cast<double2 *>(rs + n0 * DD);
-                double2 *vk = reinterpret_cast<double2 *>(rk + n0 * DD);
-#pragma unroll
-                for (int j = 0; j < G * DD / 2; ++j) {
-                    double2 s = vs[j], k = vk[j];
-                    item(s.x, k.x, 2 * j);
-                    item(s.y, k.y, 2 * j + 1);
-                    vs[j] = s;
-                    vk[j] = k;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < G * DD; ++e) {
-                    double s = rs[n0 * DD + e], k = rk[n0 * DD + e];
-                    item(s, k, e);
-                    rs[n0 * DD + e] = s;
-                    rk[n0 * DD + e] = k;
-                }
+            if constexpr (CHUNKED) {                          // write this chunk back before its buffer is reused
+                sgptx::fence_async_smem();
+                sgptx::bulk_s2g(f.s_tilde + node * ROW + c0 * DD, buf_s + lane * CROW, (uint32_t)(len * DD * 8));
+                sgptx::bulk_s2g(f.sigma_tilde + node * ROW + c0 * DD, buf_k + lane * CROW, (uint32_t)(len * DD * 8));
+                sgptx::bulk_commit();
+                sgptx::bulk_wait_read0();
+                __syncwarp();
             }
         }
 #pragma unroll
@@ -543,8 +597,10 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
         sgptx::fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            sgptx::bulk_s2g(f.s_tilde + node0 * ROW, buf_s, C::S_BYTES);
-            sgptx::bulk_s2g(f.sigma_tilde + node0 * ROW, buf_k, C::S_BYTES);
+            if constexpr (!CHUNKED) {
+                sgptx::bulk_s2g(f.s_tilde + node0 * ROW, buf_s, C::S_BYTES);
+                sgptx::bulk_s2g(f.sigma_tilde + node0 * ROW, buf_k, C::S_BYTES);
+            }
             sgptx::bulk_s2g(f.Tf_partial + node0 * N, buf_t, C::TFP_BYTES);
             sgptx::bulk_s2g(f.sigma + node0 * DD, buf_o, C::SIG_BYTES);
             sgptx::bulk_commit();

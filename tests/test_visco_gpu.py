@@ -82,6 +82,24 @@ def check_against_oracle(p, T_cur, T_prev, Tfp_prev, s_prev, k_prev, g, full=Tru
 
 
 @pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("N", [3, 4, 6, 8, 10, 12])
+def test_fast_path_all_term_counts(sg_ctx, d, N):
+    """The persistent TMA kernel (minimal materialisation, full tiles) for every term count of the Prony sweep; from 8
+    terms on the history rows are staged 6 terms at a time (per-lane bulk copies).  Bit-exact given the GPU's exp."""
+    n = 32 * 300
+    p = vo.ViscoParams(dim=d, dt=0.1, **vo.prony_tables(N))
+    T_cur, T_prev, Tfp, s, k = random_visco_state(n, d, N, seed=7 * N + d)
+    plan = make_plan(sg_ctx, p)
+    t = gpu_state(p, T_cur, T_prev, Tfp, s, k, materialize=False)
+    plan.update(n, t)
+    torch.cuda.synchronize()
+    g = {name: v.cpu().numpy() for name, v in t.items()}
+    g["xi"] = t["xi"].cpu().numpy()
+    # xi on the GPU comes from the GPU's own phi / phi_next: take it as given, everything downstream must be bit-exact
+    check_against_oracle(p, T_cur, T_prev, Tfp, s, k, g, full=False)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
 @pytest.mark.parametrize("N", [3, 6, 12])
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 4097])
 def test_fused_update_matches_oracle(sg_ctx, d, N, n):

@@ -41,7 +41,7 @@ def peak_gbs():
         return 6650.0, "fallback"
 
 
-def run(ctx, n, d, N, iters, full):
+def run(ctx, n, d, N, iters, full, corrected=False):
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(1234)
     dd = d * d
@@ -60,7 +60,7 @@ def run(ctx, n, d, N, iters, full):
         for name in ("ds_partial", "dsigma_partial", "s_partial", "sigma_partial"):
             t[name] = torch.zeros(n * N * dd, dtype=torch.float64, device=dev)
     plan = _lib.ViscoPlan(ctx, dim=d, dt=0.1, H=627.8e3, Rg=8.314, Tb=869.0, alpha_solid=9.10e-6,
-                          alpha_liquid=25.10e-6, **tables(N))
+                          alpha_liquid=25.10e-6, mode=_lib.VISCO_CORRECTED if corrected else _lib.VISCO_REFERENCE, **tables(N))
     bpn = plan.bytes_per_node(t)
     for _ in range(3):
         plan.update(n, t)
@@ -75,7 +75,7 @@ def run(ctx, n, d, N, iters, full):
     med = ms[len(ms) // 2]
     gbs = n * bpn / (med * 1e-3) / 1e9
     pk, how = peak_gbs()
-    return dict(kernel="visco_fused", n_nodes=n, dim=d, terms=N, full_materialisation=full, bytes_per_node=bpn,
+    return dict(kernel="visco_fused" + ("_corrected_scheme" if corrected else ""), n_nodes=n, dim=d, terms=N, full_materialisation=full, bytes_per_node=bpn,
                 ms_median=round(med, 4), ms_min=round(ms[0], 4), node_updates_per_s=n / (med * 1e-3),
                 achieved_GBs=round(gbs, 1), frac_of_peak=round(gbs / pk, 3), peak=f"{pk} GB/s {how}",
                 frac_of_8TBs=round(gbs / 8000, 3))
@@ -98,6 +98,7 @@ def main():
         print(json.dumps(run(ctx, 30_710_797, 2, 6, a.iters, False)), flush=True)
         print(json.dumps(run(ctx, 30_710_797, 1, 6, a.iters, False)), flush=True)
         print(json.dumps(run(ctx, a.n // 3, 3, 6, a.iters, True)), flush=True)
+        print(json.dumps(run(ctx, a.n, 3, 6, a.iters, False, corrected=True)), flush=True)
     else:
         print(json.dumps(run(ctx, a.n, a.d, a.terms, a.iters, a.full)), flush=True)
 
