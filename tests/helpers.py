@@ -91,3 +91,15 @@ def load_main_py_history():
     arr = lambda v: np.array([float("nan") if q == "nan" else float.fromhex(q) for q in v])
     steps = [{k: (arr(v) if isinstance(v, list) else v) for k, v in s.items()} for s in data["steps"]]
     return dict(dt=data["dt"], T_0=data["T_0"], points=arr(data["points"]), winner_dof=np.array(data["winner_dof"]), steps=steps)
+
+
+def load_thermal_kat_p2():
+    """tests/golden/thermal_kat_p2.json: hand-evaluated CG2 residual / Jacobian-vector product on small perturbed 2-D and
+    3-D meshes (generator: tests/golden/make_thermal_kat_p2.py); includes the P2 dofmap it assumed."""
+    with open(os.path.join(GOLDEN, "thermal_kat_p2.json")) as fh:
+        data = json.load(fh)
+    arr = lambda v: np.array(unhex(v))
+    cases = [dict(dim=c["dim"], family=c["family"], degree=c["degree"], x=np.array([unhex(p) for p in c["x"]]),
+                  cells=np.array(c["cells"]), dofmap=np.array(c["dofmap"]), T=arr(c["T"]), T_prev=arr(c["T_prev"]),
+                  v=arr(c["v"]), residual=arr(c["residual"]), jac_x=arr(c["jac_x"])) for c in data["cases"]]
+    return dict(dt=data["dt"], cases=cases)

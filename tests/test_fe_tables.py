@@ -261,3 +261,21 @@ def test_oracle_against_the_hand_evaluated_2d_3d_vectors():
         Jx = orc.jacobian(c["T"]) @ c["v"]
         assert np.max(np.abs(F - c["residual"])) <= 1e-12 * np.max(np.abs(c["residual"])), (c["dim"], c["family"])
         assert np.max(np.abs(Jx - c["jac_x"])) <= 1e-12 * np.max(np.abs(c["jac_x"])), (c["dim"], c["family"])
+
+
+def test_oracle_and_p2_numbering_against_the_hand_evaluated_cg2_vectors():
+    """CG2 (the element of BASELINE configs 2 and 4): the oracle and the product's P2 dof numbering against
+    tests/golden/thermal_kat_p2.json (plain-Python P2 basis, Duffy-Gauss integration, TVP:293-306).  1e-12 relative."""
+    from helpers import load_thermal_kat_p2
+    from fem_glass_tempering_b200.mesh import Mesh
+    kat = load_thermal_kat_p2()
+    assert [c["dim"] for c in kat["cases"]] == [2, 3]
+    for c in kat["cases"]:
+        m = Mesh(c["x"], c["cells"])
+        space = fe.ScalarSpace(m, "CG", 2)
+        assert np.array_equal(space.dofmap, c["dofmap"])        # vertices, then edges sorted by (min, max) vertex
+        orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "CG", 2, MAIN_PARAMS, kat["dt"])
+        F = orc.residual(c["T"], c["T_prev"])
+        Jx = orc.jacobian(c["T"]) @ c["v"]
+        assert np.max(np.abs(F - c["residual"])) <= 1e-12 * np.max(np.abs(c["residual"])), c["dim"]
+        assert np.max(np.abs(Jx - c["jac_x"])) <= 1e-12 * np.max(np.abs(c["jac_x"])), c["dim"]

@@ -97,6 +97,23 @@ def test_hand_evaluated_vectors_on_perturbed_2d_3d_meshes(sg_ctx, use_classes):
         assert np.max(np.abs(Jx - c["jac_x"])) <= 1e-12 * np.max(np.abs(c["jac_x"])), (c["dim"], c["family"])
 
 
+@pytest.mark.parametrize("use_classes", [True, False], ids=["class_tables", "per_cell_geometry"])
+def test_hand_evaluated_cg2_vectors(sg_ctx, use_classes):
+    """CUDA residual / Jacobian apply for CG2 (BASELINE configs 2 and 4) against tests/golden/thermal_kat_p2.json
+    (plain-Python P2 basis and Duffy-Gauss integration on perturbed meshes): 1e-12 relative."""
+    from helpers import load_thermal_kat_p2
+    from fem_glass_tempering_b200.mesh import Mesh
+    kat = load_thermal_kat_p2()
+    for c in kat["cases"]:
+        space = fe.ScalarSpace(Mesh(c["x"], c["cells"]), "CG", 2)
+        op = ThermalOperator(sg_ctx, space, MAIN_PARAMS, kat["dt"], use_classes=use_classes)
+        out = torch.empty(space.n_nodes, dtype=torch.float64, device="cuda:0")
+        F = op.residual(dev(c["T"]), dev(c["T_prev"]), out).cpu().numpy()
+        assert np.max(np.abs(F - c["residual"])) <= 1e-12 * np.max(np.abs(c["residual"])), c["dim"]
+        Jx = op.jac_apply(dev(c["T"]), dev(c["v"]), out).cpu().numpy()
+        assert np.max(np.abs(Jx - c["jac_x"])) <= 1e-12 * np.max(np.abs(c["jac_x"])), c["dim"]
+
+
 @pytest.mark.parametrize("dim,family,degree", [(1, "DG", 1), (2, "CG", 2), (3, "DG", 1), (3, "CG", 2), (2, "DG", 2)])
 def test_pcg_solves_the_linear_system(sg_ctx, dim, family, degree):
     import scipy.sparse.linalg as spla
