@@ -373,7 +373,11 @@ def run_gpu(args):
     peak, peak_how = measured_peak()
     cls = op.class_info()
     fam = cfg["T"]["element"]
-    if cls["active"]:
+    stc = op.stencil_info()
+    if stc["active"]:
+        kname = (f"thermal k_stencil_apply (CG Jacobian apply in gather form: 16-bit row class + the class's (offset, coefficient) "
+                 f"list in shared memory, plain stores, fused x.Ax reduction; {stc['classes']} row classes, {stc['entries']} entries)")
+    elif cls["active"]:
         kname = (f"thermal {'dg' if fam == 'DG' else 'cg'}_class_apply (matrix-free Jacobian apply from local-matrix class tables "
                  f"in shared memory, fused x.Ax reduction; {cls['self']} cell + {cls['facet']} facet classes)")
     else:
@@ -381,6 +385,10 @@ def run_gpu(args):
     apply_bytes = op.apply_bytes()
     apply_ms = ms_apply.value / max(1, n_apply.value)
     apply_gbs = apply_bytes / (apply_ms * 1e-3) / 1e9 if n_apply.value else None
+    # SURVEY 8(d)'s layout-independent figure for a CG apply: read x, write y, per cell the symmetric geometry tensor + |detJ|
+    # and the dofmap.  Reported next to the bytes of the layout actually in use (which the class/stencil tables shrink).
+    n_ld_T = (dim + 1) if cfg["T"]["degree"] == 1 else (dim + 1) * (dim + 2) // 2
+    survey_bytes = (16 * nT + (op.cell_hi - op.cell_lo) * (8 * (dim * (dim + 1) // 2 + 1) + 4 * n_ld_T)) if fam == "CG" else None
     visco_bytes = prob.material_model.plan.bytes_per_node(prob._visco_tensors()) * nS
     visco_gbs = visco_bytes / (ms_visco * 1e-3) / 1e9
     line = {
@@ -398,7 +406,7 @@ def run_gpu(args):
                                   else "NCCL send/recv + all-reduce")),
                    "cache": "state per GPU (>17 GB) is far larger than the 126 MB L2; no L2 flush needed",
                    "newton_its_per_step": newton_its / args.steps, "pcg_its_per_step": lin_its / args.steps,
-                   "setup_s": round(t_setup, 1), "local_matrix_classes": cls,
+                   "setup_s": round(t_setup, 1), "local_matrix_classes": cls, "row_stencil_classes": stc,
                    "kernel_timing": ("CUDA events inside the timed region" if prof_in_timed_region else
                                      "separate profiled pass after the timed region (the timed region replays CUDA graphs)"),
                    "preconditioner": (f"Chebyshev degree {op.chebyshev_info()['degree']} in M^-1 J on "
@@ -417,7 +425,10 @@ def run_gpu(args):
                            "bound": "hbm", "achieved": apply_gbs, "peak": peak, "unit": "GB/s",
                            "frac": (apply_gbs / peak) if apply_gbs else None, "traffic": None, "peak_source": peak_how,
                            "algorithmic_bytes_per_launch": int(apply_bytes), "launches_timed": int(n_apply.value),
-                           "avg_launch_ms": apply_ms, "share_of_step": ms_apply.value / ms_total},
+                           "avg_launch_ms": apply_ms, "share_of_step": ms_apply.value / ms_total,
+                           **({"survey_8d_bytes_per_launch": int(survey_bytes),
+                               "frac_on_survey_8d_bytes": survey_bytes / (apply_ms * 1e-3) / 1e9 / peak}
+                              if survey_bytes and n_apply.value else {})},
         "roofline_visco": {"kernel": "visco_fast_kernel (fused viscoelastic update)", "bound": "hbm",
                            "achieved": visco_gbs, "peak": peak, "unit": "GB/s", "frac": visco_gbs / peak,
                            "algorithmic_bytes_per_launch": int(visco_bytes), "avg_launch_ms": ms_visco,

@@ -41,6 +41,7 @@ def bind(L) -> None:
     L.sg_thermal_jac_apply.argtypes = [vp, vp, vp, vp, vp]
     L.sg_thermal_jac_diag.argtypes = [vp, vp, vp, vp]
     L.sg_thermal_class_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.sg_thermal_stencil_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.sg_thermal_profile.argtypes = [vp, C.c_int32, C.c_int32]
     L.sg_thermal_profile_read.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.sg_thermal_profile_read_kind.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]

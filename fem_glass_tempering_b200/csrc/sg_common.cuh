@@ -85,6 +85,16 @@ int sg_peer_allreduce(SgPeer *p, double *vals, int count, cudaStream_t st);
 // rep_out[k] = index of one member of class k; both are cudaMalloc'ed here and freed by the caller.
 int sg_classify_u64(const uint64_t *keys_dev, int64_t n, int32_t **cls_out, int32_t *n_cls, int32_t **rep_out);
 
+// stencil.cu: row-stencil classes of a CG operator (gather form of the Jacobian apply).  *out stays NULL (and SG_OK is
+// returned) when the mesh has no small set of repeating rows.  dot2[0] = x.y over the rows [own_lo, own_hi), dot2[1] = 0.
+struct SgStencil;
+int sg_stencil_build(sg_ctx *ctx, const int32_t *dofmap, int64_t n_cells, int n_ld, int64_t cell_lo, int64_t cell_hi,
+                     const uint16_t *cls16, const double *tab, int S, int64_t n_rows, SgStencil **out);
+int sg_stencil_apply(const SgStencil *s, const double *x, double *y, int64_t own_lo, int64_t own_hi, SgRed red, double *dot2,
+                     const int *skip, cudaStream_t st);
+void sg_stencil_destroy(SgStencil *s);
+void sg_stencil_info(const SgStencil *s, int32_t *n_classes, int32_t *n_entries, int32_t *max_nnz);
+
 #define SG_CHECK_CUDA(expr)                                                                  \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \

@@ -1032,6 +1032,48 @@ __global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_cheb_step(const ClsDev cd
     if (LAST) sg_grid_reduce<1>(dsum, red, dot_out, cd.accumulate != 0);
 }
 
+// Exterior facets of a CG space from their linearised matrices: y += B_F x_F (RED.ADD), dsum += x_F . (B_F x_F) over the
+// facets of the cells [dot_lo, dot_hi).
+template <int D, int P>
+__device__ __forceinline__ void cg_bfacets(const ClsDev &cd, const double *__restrict__ x, double *__restrict__ y, double &dsum) {
+    constexpr int NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
+    const long nc = cd.n_cells;
+    for (long b = (long)blockIdx.x * CB + threadIdx.x; b < cd.n_bf; b += (long)gridDim.x * CB) {
+        const long c = cd.bf_cell[b];
+        if (c < cd.cell_lo || c >= cd.cell_hi) continue;
+        const int f = cd.bf_facet[b];
+        long dof[NFD];
+        double xk[NFD], yk[NFD], B[NFDP];
+#pragma unroll
+        for (int k = 0; k < NFD; ++k) {
+            int fd = 0;
+#pragma unroll
+            for (int ff = 0; ff < D + 1; ++ff)
+                if (ff == f) fd = facet_dof(D, P, ff, k);
+            dof[k] = cd.dofmap[(long)fd * nc + c];
+            xk[k] = x[dof[k]];
+            yk[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < NFDP; ++k) B[k] = cd.bmat[b * NFDP + k];
+        int m = 0;
+#pragma unroll
+        for (int k = 0; k < NFD; ++k)
+#pragma unroll
+            for (int l = k; l < NFD; ++l) {
+                yk[k] += B[m] * xk[l];
+                if (l != k) yk[l] += B[m] * xk[k];
+                ++m;
+            }
+        const bool counted = c >= cd.dot_lo && c < cd.dot_hi;
+#pragma unroll
+        for (int k = 0; k < NFD; ++k) {
+            atomicAdd(&y[dof[k]], yk[k]);
+            if (counted) dsum += xk[k] * yk[k];
+        }
+    }
+}
+
 // CG fast apply: gather through the dofmap, class matrix from shared memory, scatter with RED.ADD.F64; then, in the
 // same launch, the exterior facets from their linearised matrices (both parts only add into y, no ordering needed).
 // x.y is reduced cell-wise as x_K . (A_K x_K) over the cells [dot_lo, dot_hi) (each global cell on one rank) plus
@@ -1066,44 +1108,35 @@ __global__ void __launch_bounds__(CB, 4) cg_class_apply(const ClsDev cd, const d
         }
         if (c >= cd.dot_lo && c < cd.dot_hi) dsum[0] += d;
     }
-    if (cd.bmat) {
-        constexpr int NFD = nfd_of(D, P), NFDP = NFD * (NFD + 1) / 2;
-        for (long b = (long)blockIdx.x * CB + threadIdx.x; b < cd.n_bf; b += (long)gridDim.x * CB) {
-            const long c = cd.bf_cell[b];
-            if (c < cd.cell_lo || c >= cd.cell_hi) continue;
-            const int f = cd.bf_facet[b];
-            long dof[NFD];
-            double xk[NFD], yk[NFD], B[NFDP];
-#pragma unroll
-            for (int k = 0; k < NFD; ++k) {
-                int fd = 0;
-#pragma unroll
-                for (int ff = 0; ff < D + 1; ++ff)
-                    if (ff == f) fd = facet_dof(D, P, ff, k);
-                dof[k] = cd.dofmap[(long)fd * nc + c];
-                xk[k] = x[dof[k]];
-                yk[k] = 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < NFDP; ++k) B[k] = cd.bmat[b * NFDP + k];
-            int m = 0;
-#pragma unroll
-            for (int k = 0; k < NFD; ++k)
-#pragma unroll
-                for (int l = k; l < NFD; ++l) {
-                    yk[k] += B[m] * xk[l];
-                    if (l != k) yk[l] += B[m] * xk[k];
-                    ++m;
-                }
-            const bool counted = c >= cd.dot_lo && c < cd.dot_hi;
-#pragma unroll
-            for (int k = 0; k < NFD; ++k) {
-                atomicAdd(&y[dof[k]], yk[k]);
-                if (counted) dsum[1] += xk[k] * yk[k];
-            }
-        }
-    }
+    if (cd.bmat) cg_bfacets<D, P>(cd, x, y, dsum[1]);
     sg_grid_reduce<2>(dsum, red, dot_out);
+}
+
+// The exterior facets on their own, after the row-stencil apply (stencil.cu) has stored the cell part of y.
+template <int D, int P>
+__global__ void __launch_bounds__(CB) cg_bfacet_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y, SgRed red,
+                                                      double *dot_out, const int *skip) {
+    if (skip && *skip) return;
+    double dsum[1] = {0.0};
+    cg_bfacets<D, P>(cd, x, y, dsum[0]);
+    sg_grid_reduce<1>(dsum, red, dot_out);
+}
+
+// set-up check of the row-stencil tables: x_i = hash(i) in [-1, 1); out[0] = max |a|, out[1] = max |a - b| (as bit patterns)
+__global__ void k_hash_vec(long n, double *x) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long h = (unsigned long long)i * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    x[i] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+__global__ void k_max_diff(long n, const double *__restrict__ a, const double *__restrict__ b, unsigned long long *out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(fabs(a[i])));
+    atomicMax(&out[1], (unsigned long long)__double_as_longlong(fabs(a[i] - b[i])));
 }
 
 }  // namespace
@@ -1130,6 +1163,7 @@ struct sg_thermal_op {
     int y_is_zero;         // set by sg_thermal_apply_dot: the caller guarantees y == 0 on entry (CG scatter needs no memset)
     int32_t *nbr_ext;      // DG P1: neighbour ids with exterior facets encoded (see ClsDev::bmat)
     double *bmat;
+    SgStencil *stencil;    // CG: row-stencil classes (stencil.cu); nullptr: cell-centric cg_class_apply
     int (*linearize)(const sg_thermal_op *, const double *T_lin, cudaStream_t st);
     int (*cheb_step)(const sg_thermal_op *, const SgChebStep &, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
     // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
@@ -1204,10 +1238,11 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
     const long ncell = dv.cell_hi - dv.cell_lo;
     const unsigned gc = (unsigned)((ncell + TB - 1) / TB), gb = capped_grid(dv.n_bf, TB);
     const bool fast = mode == MODE_APPLY && op->cls.tab != nullptr;
-    if (!DG && !(mode == MODE_APPLY && op->y_is_zero)) SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
+    if (!DG && !(mode == MODE_APPLY && (op->y_is_zero || (fast && op->stencil)))) SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
     if (fast) {
         // the class kernels always reduce x.y; without a consumer it lands in a scratch slot
         double *dst = dot2 ? dot2 : red.partials + 2 * SG_MAX_BLOCKS;
+        {
         ProfScope ps(op, mode, st);
         const bool wide = (((uintptr_t)x | (uintptr_t)y) & 31) == 0;
         if constexpr (DG) {
@@ -1220,10 +1255,22 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
                 const ClsDev cdv = part_view(op, op->part, &grid);
                 k<<<grid, CB, op->cls_smem, st>>>(cdv, x, y, red, dst, skip);
             }
+        } else if (op->stencil) {
+            // gather form: plain stores of every row, no zeroing of y needed
+            const int rc = sg_stencil_apply(op->stencil, x, y, op->d.own_lo, op->d.own_hi, red, dst, skip, st);
+            if (rc) return rc;
         } else
             cg_class_apply<D, P><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
         SG_CHECK_CUDA(cudaGetLastError());
-        sg_count_launch();
+        if (DG || !op->stencil) sg_count_launch();
+        }
+        if constexpr (!DG) {
+            if (op->stencil && op->bmat && dv.n_bf > 0) {
+                cg_bfacet_apply<D, P><<<capped_grid(dv.n_bf, CB), CB, 0, st>>>(op->cls, x, y, red, dst + 1, skip);
+                SG_CHECK_CUDA(cudaGetLastError());
+                sg_count_launch();
+            }
+        }
     } else if (mode == MODE_RESID && op->cls.tab != nullptr && !(op->d.flags & SG_THERMAL_GENERAL_RESIDUAL)) {
         ResidDev rd;
         rd.xprev = xprev;
@@ -1338,6 +1385,68 @@ struct DevBuf {  // scoped cudaMalloc
     template <class T>
     T *as() { return static_cast<T *>(p); }
 };
+
+int ensure_own_red(sg_thermal_op *op) {
+    if (!op->own_red.partials) {
+        SG_CHECK_CUDA(cudaMalloc(&op->own_red.partials, sizeof(double) * (2 * SG_MAX_BLOCKS + 2)));
+        SG_CHECK_CUDA(cudaMalloc(&op->own_red.counter, sizeof(unsigned)));
+        SG_CHECK_CUDA(cudaMemset(op->own_red.counter, 0, sizeof(unsigned)));
+    }
+    return SG_OK;
+}
+
+// CG: try the row-stencil form of the apply (stencil.cu) and keep it only if it reproduces the cell part of
+// cg_class_apply on a pseudo-random vector (guards the 64-bit row hash and the table construction).
+template <int D, int P>
+int build_stencil_t(sg_thermal_op *op) {
+    constexpr int NLD = nld_of(D, P);
+    const OpDev &dv = op->dev;
+    SgStencil *st = nullptr;
+    int rc = sg_stencil_build(op->ctx, dv.dofmap, dv.n_cells, NLD, dv.cell_lo, dv.cell_hi, op->cls.cls16, op->cls_tab, op->cls.S,
+                              dv.n_dofs, &st);
+    if (rc || !st) return rc;
+    if ((rc = ensure_own_red(op))) {
+        sg_stencil_destroy(st);
+        return rc;
+    }
+    const long n = dv.n_dofs;
+    DevBuf xb, ya, yb, mx;
+    cudaError_t e = cudaMalloc(&xb.p, sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&ya.p, sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&yb.p, sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&mx.p, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ya.p, 0, sizeof(double) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemset(mx.p, 0, 2 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        sg_stencil_destroy(st);
+        sg_set_error("build_stencil: %s", cudaGetErrorString(e));
+        return SG_E_CUDA;
+    }
+    const unsigned g = (unsigned)((n + 255) / 256);
+    k_hash_vec<<<g, 256>>>(n, xb.as<double>());
+    ClsDev cells_only = op->cls;
+    cells_only.bmat = nullptr;
+    double *scratch = op->own_red.partials + 2 * SG_MAX_BLOCKS;
+    cg_class_apply<D, P><<<op->cls_grid, CB, op->cls_smem>>>(cells_only, xb.as<double>(), ya.as<double>(), op->own_red, scratch, nullptr);
+    rc = sg_stencil_apply(st, xb.as<double>(), yb.as<double>(), 0, n, op->own_red, scratch, nullptr, 0);
+    k_max_diff<<<g, 256>>>(n, ya.as<double>(), yb.as<double>(), mx.as<unsigned long long>());
+    unsigned long long bits[2] = {0, 0};
+    e = cudaMemcpy(bits, mx.p, sizeof(bits), cudaMemcpyDeviceToHost);
+    if (rc || e != cudaSuccess) {
+        sg_stencil_destroy(st);
+        if (!rc) sg_set_error("build_stencil: %s", cudaGetErrorString(e));
+        return rc ? rc : SG_E_CUDA;
+    }
+    double ymax, dmax;
+    memcpy(&ymax, &bits[0], 8);
+    memcpy(&dmax, &bits[1], 8);
+    if (!(dmax <= 1e-12 * ymax)) {   // never seen; keeps the cell-centric kernel rather than a wrong operator
+        sg_stencil_destroy(st);
+        return SG_OK;
+    }
+    op->stencil = st;
+    return SG_OK;
+}
 
 // Find the local-matrix classes of this mesh and build the tables (see the comment above key_mix).
 // Leaves op->cls.tab == nullptr (general kernel stays in use) when the mesh has too many classes.
@@ -1516,6 +1625,12 @@ int build_classes_t(sg_thermal_op *op) {
         cd.bmat = op->bmat;
     }
     cd.tab = op->cls_tab;  // set last: marks the fast path as available
+    if constexpr (!DG) {
+        if (!(op->d.flags & SG_THERMAL_NO_STENCIL)) {
+            const int rs = build_stencil_t<D, P>(op);
+            if (rs) return rs;
+        }
+    }
     return SG_OK;
 }
 
@@ -1726,6 +1841,7 @@ int sg_thermal_op_destroy(sg_thermal_op *op) {
     if (op->cls_words) cudaFree(op->cls_words);
     if (op->nbr_ext) cudaFree(op->nbr_ext);
     if (op->bmat) cudaFree(op->bmat);
+    sg_stencil_destroy(op->stencil);
     if (op->own_red.partials) cudaFree(op->own_red.partials);
     if (op->own_red.counter) cudaFree(op->own_red.counter);
     for (int i = 0; i < 2 * op->prof_cap; ++i) cudaEventDestroy(op->prof_ev[i]);
@@ -1745,13 +1861,10 @@ int sg_thermal_residual(sg_thermal_op *op, const double *T, const double *T_prev
 
 int sg_thermal_jac_apply(sg_thermal_op *op, const double *T_lin, const double *x, double *y, void *stream) {
     SG_REQUIRE(op && T_lin && x && y, "sg_thermal_jac_apply: NULL argument");
-    if (op->cls.tab && !op->own_red.partials) {
-        // the class kernels reduce x.y as they go and need scratch for it even when nobody reads the result
-        SG_CHECK_CUDA(cudaMalloc(&op->own_red.partials, sizeof(double) * (2 * SG_MAX_BLOCKS + 2)));
-        SG_CHECK_CUDA(cudaMalloc(&op->own_red.counter, sizeof(unsigned)));
-        SG_CHECK_CUDA(cudaMemset(op->own_red.counter, 0, sizeof(unsigned)));
-    }
-    int rc = op->linearize(op, T_lin, (cudaStream_t)stream);
+    // the class kernels reduce x.y as they go and need scratch for it even when nobody reads the result
+    int rc = op->cls.tab ? ensure_own_red(op) : SG_OK;
+    if (rc) return rc;
+    rc = op->linearize(op, T_lin, (cudaStream_t)stream);
     if (rc) return rc;
     return op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, op->own_red, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -1767,6 +1880,13 @@ int sg_thermal_class_info(const sg_thermal_op *op, int32_t *n_geometry, int32_t 
     if (n_self) *n_self = op->cls.tab ? op->cls.n_self : 0;
     if (n_facet) *n_facet = op->cls.tab ? op->cls.n_nb : 0;
     return op->cls.tab ? 1 : 0;
+}
+
+int sg_thermal_stencil_info(const sg_thermal_op *op, int32_t *n_classes, int32_t *n_entries, int32_t *max_nnz) {
+    SG_REQUIRE(op, "sg_thermal_stencil_info: NULL operator");
+    if (!op->stencil) return 0;
+    sg_stencil_info(op->stencil, n_classes, n_entries, max_nnz);
+    return 1;
 }
 
 int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity) {
@@ -1833,6 +1953,7 @@ int64_t sg_thermal_apply_bytes(const sg_thermal_op *op) {
     const sg_thermal_desc &d = op->d;
     const int64_t ncell = d.cell_hi - d.cell_lo;
     const int64_t ndof = d.family == 1 ? ncell * d.n_ld : d.n_dofs;
+    if (op->stencil) return 18 * d.n_dofs;   // row-stencil form: class id + x + y per row; the class lists live in shared memory
     int64_t per_cell;
     if (op->cls.tab) {
         per_cell = d.family == 1 ? 8 + 4 * (d.dim + 1)   // class word + neighbour ids

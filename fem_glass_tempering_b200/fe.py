@@ -383,7 +383,14 @@ class ScalarSpace:
 
 def _p2_dofmap(mesh: Mesh):
     """P2 numbering: on a lattice mesh every P2 node is a point of the half-step lattice, so its id is
-    pure arithmetic; otherwise edges are numbered with np.unique."""
+    pure arithmetic; otherwise edges are numbered with np.unique.
+
+    Lattice order (d >= 2): x half-planes slowest (what the slab partition of distributed.py relies on); inside a
+    plane the LONGEST remaining axis is the run axis, and along it the even half-steps come before the odd ones
+    (id = ... + parity * n_even + index // 2).  Consecutive ids therefore share the node type (vertex / which edge
+    midpoint) over a whole run, while `column id - row id` still only depends on the node type and the lattice
+    offset - the two properties the row-stencil form of the CG apply (csrc/stencil.cu) needs: one class per warp
+    and contiguous loads."""
     d, nc = mesh.dim, mesh.n_cells
     edges = ref_edges(d)
     lat = mesh.lattice
@@ -393,10 +400,17 @@ def _p2_dofmap(mesh: Mesh):
         cv = vc[mesh.cells]                              # [nc, d+1, d]
         loc = [2 * cv[:, i] for i in range(d + 1)] + [cv[:, a] + cv[:, b] for a, b in edges]
         loc = np.stack(loc, axis=1).astype(np.int64)     # [nc, n_ld, d] doubled-lattice coordinates
-        strides = np.ones(d, dtype=np.int64)
-        for c in range(d - 2, -1, -1):
-            strides[c] = strides[c + 1] * dims2[c + 1]
-        ids = loc @ strides
+        if d == 1:
+            return loc[:, :, 0].astype(np.int32), int(dims2[0])
+        run = 1 + int(np.argmax(dims2[1:]))              # run axis: the longest of the in-plane axes
+        n_run = int(dims2[run])
+        ids = (loc[:, :, run] & 1) * ((n_run + 1) // 2) + (loc[:, :, run] >> 1)
+        stride = n_run
+        for c in range(d - 1, -1, -1):                   # remaining axes, x last (slowest)
+            if c == run:
+                continue
+            ids = ids + loc[:, :, c] * stride
+            stride *= int(dims2[c])
         return ids.astype(np.int32), int(np.prod(dims2))
     nv = mesh.n_vertices
     ev = np.stack([np.stack([mesh.cells[:, a], mesh.cells[:, b]], axis=1) for a, b in edges], axis=1).astype(np.int64)

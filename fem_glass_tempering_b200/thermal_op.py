@@ -31,7 +31,8 @@ class ThermalOperator:
     """
 
     def __init__(self, ctx: _lib.Context, space: fe.ScalarSpace, params: dict, dt: float, partition: dict | None = None,
-                 use_classes: bool = True, cheb_degree: int | None = None, use_pairs: bool | None = None):
+                 use_classes: bool = True, cheb_degree: int | None = None, use_pairs: bool | None = None,
+                 use_stencil: bool | None = None):
         import torch
         self.ctx, self.space, self.dt = ctx, space, float(dt)
         mesh, d = space.mesh, space.mesh.dim
@@ -75,7 +76,11 @@ class ThermalOperator:
         if use_pairs is None:
             import os
             use_pairs = os.environ.get("SG_PAIRS", "0") == "1"      # two cells per thread: measured slower, opt-in
-        desc.flags = (0 if use_classes else 1) | (4 if use_pairs else 0)     # SG_THERMAL_NO_CLASSES, SG_THERMAL_PAIRS
+        if use_stencil is None:
+            import os
+            use_stencil = os.environ.get("SG_NO_STENCIL", "0") != "1"   # CG: gather form of the apply where rows repeat
+        # SG_THERMAL_NO_CLASSES, SG_THERMAL_PAIRS, SG_THERMAL_NO_STENCIL
+        desc.flags = (0 if use_classes else 1) | (4 if use_pairs else 0) | (0 if use_stencil else 8)
         for name in ("dofmap", "geom", "nbr", "nbinfo", "bf_cell", "bf_facet", "bf_area"):
             setattr(desc, name, _lib.ptr(keep.get(name)))
         desc.n_bfacets = nbf
@@ -93,6 +98,19 @@ class ThermalOperator:
         hnd = C.c_void_p()
         _lib.check(L.sg_thermal_op_create(ctx.handle, C.byref(desc), C.byref(hnd)))
         self.handle = hnd
+        if ctx.nranks > 1:
+            # the ranks' shares of the fused x.Ax tile the global sum only if all of them reduce the same way
+            # (row-wise with the stencil form, cell-wise with the class kernels, dof-wise with the general kernel)
+            import torch.distributed as dist
+            mine = (self.class_info()["active"], self.stencil_info()["active"])
+            paths = [None] * ctx.nranks
+            dist.all_gather_object(paths, mine)
+            if any(p != mine for p in paths):
+                _lib.check(L.sg_thermal_op_destroy(self.handle))
+                desc.flags |= 8 | (0 if all(p[0] for p in paths) else 1)
+                hnd = C.c_void_p()
+                _lib.check(L.sg_thermal_op_create(ctx.handle, C.byref(desc), C.byref(hnd)))
+                self.handle = hnd
         # halo plan + solver
         self.halo = None
         segs = part.get("halo") or []
@@ -184,6 +202,14 @@ class ThermalOperator:
         if rc < 0:
             _lib.check(rc)
         return dict(active=bool(rc), geometry=g.value, self=s_.value, facet=f.value)
+
+    def stencil_info(self) -> dict:
+        """Row-stencil form of the CG apply (sg_thermal_stencil_info): in use or not, table sizes."""
+        n, e, m = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        rc = _lib.lib().sg_thermal_stencil_info(self.handle, C.byref(n), C.byref(e), C.byref(m))
+        if rc < 0:
+            _lib.check(rc)
+        return dict(active=bool(rc), classes=n.value, entries=e.value, max_nnz=m.value)
 
     def apply_bytes(self) -> int:
         return int(_lib.lib().sg_thermal_apply_bytes(self.handle))

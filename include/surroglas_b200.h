@@ -181,9 +181,11 @@ typedef struct {
 enum {
     SG_THERMAL_NO_CLASSES = 1,      /* never use the local-matrix class tables (general per-cell-geometry kernel only) */
     SG_THERMAL_GENERAL_RESIDUAL = 2,/* evaluate the residual with the per-cell-geometry kernel even when the tables exist */
-    SG_THERMAL_PAIRS = 4            /* DG class kernels: two cells per thread sharing the shared-memory table reads.  Off by
+    SG_THERMAL_PAIRS = 4,           /* DG class kernels: two cells per thread sharing the shared-memory table reads.  Off by
                                        default: measured SLOWER on B200 (Chebyshev step 211 vs 183 us on C3; 128 registers halve
                                        the resident warps), kept for experiments */
+    SG_THERMAL_NO_STENCIL = 8       /* CG spaces: never use the row-stencil form of the Jacobian apply (see
+                                       sg_thermal_stencil_info); the cell-centric class kernel scatters instead */
 };
 
 typedef struct sg_thermal_op sg_thermal_op;
@@ -200,6 +202,11 @@ int sg_thermal_jac_diag(sg_thermal_op *op, const double *T_lin, double *diag, vo
  * precomputed element matrix; sg_thermal_jac_apply then reads no geometry).  Returns 1 when the class
  * tables are in use, 0 when the mesh has too many classes and the general kernel runs, <0 on error. */
 int sg_thermal_class_info(const sg_thermal_op *op, int32_t *n_geometry, int32_t *n_self, int32_t *n_facet);
+/* CG spaces on a mesh whose rows repeat (lattice-numbered plates): the Jacobian apply runs in gather form, one 16-bit
+ * class id per row and the class's (column offset, coefficient) list in shared memory - what PETSc's assembled MatMult
+ * does with a CSR matrix (TVP:340-346), without the matrix.  Returns 1 and the table sizes when that form is in use,
+ * 0 when the cell-centric kernels run, <0 on error. */
+int sg_thermal_stencil_info(const sg_thermal_op *op, int32_t *n_classes, int32_t *n_entries, int32_t *max_nnz);
 /* Optional timing of the Jacobian-apply cell kernel with CUDA event pairs on its launch stream
  * (measurement harness only; at most `capacity` launches are recorded after each enable). */
 int sg_thermal_profile(sg_thermal_op *op, int32_t enable, int32_t capacity);

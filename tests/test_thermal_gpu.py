@@ -275,6 +275,63 @@ def test_cuda_graph_batches_match_plain_launches(sg_ctx, dim, family, degree, mo
     assert res["0"][0][0] > 8          # more than one batch: the graph path was exercised
 
 
+@pytest.mark.parametrize("dim,degree,dims", [(2, 1, (9, 5)), (2, 2, (9, 5)), (3, 1, (5, 4, 3)), (3, 2, (5, 4, 3)),
+                                             (3, 2, (37, 30, 6)), (2, 2, (130, 70)), (1, 2, None)])
+def test_cg_row_stencil_form_matches_the_cell_kernel(sg_ctx, dim, degree, dims):
+    """CG spaces: the gather form of the apply (row-stencil classes, csrc/stencil.cu) against the cell-centric class kernel
+    (RED.ADD scatter), and on the small meshes against the assembled oracle: 1e-12 relative.  The gather form is
+    deterministic (bit-identical repeats); PCG must not care which form runs."""
+    m = msh.graded_line_mesh() if dim == 1 else msh.plate_mesh(dim, dims, tuple(float(k) for k in dims))
+    space = fe.ScalarSpace(m, "CG", degree)
+    ops = {st: ThermalOperator(sg_ctx, space, MAIN_PARAMS, 0.1, use_stencil=st, cheb_degree=0) for st in (True, False)}
+    info = ops[True].stencil_info()
+    assert info["active"] and not ops[False].stencil_info()["active"], info
+    if dim > 1:
+        # lattice-numbered plate: (boundary-lo, odd, even, boundary-hi) per axis for P2, (lo, interior, hi) for P1
+        assert info["classes"] <= (4 if degree == 2 else 3) ** dim * 2, info
+    n = space.n_nodes
+    rng = np.random.default_rng(3)
+    T = 700 + 100 * rng.random(n)
+    x = rng.standard_normal(n)
+    Td, xd = dev(T), dev(x)
+    ys = ops[True].jac_apply(Td, xd, torch.empty(n, dtype=torch.float64, device="cuda:0")).cpu().numpy()
+    ys2 = ops[True].jac_apply(Td, xd, torch.full((n,), 7.0, dtype=torch.float64, device="cuda:0")).cpu().numpy()
+    yc = ops[False].jac_apply(Td, xd, torch.empty(n, dtype=torch.float64, device="cuda:0")).cpu().numpy()
+    # y need not be zeroed; the cell part has no atomics, only the exterior-facet part adds in arbitrary order
+    assert np.max(np.abs(ys - ys2)) <= 1e-15 * np.max(np.abs(ys))
+    assert np.max(np.abs(ys - yc)) <= 1e-12 * np.max(np.abs(yc))
+    if m.n_cells < 5000:
+        orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "CG", degree, MAIN_PARAMS, 0.1)
+        yo = orc.jacobian(T) @ x
+        assert np.max(np.abs(ys - yo)) <= 1e-12 * np.max(np.abs(yo))
+    res = {}
+    b = rng.standard_normal(n)
+    for st, op in ops.items():
+        xs = torch.zeros(n, dtype=torch.float64, device="cuda:0")
+        op.prepare_preconditioner(Td)
+        its, _ = op.pcg(Td, dev(b), xs, rtol=1e-12)
+        res[st] = (its, xs.cpu().numpy())
+    assert abs(res[True][0] - res[False][0]) <= 2 + res[False][0] // 16
+    assert np.max(np.abs(res[True][1] - res[False][1])) <= 1e-10 * np.max(np.abs(res[False][1]))
+
+
+def test_cg_row_stencil_on_a_rank_slab(sg_ctx):
+    """One rank's slab of a partitioned plate (ghost columns on both sides, cell range inside the local mesh): the gather
+    form must reproduce the cell kernel on every local row, including the incomplete ghost rows."""
+    from fem_glass_tempering_b200 import distributed
+    m, part, _ = distributed.slab_partition(3, (12, 5, 3), (12.0, 5.0, 3.0), "CG", 2, 1, 3)
+    part = dict(part, halo=[])
+    space = fe.ScalarSpace(m, "CG", 2)
+    ops = {st: ThermalOperator(sg_ctx, space, MAIN_PARAMS, 0.1, partition=part, use_stencil=st, cheb_degree=0) for st in (True, False)}
+    assert ops[True].stencil_info()["active"]
+    n = space.n_nodes
+    rng = np.random.default_rng(4)
+    Td, xd = dev(700 + 100 * rng.random(n)), dev(rng.standard_normal(n))
+    ys = ops[True].jac_apply(Td, xd, torch.empty(n, dtype=torch.float64, device="cuda:0")).cpu().numpy()
+    yc = ops[False].jac_apply(Td, xd, torch.empty(n, dtype=torch.float64, device="cuda:0")).cpu().numpy()
+    assert np.max(np.abs(ys - yc)) <= 1e-12 * np.max(np.abs(yc))
+
+
 def test_many_shapes_fall_back_to_per_cell_geometry(sg_ctx):
     """A mesh whose cells all differ (randomly perturbed vertices) has too many classes for the shared-memory tables:
     the library must keep the general kernel and still match the oracle."""
