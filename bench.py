@@ -453,9 +453,10 @@ def run_gpu(args):
             traffic = json.load(fh).get(args.workload, {}) 
     except Exception:
         traffic = {}
-    for key, kern in (("roofline_cheb_step", "dg_cheb_step"), ("roofline_apply", "dg_class_apply"), ("roofline_visco", "visco_fast_kernel")):
+    for key, kerns in (("roofline_cheb_step", ("dg_cheb_step",)), ("roofline_apply", ("dg_class_apply", "k_stencil_apply")),
+                       ("roofline_visco", ("visco_fast_kernel",))):
         if line.get(key):
-            line[key]["traffic"] = traffic.get(kern) if kern in line[key]["kernel"] else None
+            line[key]["traffic"] = next((traffic.get(k) for k in kerns if k in line[key]["kernel"]), None)
             line[key].setdefault("peak_source", peak_how)
     cands = [line[k] for k in ("roofline_cheb_step", "roofline_apply", "roofline_visco") if line.get(k)]
     line["roofline"] = max(cands, key=lambda r: r["share_of_step"])

@@ -17,6 +17,8 @@
 // against cg_class_apply on a pseudo-random vector before it switches the operator over; a mesh with too many classes
 // (unstructured numbering) simply keeps the cell-centric kernel.
 // Reference: the assembled PETSc MatMult inside KSP cg of TVP:340-346, on the Jacobian of TVP:293-306.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -135,10 +137,12 @@ __global__ void k_narrow16(long n, const int32_t *__restrict__ in, uint16_t *__r
     if (i < n) out[i] = (uint16_t)in[i];
 }
 
-// y_i = sum_k coef[cls_i][k] x[i + off[cls_i][k]];  dot_out[0] = sum over owned rows of x_i y_i, dot_out[1] = 0
-template <bool SMEM>
-__global__ void __launch_bounds__(STB, 4) k_stencil_apply(const StDev sd, const double *__restrict__ x, double *__restrict__ y,
-                                                         SgRed red, double *dot_out, const int *skip) {
+// y_i = sum_k coef[cls_i][k] x[i + off[cls_i][k]];  dot_out[0] = sum over owned rows of x_i y_i, dot_out[1] = 0.
+// The x loads of U entries are issued before the first FMA (they are independent; two thirds of them miss L1 and
+// come from L2, so the loads in flight per warp set the pace); the sum itself stays in entry order for every U.
+template <bool SMEM, int U, int MINB>
+__global__ void __launch_bounds__(STB, MINB) k_stencil_apply(const StDev sd, const double *__restrict__ x, double *__restrict__ y,
+                                                            SgRed red, double *dot_out, const int *skip) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     if (skip && *skip) return;
     const Entry *ent = sd.ent;
@@ -155,11 +159,21 @@ __global__ void __launch_bounds__(STB, 4) k_stencil_apply(const StDev sd, const 
     double dsum[2] = {0.0, 0.0};
     for (long row = (long)blockIdx.x * STB + threadIdx.x; row < sd.n_rows; row += (long)gridDim.x * STB) {
         const int c = sd.rcls[row];
-        const int p0 = ptr[c], p1 = ptr[c + 1];
+        const int p1 = ptr[c + 1];
+        int k = ptr[c];
         const double *xr = x + row;
         double acc = 0.0;
-#pragma unroll 4
-        for (int k = p0; k < p1; ++k) {
+        for (; k + U <= p1; k += U) {
+            Entry e[U];
+            double xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) e[u] = ent[k + u];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = __ldg(xr + e[u].off);
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc = fma(e[u].coef, xv[u], acc);
+        }
+        for (; k < p1; ++k) {
             const Entry e = ent[k];
             acc = fma(e.coef, __ldg(xr + e.off), acc);
         }
@@ -168,6 +182,26 @@ __global__ void __launch_bounds__(STB, 4) k_stencil_apply(const StDev sd, const 
     }
     sg_grid_reduce<2>(dsum, red, dot_out);
 }
+
+using StencilKernel = void (*)(const StDev, const double *, double *, SgRed, double *, const int *);
+struct Variant {
+    StencilKernel smem, global;
+    const char *what;
+};
+// SG_STENCIL_VARIANT selects one at operator creation (measurement only); the default is variant 0.  Measured on one
+// GPU's share of config 4 (3.86 M rows, tools/cg_apply_probe.py, profiles/r1s_cg_apply_probe.jsonl): 76.2 / 77.9 / 82.0 /
+// 76.3 / - / 76.9 us - neither more loads in flight nor more resident warps help: ncu has the L1 at 65 % of its peak
+// with 8.5 sectors per request and a 33 % hit rate (600 MB of L2->L1 traffic per apply), i.e. the gather is bound by
+// L1 wavefronts (an unaligned 256-B warp load touches 3 lines), not by latency and not by HBM (42 MB of DRAM traffic).
+const Variant VARIANTS[] = {
+    {k_stencil_apply<true, 4, 4>, k_stencil_apply<false, 4, 4>, "4 loads in flight, 4 blocks/SM"},
+    {k_stencil_apply<true, 8, 4>, k_stencil_apply<false, 8, 4>, "8 loads in flight, 4 blocks/SM"},
+    {k_stencil_apply<true, 4, 8>, k_stencil_apply<false, 4, 8>, "4 loads in flight, 8 blocks/SM"},
+    {k_stencil_apply<true, 8, 6>, k_stencil_apply<false, 8, 6>, "8 loads in flight, 6 blocks/SM"},
+    {k_stencil_apply<true, 12, 3>, k_stencil_apply<false, 12, 3>, "12 loads in flight, 3 blocks/SM"},
+    {k_stencil_apply<true, 6, 5>, k_stencil_apply<false, 6, 5>, "6 loads in flight, 5 blocks/SM"},
+};
+constexpr int N_VARIANTS = (int)(sizeof(VARIANTS) / sizeof(VARIANTS[0]));
 
 struct DevBuf {
     void *p = nullptr;
@@ -188,6 +222,7 @@ struct SgStencil {
     int grid;
     size_t smem;   // bytes of the shared-memory copy of the class lists; 0: read through L1
     int max_nnz;
+    StencilKernel kernel;
 };
 
 void sg_stencil_destroy(SgStencil *s) {
@@ -259,9 +294,12 @@ int sg_stencil_build(sg_ctx *ctx, const int32_t *dofmap, int64_t n_cells, int n_
     SG_CHECK_CUDA(cudaDeviceSynchronize());
     const size_t table = sizeof(Entry) * (size_t)ptr[R] + sizeof(int32_t) * (size_t)(R + 1);
     s->smem = table <= MAX_SMEM_TABLE ? table : 0;
+    int variant = 0;
+    if (const char *v = getenv("SG_STENCIL_VARIANT")) variant = atoi(v);
+    if (variant < 0 || variant >= N_VARIANTS) variant = 0;
+    s->kernel = s->smem ? VARIANTS[variant].smem : VARIANTS[variant].global;
     int per_sm = 0;
-    if (s->smem) SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stencil_apply<true>, STB, s->smem));
-    else SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stencil_apply<false>, STB, 0));
+    SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->kernel, STB, s->smem));
     long grid = (long)(per_sm > 0 ? per_sm : 1) * ctx->sm_count;
     const long need = (n_rows + STB - 1) / STB;
     if (grid > need) grid = need;
@@ -285,8 +323,7 @@ int sg_stencil_apply(const SgStencil *s, const double *x, double *y, int64_t own
     StDev sd = s->dev;
     sd.own_lo = own_lo;
     sd.own_hi = own_hi;
-    if (s->smem) k_stencil_apply<true><<<s->grid, STB, s->smem, st>>>(sd, x, y, red, dot2, skip);
-    else k_stencil_apply<false><<<s->grid, STB, 0, st>>>(sd, x, y, red, dot2, skip);
+    s->kernel<<<s->grid, STB, s->smem, st>>>(sd, x, y, red, dot2, skip);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;

@@ -94,3 +94,53 @@ def jac_apply(space, tabs, geo, topo, params, dt, x, T_lin=None, xm=None, residu
 
 def fe_penalty():
     return 5.0
+
+
+def cell_matrices(space, tabs, geo, params, dt):
+    """The cell part of the Jacobian per cell, A_K = |detJ| M_ref + dt alpha K_K  (what the class tables of thermal.cu hold)."""
+    g = np.einsum("cab,qai->cqbi", geo.Jinv, tabs.cq_grad)
+    K = np.einsum("cqbi,cqbj,q,c->cij", g, g, tabs.cq_w, geo.detJ)
+    return geo.detJ[:, None, None] * tabs.mass[None] + dt * float(params["alpha"]) * K
+
+
+def row_stencil_classes(dofmap, cell_class, n_rows):
+    """numpy emulation of csrc/stencil.cu: rows are equivalent when the multisets {(class of K, local row a,
+    dofmap[K][.] - row)} over their (cell, local row) pairs agree.  Returns (class id per row, number of classes)."""
+    nc, nl = dofmap.shape
+    dm = dofmap.astype(np.int64)
+    rel = (dm[:, None, :] - dm[:, :, None]).reshape(nc * nl, nl)                 # [K, a, b] -> dm[K, b] - dm[K, a]
+    key = np.concatenate([np.repeat(cell_class, nl)[:, None], np.tile(np.arange(nl), nc)[:, None], rel], axis=1)
+    uniq, contrib = np.unique(key, axis=0, return_inverse=True)                  # exact (no hashing) contribution ids
+    rows = dm.ravel()
+    order = np.lexsort((contrib.ravel(), rows))
+    sig = {}
+    cls = np.zeros(n_rows, dtype=np.int64)
+    start = np.searchsorted(rows[order], np.arange(n_rows + 1))
+    cs = contrib.ravel()[order]
+    for r in range(n_rows):
+        cls[r] = sig.setdefault(tuple(cs[start[r]:start[r + 1]]), len(sig))
+    return cls, len(sig)
+
+
+def row_stencil_apply(dofmap, cell_class, mats_by_class, row_class, n_classes, x):
+    """y = A x in gather form: per class ONE (offset, coefficient) list taken from a representative row."""
+    nc, nl = dofmap.shape
+    dm = dofmap.astype(np.int64)
+    rep = np.full(n_classes, -1, dtype=np.int64)
+    rep[row_class[::-1]] = np.arange(row_class.size)[::-1]                       # first row of every class
+    table = [dict() for _ in range(n_classes)]
+    is_rep = np.zeros(row_class.size, dtype=bool)
+    is_rep[rep] = True
+    for K in np.nonzero(is_rep[dm].any(axis=1))[0]:                              # ascending cell order, like the kernel
+        for a in range(nl):
+            r = dm[K, a]
+            if is_rep[r]:
+                t = table[row_class[r]]
+                for b in range(nl):
+                    t[dm[K, b] - r] = t.get(dm[K, b] - r, 0.0) + mats_by_class[cell_class[K]][a, b]
+    y = np.zeros(row_class.size)
+    for c in range(n_classes):
+        rows = np.nonzero(row_class == c)[0]
+        for off, coef in sorted(table[c].items()):
+            y[rows] += coef * x[rows + off]
+    return y, table

@@ -279,3 +279,48 @@ def test_oracle_and_p2_numbering_against_the_hand_evaluated_cg2_vectors():
         Jx = orc.jacobian(c["T"]) @ c["v"]
         assert np.max(np.abs(F - c["residual"])) <= 1e-12 * np.max(np.abs(c["residual"])), c["dim"]
         assert np.max(np.abs(Jx - c["jac_x"])) <= 1e-12 * np.max(np.abs(c["jac_x"])), c["dim"]
+
+
+@pytest.mark.parametrize("dim,n,degree", [(2, (10, 6), 1), (2, (10, 6), 2), (3, (4, 7, 3), 1), (3, (4, 7, 3), 2)])
+def test_row_stencil_form_of_the_cg_apply(dim, n, degree):
+    """The gather form csrc/stencil.cu builds (numpy emulation, tests/kernel_mirror.py): on a lattice-numbered plate the
+    rows fall into a handful of classes and ONE (offset, coefficient) list per class reproduces the scattered cell
+    matrices to rounding; with a scrambled numbering the classes do not repeat (the library then keeps the cell kernel)."""
+    import kernel_mirror
+    from fem_glass_tempering_b200 import mesh as msh
+    m = msh.plate_mesh(dim, n, tuple(float(k) for k in n))
+    space = fe.ScalarSpace(m, "CG", degree)
+    tabs, geo = fe.operator_tables(dim, degree), fe.cell_geometry(m)
+    A = kernel_mirror.cell_matrices(space, tabs, geo, MAIN_PARAMS, 0.1)
+    gkey = np.round(np.concatenate([geo.Jinv.reshape(m.n_cells, -1), geo.detJ[:, None]], axis=1), 9)
+    _, first, ccls = np.unique(gkey, axis=0, return_index=True, return_inverse=True)
+    rcls, R = kernel_mirror.row_stencil_classes(space.dofmap, ccls, space.n_nodes)
+    assert R <= (4 if degree == 2 else 3) ** dim                      # (lo, odd, even, hi) per axis for P2, (lo, inner, hi) for P1
+    x = np.random.default_rng(0).standard_normal(space.n_nodes)
+    y, table = kernel_mirror.row_stencil_apply(space.dofmap, ccls, A[first], rcls, R, x)
+    ys = np.zeros(space.n_nodes)
+    np.add.at(ys, space.dofmap.ravel(), np.einsum("cij,cj->ci", A, x[space.dofmap]).ravel())
+    assert np.max(np.abs(y - ys)) <= 1e-13 * np.max(np.abs(ys))
+    assert max(len(t) for t in table) == {(2, 1): 7, (2, 2): 19, (3, 1): 15, (3, 2): 65}[(dim, degree)]   # Kuhn vertex stars
+    perm = np.random.default_rng(1).permutation(space.n_nodes)
+    _, R_scrambled = kernel_mirror.row_stencil_classes(perm[space.dofmap], ccls, space.n_nodes)
+    assert R_scrambled > space.n_nodes // 2
+
+
+def test_p2_lattice_numbering_keeps_planes_and_runs():
+    """The P2 numbering of the plate meshes: x half-planes are contiguous id ranges (distributed.slab_partition relies on
+    it) and inside a plane consecutive ids run along the longest in-plane axis with even half-steps before odd ones, so
+    that neighbouring ids are nodes of the same type (one row class per warp in csrc/stencil.cu)."""
+    from fem_glass_tempering_b200 import mesh as msh
+    m = msh.box_mesh(3, 8, 2, 3.0, 8.0, 2.0)
+    space = fe.ScalarSpace(m, "CG", 2)
+    X = space.tabulate_dof_coordinates()
+    h2 = np.rint(2 * X).astype(int)                                  # half-step lattice coordinates (unit cells)
+    plane = 17 * 5
+    assert space.n_nodes == 7 * plane
+    ids = np.arange(space.n_nodes)
+    assert np.array_equal(h2[:, 0], ids // plane)                    # x slowest
+    inp = ids % plane
+    assert np.array_equal(h2[:, 2], inp // 17)                       # then z (the short axis)
+    run = inp % 17
+    assert np.array_equal(h2[:, 1], np.where(run < 9, 2 * run, 2 * (run - 9) + 1))   # y: 9 even half-steps, then 8 odd
