@@ -21,6 +21,9 @@ def _np_ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+STENCIL_MIN_ROWS = 1_000_000     # below this the CG apply is launch-latency bound either way (see use_stencil)
+
+
 class ThermalOperator:
     """Matrix-free Jacobian/residual of the heat equation on one GPU (one rank's part of the mesh).
 
@@ -77,8 +80,12 @@ class ThermalOperator:
             import os
             use_pairs = os.environ.get("SG_PAIRS", "0") == "1"      # two cells per thread: measured slower, opt-in
         if use_stencil is None:
+            # CG: gather form of the apply where rows repeat (csrc/stencil.cu).  It needs a second small launch for the
+            # exterior facets, so meshes whose kernels are launch-latency bound anyway (config 2: 334 k rows, 4 us
+            # kernels) keep the one-launch scatter kernel; SG_STENCIL=1 / SG_NO_STENCIL=1 override.
             import os
-            use_stencil = os.environ.get("SG_NO_STENCIL", "0") != "1"   # CG: gather form of the apply where rows repeat
+            env = os.environ
+            use_stencil = (env.get("SG_NO_STENCIL", "0") != "1") and (env.get("SG_STENCIL", "0") == "1" or space.n_nodes >= STENCIL_MIN_ROWS)
         # SG_THERMAL_NO_CLASSES, SG_THERMAL_PAIRS, SG_THERMAL_NO_STENCIL
         desc.flags = (0 if use_classes else 1) | (4 if use_pairs else 0) | (0 if use_stencil else 8)
         for name in ("dofmap", "geom", "nbr", "nbinfo", "bf_cell", "bf_facet", "bf_area"):

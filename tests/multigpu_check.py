@@ -54,6 +54,9 @@ def main():
         n = (n_per[0] * world,) + tuple(n_per[1:])
         lengths = tuple(edge * k for k in n)
         fam, deg = cfg["T"]["element"], cfg["T"]["degree"]
+        # CG: the 3-D case runs the gather form of the apply (row-wise share of x.Ax), the 2-D case the scatter form
+        # (cell-wise share); small meshes default to the latter (thermal_op.STENCIL_MIN_ROWS)
+        os.environ["SG_STENCIL"] = "1" if (fam == "CG" and dim == 3) else "0"
         m, part, info = distributed.slab_partition(dim, n, lengths, fam, deg, rank, world)
         prob = make_problem(m, cfg, ctx, part)
         if fam == "DG":      # the partitioned run uses the Chebyshev-preconditioned solver (halo exchange of every
