@@ -1164,6 +1164,7 @@ struct sg_thermal_op {
     int32_t *nbr_ext;      // DG P1: neighbour ids with exterior facets encoded (see ClsDev::bmat)
     double *bmat;
     SgStencil *stencil;    // CG: row-stencil classes (stencil.cu); nullptr: cell-centric cg_class_apply
+    double *diag_cells;    // CG: the cell part of diag J (M + dt alpha K does not depend on T), computed once at creation
     int (*linearize)(const sg_thermal_op *, const double *T_lin, cudaStream_t st);
     int (*cheb_step)(const sg_thermal_op *, const SgChebStep &, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
     // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
@@ -1238,8 +1239,13 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
     const long ncell = dv.cell_hi - dv.cell_lo;
     const unsigned gc = (unsigned)((ncell + TB - 1) / TB), gb = capped_grid(dv.n_bf, TB);
     const bool fast = mode == MODE_APPLY && op->cls.tab != nullptr;
-    if (!DG && !(mode == MODE_APPLY && (op->y_is_zero || (fast && op->stencil)))) SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
-    if (fast) {
+    const bool cached_diag = !DG && mode == MODE_DIAG && op->diag_cells != nullptr && y != op->diag_cells;
+    if (!DG && !cached_diag && !(mode == MODE_APPLY && (op->y_is_zero || (fast && op->stencil))))
+        SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
+    if (cached_diag) {
+        // point Jacobi asks for diag J(T) in every Newton iteration; only the exterior facets (below) depend on T
+        SG_CHECK_CUDA(cudaMemcpyAsync(y, op->diag_cells, sizeof(double) * (size_t)dv.n_dofs, cudaMemcpyDeviceToDevice, st));
+    } else if (fast) {
         // the class kernels always reduce x.y; without a consumer it lands in a scratch slot
         double *dst = dot2 ? dot2 : red.partials + 2 * SG_MAX_BLOCKS;
         {
@@ -1829,6 +1835,30 @@ int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *d, sg_thermal_op **
             return rc;
         }
     }
+    if (d->family == 0 && d->n_dofs > 0) {
+        // diag of the cell part with the general kernel (into the cache itself: launch_op then takes the uncached route
+        // with no exterior facets), once
+        double *cache = nullptr;
+        cudaError_t e = cudaMalloc(&cache, sizeof(double) * (size_t)d->n_dofs);
+        if (e != cudaSuccess) {
+            sg_set_error("sg_thermal_op_create: %s", cudaGetErrorString(e));
+            sg_thermal_op_destroy(op);
+            return SG_E_CUDA;
+        }
+        const int64_t n_bf = op->dev.n_bf;
+        op->dev.n_bf = 0;
+        op->diag_cells = cache;
+        rc = op->launch(op, MODE_DIAG, nullptr, nullptr, nullptr, cache, SgRed{nullptr, nullptr}, nullptr, nullptr, 0);
+        op->dev.n_bf = n_bf;
+        if (rc == SG_OK && cudaDeviceSynchronize() != cudaSuccess) {
+            sg_set_error("sg_thermal_op_create: diagonal of the cell part failed");
+            rc = SG_E_CUDA;
+        }
+        if (rc != SG_OK) {
+            sg_thermal_op_destroy(op);
+            return rc;
+        }
+    }
     *out = op;
     return SG_OK;
 }
@@ -1842,6 +1872,7 @@ int sg_thermal_op_destroy(sg_thermal_op *op) {
     if (op->nbr_ext) cudaFree(op->nbr_ext);
     if (op->bmat) cudaFree(op->bmat);
     sg_stencil_destroy(op->stencil);
+    if (op->diag_cells) cudaFree(op->diag_cells);
     if (op->own_red.partials) cudaFree(op->own_red.partials);
     if (op->own_red.counter) cudaFree(op->own_red.counter);
     for (int i = 0; i < 2 * op->prof_cap; ++i) cudaEventDestroy(op->prof_ev[i]);
