@@ -2,6 +2,8 @@
 import ctypes
 import os
 
+import pytest
+
 from fem_glass_tempering_b200 import _lib
 
 
@@ -34,3 +36,31 @@ def test_bytes_per_node_formula():
         p.dim, p.n_terms = d, N
         f = _lib.ViscoFieldsC()
         assert L.sg_visco_bytes_per_node(ctypes.byref(p), ctypes.byref(f), _lib.PHASE_ALL) == expect
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in _lib.py / _lib_thermal.py against the C structs of include/surroglas_b200.h: gcc prints
+    sizeof and every offsetof (field names must exist in the header for this to compile), ctypes must agree."""
+    import shutil
+    import subprocess
+    from fem_glass_tempering_b200 import _lib_thermal as lt
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = [("sg_visco_params", _lib.ViscoParamsC), ("sg_visco_fields", _lib.ViscoFieldsC),
+             ("sg_visco_gather", _lib.ViscoGatherC), ("sg_thermal_desc", lt.ThermalDescC),
+             ("sg_halo_segment", lt.HaloSegmentC), ("sg_newton_opts", lt.NewtonOptsC), ("sg_newton_stats", lt.NewtonStatsC)]
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "surroglas_b200.h")
+    lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{header}"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
