@@ -271,7 +271,15 @@ def facet_topology(mesh: Mesh, exterior_mask=None) -> FacetTopology:
     d, nc = mesh.dim, mesh.n_cells
     keys = _facet_keys(mesh)
     nf = keys.shape[0]
-    order = np.lexsort(tuple(keys[:, c] for c in range(d - 1, -1, -1)))
+    nv = int(mesh.n_vertices)
+    if nv ** d < 2 ** 62:
+        # one 64-bit key per facet and a stable sort: same order as the lexicographic sort, several times faster
+        packed = keys[:, 0].copy()
+        for c in range(1, d):
+            packed = packed * nv + keys[:, c]
+        order = np.argsort(packed, kind="stable")
+    else:
+        order = np.lexsort(tuple(keys[:, c] for c in range(d - 1, -1, -1)))
     sk = keys[order]
     same = np.all(sk[1:] == sk[:-1], axis=1) if nf > 1 else np.zeros(0, dtype=bool)
     neighbor = np.full(nf, -1, dtype=np.int32)
