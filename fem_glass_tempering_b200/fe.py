@@ -278,37 +278,41 @@ def facet_topology(mesh: Mesh, exterior_mask=None) -> FacetTopology:
         for c in range(1, d):
             packed = packed * nv + keys[:, c]
         order = np.argsort(packed, kind="stable")
+        sp = packed[order]
+        same = sp[1:] == sp[:-1] if nf > 1 else np.zeros(0, dtype=bool)
     else:
         order = np.lexsort(tuple(keys[:, c] for c in range(d - 1, -1, -1)))
-    sk = keys[order]
-    same = np.all(sk[1:] == sk[:-1], axis=1) if nf > 1 else np.zeros(0, dtype=bool)
+        sk = keys[order]
+        same = np.all(sk[1:] == sk[:-1], axis=1) if nf > 1 else np.zeros(0, dtype=bool)
     neighbor = np.full(nf, -1, dtype=np.int32)
     nb_facet = np.zeros(nf, dtype=np.int8)
-    a, b = order[:-1][same], order[1:][same]
+    a, b = order[:-1][same], order[1:][same]          # the two views of every interior facet (a < b: stable sort)
     neighbor[a], neighbor[b] = (b // (d + 1)).astype(np.int32), (a // (d + 1)).astype(np.int32)
     nb_facet[a], nb_facet[b] = (b % (d + 1)).astype(np.int8), (a % (d + 1)).astype(np.int8)
-    # vertex permutation between the two cells' views of the facet
+    # vertex permutation between the two cells' views of the facet: for view i with neighbour view j,
+    # s(k') = position in gv_i of gv_j[k']; the permutation of view b is the inverse of the one of view a
     fac = np.array(ref_facets(d), dtype=np.int64)  # [d+1, d]
     nb_perm = np.zeros(nf, dtype=np.int8)
-    if d > 1:
+    if d > 1 and a.size:
         perms = list(itertools.permutations(range(d)))
-        interior = np.nonzero(neighbor >= 0)[0]
-        ci, fi = interior // (d + 1), interior % (d + 1)
-        gv_k = mesh.cells[ci[:, None], fac[fi]].astype(np.int64)                                  # [ni, d]
-        gv_n = mesh.cells[neighbor[interior][:, None], fac[nb_facet[interior].astype(np.int64)]].astype(np.int64)
-        # s(k') = position in gv_k of gv_n[k']
-        s = np.argmax(gv_n[:, :, None] == gv_k[:, None, :], axis=2)                               # [ni, d]
-        code = np.zeros(len(interior), dtype=np.int64)
+        gv_a = mesh.cells[(a // (d + 1))[:, None], fac[a % (d + 1)]]                              # [npair, d]
+        gv_b = mesh.cells[(b // (d + 1))[:, None], fac[b % (d + 1)]]
+        s = np.argmax(gv_b[:, :, None] == gv_a[:, None, :], axis=2)                               # [npair, d]
+        code = np.zeros(a.size, dtype=np.int64)
         for c in range(d):
             code = code * d + s[:, c]
         lut = np.full(d ** d, -1, dtype=np.int8)
+        inverse = np.zeros(len(perms), dtype=np.int8)
         for pid, p in enumerate(perms):
             cc = 0
             for c in range(d):
                 cc = cc * d + p[c]
             lut[cc] = pid
-        nb_perm[interior] = lut[code]
-        assert (nb_perm[interior] >= 0).all()
+            inverse[pid] = perms.index(tuple(int(k) for k in np.argsort(p)))
+        pid_a = lut[code]
+        assert (pid_a >= 0).all()
+        nb_perm[a] = pid_a
+        nb_perm[b] = inverse[pid_a]
     bnd = np.nonzero(neighbor < 0)[0]
     if exterior_mask is not None and bnd.size:
         ci, fi = bnd // (d + 1), bnd % (d + 1)
