@@ -98,6 +98,7 @@ def slab_partition(dim: int, n, lengths, family: str, degree: int, rank: int, wo
             halo.append((rank + 1, own_hi - blk, blk, own_hi, blk))
         owned_points = (c1 - c0) * col_cells * n_ld
         own_cells = (cell_lo, cell_hi)
+        global_offset, global_n = c0 * blk, nx * blk
     else:
         gp = degree                                        # ghost planes on the left: 1 (P1) or 2 (P2)
         planes_owned = (c1 - c0) * degree + (1 if rank == world - 1 else 0)
@@ -110,8 +111,10 @@ def slab_partition(dim: int, n, lengths, family: str, degree: int, rank: int, wo
         if rank < world - 1:
             halo.append((rank + 1, own_hi - gp * plane, gp * plane, own_hi, plane))
         owned_points = (c1 - c0) * col_cells * n_ld
+        global_offset, global_n = c0 * degree * plane, (nx * degree + 1) * plane
     part = dict(cell_lo=cell_lo, cell_hi=cell_hi, own_lo=own_lo, own_hi=own_hi, exterior_mask=exterior_mask,
-                halo=halo, own_cell_lo=own_cells[0], own_cell_hi=own_cells[1])
+                halo=halo, own_cell_lo=own_cells[0], own_cell_hi=own_cells[1],
+                global_own_offset=global_offset, global_n_dofs=global_n)    # where the owned range sits in the unpartitioned numbering
     info = dict(columns=(c0, c1), ghost_left=gl, ghost_right=gr, owned_cell_points=owned_points,
                 owned_nodes=own_hi - own_lo)
     return m, part, info

@@ -108,7 +108,11 @@ class ThermoViscoProblem:
     # ------------------------------------------------------------------------------------------ mesh
     @staticmethod
     def _load_mesh(mesh_path: str, problem_dim):
-        if mesh_path and os.path.exists(mesh_path):
+        if mesh_path:
+            # TVP:27-28 reads the file or fails; a wrong path must not silently run a different problem
+            if not os.path.exists(mesh_path):
+                raise FileNotFoundError(f"mesh file {mesh_path!r} does not exist (geometry.create_mesh(path) writes the "
+                                        "reference's graded line; mesh_path='' selects the built-in meshes)")
             from .meshio import read_msh
             return read_msh(mesh_path)
         if problem_dim in (None, 1):
@@ -227,9 +231,10 @@ class ThermoViscoProblem:
     def _set_initial_condition(self, temp_value: float) -> None:
         """TVP:187-233: T_prev = T_cur = T_0, Tf = T, every partial fictive temperature = T.x.array[0]."""
         fc, fp = self.functions_current, self.functions_previous
-        init = lambda x: np.full(x.shape[1], temp_value)
-        fp["T"].interpolate(init)
-        fc["T"].interpolate(init)
+        # TVP:193-201 interpolates `lambda x: np.full(x.shape[1], temp_value)`: a constant, so the dof coordinates (seconds
+        # of host work on a 20 M-node plate) are not tabulated for it
+        fp["T"].x.array.fill_(temp_value)
+        fc["T"].x.array.fill_(temp_value)
         fp["Tf"].x.array.copy_(fp["T"].x.array)
         fc["Tf"].x.array.copy_(fc["T"].x.array)
         v0 = float(fc["T"].x.array[0])

@@ -42,16 +42,17 @@ class ThermalOperator:
         dev = torch.device("cuda", ctx.device)
         part = partition or {}
         tabs = fe.operator_tables(d, space.degree)
-        geo = fe.cell_geometry(mesh)
-        topo = fe.facet_topology(mesh, part.get("exterior_mask"))
+        # set-up arithmetic (geometry, facet sort) runs on the device as torch array code; only small index arrays come back
+        det_d, jinv_d, h_d = fe.cell_geometry_device(mesh, dev)
+        topo = fe.facet_topology(mesh, part.get("exterior_mask"), device=dev)
         nc = mesh.n_cells
         self.tabs, self.n_dofs = tabs, space.n_nodes
         # geometry SoA [d*d + 2][nc]
-        g = np.empty((d * d + 2, nc))
-        g[: d * d] = geo.Jinv.reshape(nc, d * d).T
-        g[d * d], g[d * d + 1] = geo.detJ, geo.h
+        g = torch.empty((d * d + 2, nc), dtype=torch.float64, device=dev)
+        g[: d * d] = jinv_d.reshape(nc, d * d).T
+        g[d * d], g[d * d + 1] = det_d, h_d
         keep = {}
-        keep["geom"] = torch.from_numpy(np.ascontiguousarray(g)).to(dev)
+        keep["geom"] = g
         dg = space.family == "DG"
         if dg:
             keep["nbr"] = torch.from_numpy(np.ascontiguousarray(topo.neighbor.T.astype(np.int32))).to(dev)
@@ -65,7 +66,10 @@ class ThermalOperator:
         if nbf:
             keep["bf_cell"] = torch.from_numpy(topo.bnd_cell.astype(np.int32)).to(dev)
             keep["bf_facet"] = torch.from_numpy(topo.bnd_facet.astype(np.int32)).to(dev)
-            keep["bf_area"] = torch.from_numpy(fe.facet_measures(mesh, geo, topo.bnd_cell, topo.bnd_facet)).to(dev)
+            bc = torch.from_numpy(topo.bnd_cell.astype(np.int64)).to(dev)
+            geo_b = fe.CellGeometry(det_d[bc].cpu().numpy(), jinv_d[bc].cpu().numpy(), None)
+            keep["bf_area"] = torch.from_numpy(fe.facet_measures(mesh, geo_b, np.arange(nbf), topo.bnd_facet)).to(dev)
+        del det_d, jinv_d, h_d
         self._keep = keep
         # host tables (copied by the library during create)
         h = {k: np.ascontiguousarray(getattr(tabs, k), dtype=np.float64)
@@ -160,16 +164,19 @@ class ThermalOperator:
         mine = handle.raw if rc == 1 else None
         everyone = [None] * self.ctx.nranks
         dist.all_gather_object(everyone, mine)
-        if self.halo is None:
-            return
-        if all(h is not None for h in everyone):
-            blob = C.create_string_buffer(b"".join(everyone), 64 * self.ctx.nranks)
-            ok = L.sg_halo_peer_open(self.halo, blob) == 0
-        else:
-            L.sg_halo_peer_open(self.halo, None)
-            ok = False
+        # every rank runs the same two collectives, also one without a halo plan (it reports False and
+        # sg_thermal_solver_create then rejects the missing plan on that rank instead of the others hanging here)
+        ok = False
+        if self.halo is not None:
+            if all(h is not None for h in everyone):
+                blob = C.create_string_buffer(b"".join(everyone), 64 * self.ctx.nranks)
+                ok = L.sg_halo_peer_open(self.halo, blob) == 0
+            else:
+                L.sg_halo_peer_open(self.halo, None)
         flags = [None] * self.ctx.nranks
         dist.all_gather_object(flags, bool(ok and L.sg_halo_uses_peer_memory(self.halo)))
+        if self.halo is None:
+            return
         if not all(flags):                       # one rank could not map a neighbour: nobody uses the peer path
             L.sg_halo_peer_open(self.halo, None)
         self.peer_memory = bool(L.sg_halo_uses_peer_memory(self.halo))

@@ -103,3 +103,27 @@ def load_thermal_kat_p2():
                   cells=np.array(c["cells"]), dofmap=np.array(c["dofmap"]), T=arr(c["T"]), T_prev=arr(c["T_prev"]),
                   v=arr(c["v"]), residual=arr(c["residual"]), jac_x=arr(c["jac_x"])) for c in data["cases"]]
     return dict(dt=data["dt"], cases=cases)
+
+
+def stress_rounding_floor(vp, dT_nodes, xi_nodes):
+    """Rounding noise of the reference's own stress formula, per sigma node (absolute, same unit as sigma).
+
+    VM:185-191 evaluates  k_n tr(eps) / xi * lambda_n * (1.0 - taylor_n)  with  taylor_n = (1.0 + a) + 0.5 a^2,
+    a = -xi/lambda_n (VM:233-242): the sum (1.0 + a) is rounded to ulp(1) = 2.2e-16 ABSOLUTE, so the factor
+    (1 - taylor_n) ~ |a| carries a relative error of 2.2e-16/|a| whatever the inputs' accuracy.  Two
+    evaluations whose xi differ in the last bits draw that error independently; their stresses can therefore differ by
+    up to twice   sum_n |k_n tr(eps)| * min(1, 2.2e-16 * lambda_n / |xi|)   (the deviator of the isotropic strain is
+    round-off itself and adds nothing visible).  tr(eps) = -dim * alpha_solid * dT (VM:128-139).
+    Parity tests hold the stress to  max(1e-10 * max|sigma|, 2 * this floor)  — the first is north_star's bar, the second
+    the part of the difference no solver accuracy can remove.
+    """
+    import numpy as np
+    dT = np.abs(np.asarray(dT_nodes, dtype=np.float64))
+    xi = np.abs(np.asarray(xi_nodes, dtype=np.float64))
+    tr = vp.dim * vp.alpha_solid * dT
+    floor = np.zeros_like(dT)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for k_n, lam_n in zip(vp.k, vp.lambda_k):
+            # once |xi/lambda_n| < ulp the factor quantises to 0 or ulp: the term is wrong by at most itself
+            floor += abs(k_n) * tr * np.minimum(1.0, 2.220446049250313e-16 * lam_n / xi)
+    return floor

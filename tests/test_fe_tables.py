@@ -324,3 +324,24 @@ def test_p2_lattice_numbering_keeps_planes_and_runs():
     assert np.array_equal(h2[:, 2], inp // 17)                       # then z (the short axis)
     run = inp % 17
     assert np.array_equal(h2[:, 1], np.where(run < 9, 2 * run, 2 * (run - 9) + 1))   # y: 9 even half-steps, then 8 odd
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_device_side_setup_equals_the_numpy_statements(dim):
+    """fe.facet_topology / fe.cell_geometry run as torch array code (on the GPU when there is one); the numpy/LAPACK
+    statements they replaced stay as the checkers."""
+    from fem_glass_tempering_b200 import mesh as msh
+    rng = np.random.default_rng(dim)
+    m = {1: msh.graded_line_mesh(), 2: msh.rectangle_mesh(7, 5, 3.5, 2.0), 3: msh.box_mesh(4, 3, 5, 2.0, 1.5, 2.5)}[dim]
+    if dim > 1:                                     # perturb the interior so that every cell has its own geometry
+        inner = np.all((m.x > 1e-9) & (m.x < m.x.max(axis=0) - 1e-9), axis=1)
+        m.x[inner] += 0.05 * rng.uniform(-1, 1, (int(inner.sum()), dim))
+    a, b = fe.facet_topology(m, device="cpu"), fe._facet_topology_np(m)
+    for k in ("neighbor", "nb_facet", "nb_perm", "bnd_cell", "bnd_facet"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    mask = lambda mid: mid[:, 0] > 0.5 * m.x[:, 0].max()
+    a, b = fe.facet_topology(m, mask, device="cpu"), fe._facet_topology_np(m, mask)
+    assert np.array_equal(a.bnd_cell, b.bnd_cell) and np.array_equal(a.bnd_facet, b.bnd_facet)
+    g, h = fe.cell_geometry(m, device="cpu"), fe._cell_geometry_np(m)
+    assert np.allclose(g.detJ, h.detJ, rtol=1e-14, atol=0) and np.allclose(g.h, h.h, rtol=1e-15, atol=0)
+    assert np.max(np.abs(g.Jinv - h.Jinv)) <= 1e-13 * np.max(np.abs(h.Jinv))

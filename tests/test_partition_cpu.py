@@ -28,7 +28,7 @@ def field(x):
     return 700.0 + 10.0 * np.sin(0.7 * x[:, 0]) + 3.0 * x[:, 1] ** 2 + (x[:, 2] if x.shape[1] > 2 else 0.0)
 
 
-def _worker(rank, world, port, results):
+def _worker(rank, world, port, results, outdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import kernel_mirror
@@ -100,6 +100,28 @@ def _worker(rank, world, port, results):
             pts = torch.tensor([float(info["owned_cell_points"])], dtype=torch.float64)
             dist.all_reduce(pts)
             assert int(pts.item()) == gm.n_cells * space.n_ld
+            # per-rank output files (output.RankFiles): every rank writes its OWNED nodes, read_series() reassembles the
+            # unpartitioned field; the ranks never write the same file
+            from fem_glass_tempering_b200.output import RankFiles, read_series
+            assert part["global_own_offset"] == l2g[part["own_lo"]] and part["global_n_dofs"] == gs.n_nodes
+            case_dir = os.path.join(outdir, f"{family}{degree}_{dim}d")
+            fields = {"T": {"block_size": 1, "name": "T", "n_nodes": space.n_nodes},
+                      "sigma": {"block_size": dim * dim, "name": "sigma", "n_nodes": space.n_nodes}}
+            rf = RankFiles(case_dir, rank, world, fields, (part["own_lo"], part["own_hi"]), part["global_own_offset"],
+                           part["global_n_dofs"])
+            rf.save_coordinates("T", xl)
+            for step in range(2):
+                rf.save_step(step, 0.1 * step, {"T": u + step, "sigma": np.repeat(u, dim * dim) * (1 + np.tile(np.arange(dim * dim), u.size)) + step})
+            rf.close()
+            dist.barrier()
+            if rank == 0:
+                t, Tser = read_series(case_dir, "T")
+                assert np.allclose(t, [0.0, 0.1]) and Tser.shape == (2, gs.n_nodes)
+                assert np.array_equal(Tser[1], ug + 1)
+                _, Sser = read_series(case_dir, "sigma")
+                assert np.array_equal(Sser[1], np.repeat(ug, dim * dim) * (1 + np.tile(np.arange(dim * dim), ug.size)) + 1)
+                names = sorted(os.listdir(case_dir))
+                assert len(names) == len(set(names)) == world * (2 * 2 + 2)      # 2 steps x 2 fields + index + coordinates, per rank
     except Exception as e:  # noqa: BLE001
         ok = False
         results[rank] = repr(e)
@@ -110,9 +132,9 @@ def _worker(rank, world, port, results):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_slab_partition_over_gloo(world):
+def test_slab_partition_over_gloo(world, tmp_path):
     port = 29600 + world + (os.getpid() % 200)
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, results, str(tmp_path)), nprocs=world, join=True)
     assert all(results.get(r) == "ok" for r in range(world)), dict(results)
