@@ -40,6 +40,37 @@ def init_process_group(backend: str | None = None):
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(device: int) -> dict:
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node and the
+    node's cpulist), BEFORE any pinned host buffer is allocated: cudaHostAlloc'ed pages are first touched by this process,
+    so they land in memory local to the GPU's root complex.  With all ranks on node 0 the per-step device->host output
+    copies of 8 GPUs (16 GB per step) share one memory controller and one inter-socket link.  Returns what was done
+    (bench.py prints it); silently does nothing where sysfs has no answer."""
+    info = {"device": device, "numa_node": None, "cpus": None}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        info["pci"] = bdf
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(numa_node=node, cpus=len(cpus))
+    except Exception as e:  # noqa: BLE001
+        info["error"] = repr(e)[:120]
+    return info
+
+
 def make_context(rank: int, world: int, device: int) -> _lib.Context:
     """Library context with its own NCCL communicator; the unique id travels through torch.distributed."""
     if world == 1:

@@ -209,6 +209,18 @@ class ThermalOperator:
         _lib.check(_lib.lib().sg_thermal_solver_get_chebyshev(self.solver, C.byref(d), C.byref(lo), C.byref(hi)))
         return dict(degree=d.value, lo=lo.value, hi=hi.value)
 
+    def uses_graphs(self) -> bool:
+        """True when the solver replays its PCG batches as CUDA graphs (plain PCG on one GPU): CUDA-event pairs cannot sit
+        between graph nodes, so kernel timing then needs a separate profiled pass."""
+        return self.ctx.nranks == 1 and self.chebyshev_info()["degree"] == 0
+
+    def solver_description(self) -> str:
+        ci = self.chebyshev_info()
+        if ci["degree"]:
+            return (f"CG preconditioned by a degree-{ci['degree']} Chebyshev polynomial in M^-1 J on [{ci['lo']:.3g}, {ci['hi']:.3g}] "
+                    "(pcg its = outer iterations)")
+        return "CG + " + ("element-mass blocks" if self.space.family == "DG" else "point Jacobi")
+
     def class_info(self) -> dict:
         """Local-matrix classes found by the library (sg_thermal_class_info)."""
         g, s_, f = C.c_int32(0), C.c_int32(0), C.c_int32(0)

@@ -60,3 +60,22 @@ int cpu_pcg_jacobi(long n, const int32_t *indptr, const int32_t *indices, const 
     free(Ap);
     return rr > tol2 ? -1 : it;
 }
+
+/* y = A x on all threads (residual evaluation of the CPU port). */
+void cpu_spmv(long n, const int32_t *indptr, const int32_t *indices, const double *data, const double *x, double *y) {
+    spmv(n, indptr, indices, data, x, y);
+}
+
+#ifdef _OPENMP
+#include <omp.h>
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline sets its thread count explicitly and reports what it got. */
+int cpu_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+int cpu_set_threads(int n) {
+    (void)n;
+    return 1;
+}
+#endif

@@ -1,12 +1,15 @@
 """GPU end-to-end parity: ThermoViscoProblem (reference API, CUDA hot path) against the CPU oracle of the whole
 time step (oracle/reference_problem.py).
 
-Tolerances (north_star: 1e-10 relative for temperature, fictive temperature and stress histories):
-  * T, Tf, Tf_partial, phi: 1e-10 relative, asserted as such;
-  * xi and the stresses are proportional to the temperature INCREMENT of the step, so their
-    error is the thermal solve's error divided by |dT|/T ~ 1e-3..1e-4.  With the default solver settings
-    (PCG rtol 1e-8, Newton atol 1e-10) they are held to 1e-7; with tightened solves both sides sit on the
-    discrete solution and the 1e-10 bar is asserted;
+Tolerances (north_star: 1e-10 relative for temperature, fictive temperature and stress histories), all with the DEFAULT
+solver settings — the ones bench.py runs with (tools/parity_probe.py, profiles/r2a_parity_probe.jsonl is the data):
+  * T, Tf, Tf_partial: 1e-12 relative asserted (measured 1e-14..1e-13); phi 1e-10;
+  * xi: 1e-10 (it is proportional to the temperature INCREMENT of the step; measured <= 1.3e-11);
+  * stress, per node:  |sigma_gpu - sigma_oracle| <= 1e-10 * max|sigma| + 2 * floor_i, where floor_i is the rounding noise
+    of the reference's own formula lambda*(1 - taylor)/xi at that node (helpers.stress_rounding_floor): the
+    sum (1.0 + a) is rounded to ulp(1) whatever the inputs' accuracy, so two evaluations whose xi differ in the last
+    bits differ by up to that much, for ANY solver accuracy (tightening the solves 10x does not move the measured
+    differences).  The norm-wise figure max|d sigma|/max|sigma| is returned and held to 1e-9 on top (measured 4e-12..4e-10);
   * nodes whose temperature did not change this step (|dT| below 1e-6 K: 0/0 = NaN or round-off noise in the
     reference too) are excluded from the stress comparison and must be NaN or negligible.
 """
@@ -16,7 +19,7 @@ import torch
 
 from fem_glass_tempering_b200 import ThermoViscoProblem, fe
 from fem_glass_tempering_b200 import mesh as msh
-from helpers import assert_same, rel_err
+from helpers import assert_same, rel_err, stress_rounding_floor
 from oracle.reference_problem import OracleProblem
 from oracle.visco_oracle import MAIN_PARAMS
 
@@ -40,7 +43,7 @@ def cpu(F):
     return F.x.array.cpu().numpy()
 
 
-def compare_step(prob, orc, tol_T, tol_inc, tol_sigma):
+def compare_step(prob, orc, tol_T=1e-12, tol_inc=1e-10, tol_sigma=1e-10):
     f = orc.f
     assert rel_err(cpu(prob.functions_current["T"]), f["T_cur"]) <= tol_T
     assert rel_err(cpu(prob.functions_current["Tf"]), f["Tf_cur"]) <= tol_T
@@ -51,17 +54,22 @@ def compare_step(prob, orc, tol_T, tol_inc, tol_sigma):
     d = orc.d
     S = prob.functionSpaces["sigma"].scalar
     dT_at_S = np.abs(orc._T_at_sigma_points(f["T_cur"]) - orc._T_at_sigma_points(f["T_prev"]))
-    node_dT = np.zeros(S.n_nodes)
+    xi_at_S = np.abs(orc._T_at_sigma_points(f["xi"]))
+    node_dT, node_xi = np.zeros(S.n_nodes), np.zeros(S.n_nodes)
     node_dT[S.dofmap.ravel()] = dT_at_S
+    node_xi[S.dofmap.ravel()] = xi_at_S
     good = node_dT > 1e-6
     sig_g = cpu(prob.functions_next["sigma"]).reshape(-1, d * d)
     sig_o = f["sigma_next"].reshape(-1, d * d)
     scale = np.max(np.abs(sig_o[good]))
     assert np.isfinite(sig_g[good]).all() and np.isfinite(sig_o[good]).all()
-    assert np.max(np.abs(sig_g[good] - sig_o[good])) <= tol_sigma * scale
+    err = np.max(np.abs(sig_g[good] - sig_o[good]), axis=1)
+    floor = stress_rounding_floor(orc.vp, node_dT[good], node_xi[good])
+    assert np.all(err <= tol_sigma * scale + 2.0 * floor), float(np.max(err - 2.0 * floor) / scale)
+    assert np.max(err) <= 1e-9 * scale
     rest = sig_g[~good]
     assert np.all(np.isnan(rest) | (np.abs(rest) <= 1e-9))   # |sigma| ~ sum(k) * alpha_s * |dT| < 3.2e-10 there
-    return float(np.max(np.abs(sig_g[good] - sig_o[good])) / scale)
+    return float(np.max(err) / scale)
 
 
 def test_main_py_default_run(sg_ctx):
@@ -73,21 +81,10 @@ def test_main_py_default_run(sg_ctx):
         prob.t += prob.dt
         prob.solve_timestep(t=prob.t)
         orc.step()
-        worst = max(worst, compare_step(prob, orc, 1e-10, 1e-7, 1e-7))
+        worst = max(worst, compare_step(prob, orc))
         orc.end_step()
         assert_same(cpu(prob.functions_previous["T"]), cpu(prob.functions_current["T"]), "T_prev <- T_cur (TVP:378)")
     print("worst stress error (default solver settings):", worst)
-
-
-def test_main_py_run_meets_1e10_with_tight_solves(sg_ctx):
-    prob, orc = make_pair(sg_ctx, msh.graded_line_mesh(), MAIN_CONFIG)
-    prob.solver.linear_rtol = 1e-13
-    prob.solver.atol = 1e-13
-    for step in range(40):
-        prob.solve_timestep(t=0.0)
-        orc.step()
-        compare_step(prob, orc, 1e-12, 1e-10, 1e-10)
-        orc.end_step()
 
 
 @pytest.mark.parametrize("dim,config,n", [
@@ -106,14 +103,10 @@ def test_other_configs(sg_ctx, dim, config, n):
     else:
         m = msh.box_mesh(*n, *(float(k) for k in n))
     prob, orc = make_pair(sg_ctx, m, config)
-    prob.solver.linear_rtol = 1e-12
-    prob.solver.atol = 1e-12
     for step in range(8):
         prob.solve_timestep(t=0.0)
         orc.step()
-        # stress bound: the reference's lambda*(1 - taylor)/xi cancels to eps_mach/|xi/lambda| ~ 1e-16/3e-7 per term
-        # (SURVEY §7 H2), so a 1e-12 relative difference in xi re-rolls that rounding noise: 5e-9, not solver error
-        compare_step(prob, orc, 1e-11, 1e-9, 5e-9)
+        compare_step(prob, orc)
         orc.end_step()
 
 
@@ -138,7 +131,7 @@ def test_phase_methods_equal_fused_step_and_full_materialisation(sg_ctx):
                 assert_same(cpu(getattr(a, grp)[k]), cpu(getattr(b, grp)[k]), f"{grp}[{k}]")
         names = {"thermal_strain": "thermal_strain", "total_strain": "total_strain", "deviatoric_strain": "deviatoric_strain"}
         for k, o in names.items():
-            assert rel_err(cpu(a.functions[k]), orc.f[o]) <= 1e-7
+            assert rel_err(cpu(a.functions[k]), orc.f[o]) <= 1e-10
         assert rel_err(cpu(a.functions_next["T"]), orc.f["T_next"]) <= 1e-10
         orc.end_step()
 
@@ -260,10 +253,25 @@ def test_chebyshev_solver_gives_the_same_histories(sg_ctx):
     for step in range(6):
         prob.solve_timestep(t=0.0)
         orc.step()
-        assert rel_err(cpu(prob.functions_current["T"]), orc.f["T_cur"]) <= 1e-10
-        assert rel_err(cpu(prob.functions_current["Tf"]), orc.f["Tf_cur"]) <= 1e-10
+        compare_step(prob, orc)              # T, Tf, Tf_partial, phi, xi and the stress
         orc.end_step()
     assert prob._thermal_op.chebyshev_info()["degree"] == 3
+
+
+def test_bench_path_combination_on_a_coercive_plate(sg_ctx):
+    """What bench.py's headline runs — 32-cell class tiles of plate_mesh, sip_penalty 6.0, degree-4 Chebyshev with the
+    Lanczos interval, minimal materialisation, default tolerances — against the oracle, stress included."""
+    cfg = {"T": {"element": "DG", "degree": 1}, "sigma": {"element": "DG", "degree": 1}}
+    params = dict(MAIN_PARAMS, sip_penalty=6.0)
+    prob, orc = make_pair(sg_ctx, msh.plate_mesh(3, (12, 12, 4), (12.0, 12.0, 4.0)), cfg, params=params, materialize="minimal")
+    assert prob._thermal_op.set_chebyshev(4)
+    for step in range(8):
+        prob.solve_timestep(t=0.0)
+        orc.step()
+        compare_step(prob, orc)
+        orc.end_step()
+    info = prob._thermal_op.chebyshev_info()
+    assert info["degree"] == 4 and info["hi"] > info["lo"] > 0.0
 
 
 def test_corrected_physics_through_the_problem_api(sg_ctx):
@@ -296,8 +304,9 @@ def test_corrected_physics_through_the_problem_api(sg_ctx):
 def test_default_run_against_the_hand_evaluated_history(sg_ctx):
     """ThermoViscoProblem with main.py's configuration against tests/golden/main_py_history.json (first five steps of the
     reference's default run, hand-evaluated in plain Python: closed-form P1 matrices, dense Newton solves, the 16
-    expressions, last-cell-wins DG1 -> CG1).  T, Tf: 1e-10 relative; stress where the temperature moved: 1e-7 with the
-    default solver settings (same bound as test_main_py_default_run)."""
+    expressions, last-cell-wins DG1 -> CG1).  T, Tf: 1e-12 relative; stress where the temperature moved: 1e-9 norm-wise
+    (the fixture's own stress agrees with the oracle to 1e-11; the per-node bound with the rounding floor is asserted
+    against the oracle in test_main_py_default_run)."""
     from helpers import load_main_py_history
     g = load_main_py_history()
     prob = ThermoViscoProblem(mesh_path="", time=(0.0, 50.0), dt=g["dt"], config=MAIN_CONFIG, model_parameters=MAIN_PARAMS,
@@ -305,8 +314,8 @@ def test_default_run_against_the_hand_evaluated_history(sg_ctx):
     prob.setup(dirichlet_bc=False)
     for st in g["steps"]:
         prob.solve_timestep(t=0.0)
-        assert rel_err(cpu(prob.functions_current["T"]), st["T"]) <= 1e-10
-        assert rel_err(cpu(prob.functions_current["Tf"]), st["Tf"]) <= 1e-10
+        assert rel_err(cpu(prob.functions_current["T"]), st["T"]) <= 1e-12
+        assert rel_err(cpu(prob.functions_current["Tf"]), st["Tf"]) <= 1e-12
         moved = np.abs(st["T"] - st["T_prev"])[g["winner_dof"]] > 1e-6
         sig = cpu(prob.functions_next["sigma"])
-        assert np.max(np.abs(sig[moved] - st["sigma"][moved])) <= 1e-7 * np.max(np.abs(st["sigma"][moved]))
+        assert np.max(np.abs(sig[moved] - st["sigma"][moved])) <= 1e-9 * np.max(np.abs(st["sigma"][moved]))
