@@ -121,6 +121,19 @@ def ptr(t) -> int | None:
     return t.data_ptr()
 
 
+class _DevicePtrView:
+    """__cuda_array_interface__ wrapper of library-owned device memory."""
+
+    def __init__(self, address: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (address, False), "version": 3, "strides": None}
+
+
+def tensor_from_ptr(address: int, n: int, device):
+    """float64 torch view of n doubles of device memory the library owns (e.g. the IPC-exported solver workspace)."""
+    import torch
+    return torch.as_tensor(_DevicePtrView(address, n), device=device)
+
+
 def current_stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream

@@ -52,8 +52,10 @@ def bind(L) -> None:
     L.sg_halo_plan_create.argtypes = [vp, C.c_int32, C.POINTER(HaloSegmentC), C.POINTER(vp)]
     L.sg_halo_plan_destroy.argtypes = [vp]
     L.sg_halo_forward.argtypes = [vp, vp, C.c_int32, vp]
-    L.sg_halo_peer_alloc.argtypes = [vp, vp]
-    L.sg_halo_peer_open.argtypes = [vp, vp]
+    L.sg_halo_peer_alloc.argtypes = [vp, vp, C.c_int64]
+    L.sg_halo_peer_open.argtypes = [vp, vp, vp]
+    L.sg_halo_peer_workspace.argtypes = [vp]
+    L.sg_halo_peer_workspace.restype = vp
     L.sg_halo_uses_peer_memory.argtypes = [vp]
     L.sg_thermal_solver_workspace_doubles.argtypes = [vp]
     L.sg_thermal_solver_workspace_doubles.restype = C.c_int64

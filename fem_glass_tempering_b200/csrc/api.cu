@@ -1,6 +1,7 @@
 // Context, error reporting and NCCL binding of libsurroglas_b200.
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "sg_common.cuh"
 #include "sg_nccl.h"
@@ -11,6 +12,15 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
 void sg_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sg_next_sweep_dir() {
+    static const bool on = [] {
+        const char *e = getenv("SG_SERPENTINE");
+        return !(e && e[0] == '0');
+    }();
+    static std::atomic<unsigned> n{0};
+    return on ? (int)(n.fetch_add(1u, std::memory_order_relaxed) & 1u) : 0;
+}
 
 void sg_set_error(const char *fmt, ...) {
     va_list ap;

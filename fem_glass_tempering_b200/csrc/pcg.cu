@@ -48,7 +48,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NR], const Red red, doub
 __device__ __forceinline__ bool owned(long i, long lo, long hi) { return i >= lo && i < hi; }
 
 // x = 0, r = b, p = z = dinv*r ; S[0] = r.z, S[1] = r.r ; resets the control block
-__global__ void __launch_bounds__(VB) k_pcg_init(long n, long lo, long hi, const double *__restrict__ b,
+__global__ void __launch_bounds__(VB) k_pcg_init(long i0, long i1, long lo, long hi, const double *__restrict__ b,
                                                  const double *__restrict__ dinv, double *__restrict__ x,
                                                  double *__restrict__ r, double *__restrict__ p, Red red, double *S,
                                                  PcgCtrl *ctrl) {
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(VB) k_pcg_init(long n, long lo, long hi, const
         ctrl->rr = 0.0;
     }
     double acc[2] = {0.0, 0.0};
-    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
+    for (long i = i0 + (long)blockIdx.x * VB + threadIdx.x; i < i1; i += (long)gridDim.x * VB) {
         const double ri = b[i], zi = dinv[i] * ri;
         x[i] = 0.0;
         r[i] = ri;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(VB) k_pcg_init(long n, long lo, long hi, const
 }
 
 // alpha = rz/pAp ; x += alpha p ; r -= alpha Ap ; Snext = {r.(dinv r), r.r}
-__global__ void __launch_bounds__(VB) k_update_xr(long n, long lo, long hi, const double *__restrict__ p,
+__global__ void __launch_bounds__(VB) k_update_xr(long i0, long i1, long lo, long hi, const double *__restrict__ p,
                                                   const double *__restrict__ Ap, const double *__restrict__ dinv,
                                                   double *__restrict__ x, double *__restrict__ r, Red red,
                                                   const double *Scur, const double *SpAp, double *Snext,
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(VB) k_update_xr(long n, long lo, long hi, cons
     if (ctrl->done) return;
     const double alpha = Scur[0] / (SpAp[0] + SpAp[1]);
     double acc[2] = {0.0, 0.0};
-    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
+    for (long i = i0 + (long)blockIdx.x * VB + threadIdx.x; i < i1; i += (long)gridDim.x * VB) {
         x[i] += alpha * p[i];
         const double ri = r[i] - alpha * Ap[i];
         r[i] = ri;
@@ -120,13 +120,13 @@ __device__ __forceinline__ void pcg_check(PcgCtrl *ctrl, const double *Snext, do
 }
 
 // beta = rz_new/rz ; p = dinv r + beta p ; flags convergence for the launches that follow
-__global__ void __launch_bounds__(VB) k_update_p(long n, const double *__restrict__ r, const double *__restrict__ dinv,
+__global__ void __launch_bounds__(VB) k_update_p(long n, long i0, long i1, const double *__restrict__ r, const double *__restrict__ dinv,
                                                  double *__restrict__ p, double *__restrict__ Ap, const double *Scur,
                                                  const double *Snext, PcgCtrl *ctrl) {
     if (ctrl->done) return;
     const double beta = Snext[0] / Scur[0];
     for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
-        p[i] = dinv[i] * r[i] + beta * p[i];
+        if (i >= i0 && i < i1) p[i] = dinv[i] * r[i] + beta * p[i];   // ghost rows of p belong to the neighbour's put
         Ap[i] = 0.0;     // the next operator apply scatters into Ap (RED.ADD): zero it here instead of a memset launch
     }
     // every block has read `done` before block 0 can change it?  No ordering is needed: a block that
@@ -139,10 +139,10 @@ __global__ void __launch_bounds__(VB) k_invert(long n, double *__restrict__ d) {
 }
 
 // T -= dx ; out = |dx|^2 over owned dofs
-__global__ void __launch_bounds__(VB) k_newton_update(long n, long lo, long hi, double *__restrict__ T,
+__global__ void __launch_bounds__(VB) k_newton_update(long i0, long i1, long lo, long hi, double *__restrict__ T,
                                                       const double *__restrict__ dx, Red red, double *out) {
     double acc[1] = {0.0};
-    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB) {
+    for (long i = i0 + (long)blockIdx.x * VB + threadIdx.x; i < i1; i += (long)gridDim.x * VB) {
         const double d = dx[i];
         T[i] -= d;
         if (owned(i, lo, hi)) acc[0] += d * d;
@@ -197,7 +197,7 @@ __device__ __forceinline__ void st_row(double *__restrict__ p, const double (&v)
 }
 
 template <int NLD>
-__global__ void __launch_bounds__(VB) k_pcg_init_blk(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
+__global__ void __launch_bounds__(VB) k_pcg_init_blk(const __grid_constant__ MassInv<NLD> mi, int rev, long c0, long c1, long clo, long chi,
                                                      const double *__restrict__ detJ, const double *__restrict__ b,
                                                      double *__restrict__ x, double *__restrict__ r,
                                                      double *__restrict__ p, Red red, double *S, PcgCtrl *ctrl) {
@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(VB) k_pcg_init_blk(const __grid_constant__ Mas
         ctrl->rr = 0.0;
     }
     double acc[2] = {0.0, 0.0};
-    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
+    long c, cstep;
+    sg_sweep_begin(c0, c1, VB, rev, c, cstep);
+    for (; c >= c0 && c < c1; c += cstep) {
         double rk[NLD], zk[NLD], zero[NLD];
         ld_row<NLD>(b + c * NLD, rk);
         mass_solve<NLD>(mi, 1.0 / detJ[c], rk, zk);
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(VB) k_pcg_init_blk(const __grid_constant__ Mas
 }
 
 template <int NLD>
-__global__ void __launch_bounds__(VB) k_update_xr_blk(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
+__global__ void __launch_bounds__(VB) k_update_xr_blk(const __grid_constant__ MassInv<NLD> mi, int rev, long c0, long c1, long clo, long chi,
                                                       const double *__restrict__ detJ, const double *__restrict__ p,
                                                       const double *__restrict__ Ap, double *__restrict__ x,
                                                       double *__restrict__ r, Red red, const double *Scur,
@@ -236,7 +238,9 @@ __global__ void __launch_bounds__(VB) k_update_xr_blk(const __grid_constant__ Ma
     if (ctrl->done) return;
     const double alpha = Scur[0] / (SpAp[0] + SpAp[1]);
     double acc[2] = {0.0, 0.0};
-    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
+    long c, cstep;
+    sg_sweep_begin(c0, c1, VB, rev, c, cstep);
+    for (; c >= c0 && c < c1; c += cstep) {
         double pk[NLD], ak[NLD], xk[NLD], rk[NLD], zk[NLD];
         ld_row<NLD>(p + c * NLD, pk);
         ld_row<NLD>(Ap + c * NLD, ak);
@@ -263,13 +267,15 @@ __global__ void __launch_bounds__(VB) k_update_xr_blk(const __grid_constant__ Ma
 }
 
 template <int NLD>
-__global__ void __launch_bounds__(VB) k_update_p_blk(const __grid_constant__ MassInv<NLD> mi, long n_cells,
+__global__ void __launch_bounds__(VB) k_update_p_blk(const __grid_constant__ MassInv<NLD> mi, int rev, long c0, long c1,
                                                      const double *__restrict__ detJ, const double *__restrict__ r,
                                                      double *__restrict__ p, const double *Scur, const double *Snext,
                                                      PcgCtrl *ctrl) {
     if (ctrl->done) return;
     const double beta = Snext[0] / Scur[0];
-    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
+    long c, cstep;
+    sg_sweep_begin(c0, c1, VB, rev, c, cstep);
+    for (; c >= c0 && c < c1; c += cstep) {
         double rk[NLD], zk[NLD], pk[NLD];
         ld_row<NLD>(r + c * NLD, rk);
         ld_row<NLD>(p + c * NLD, pk);
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(VB) k_update_p_blk(const __grid_constant__ Mas
 //   x,r:    x += alpha p, r -= alpha Ap, z1 = M^-1 r / theta, |r|^2
 //   p:      p = z + beta p
 template <int NLD>
-__global__ void __launch_bounds__(VB) k_pcg_init_cheb(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
+__global__ void __launch_bounds__(VB) k_pcg_init_cheb(const __grid_constant__ MassInv<NLD> mi, int rev, long c0, long c1, long clo, long chi,
                                                       const double *__restrict__ detJ, const double *__restrict__ b,
                                                       double *__restrict__ x, double *__restrict__ r, double *__restrict__ z1,
                                                       double inv_theta, Red red, double *S1, PcgCtrl *ctrl) {
@@ -298,7 +304,9 @@ __global__ void __launch_bounds__(VB) k_pcg_init_cheb(const __grid_constant__ Ma
         ctrl->rr = 0.0;
     }
     double acc[1] = {0.0};
-    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
+    long c, cstep;
+    sg_sweep_begin(c0, c1, VB, rev, c, cstep);
+    for (; c >= c0 && c < c1; c += cstep) {
         double rk[NLD], zk[NLD], zero[NLD];
         ld_row<NLD>(b + c * NLD, rk);
         mass_solve<NLD>(mi, inv_theta / detJ[c], rk, zk);
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(VB) k_pcg_init_cheb(const __grid_constant__ Ma
 }
 
 template <int NLD>
-__global__ void __launch_bounds__(VB) k_update_xr_cheb(const __grid_constant__ MassInv<NLD> mi, long n_cells, long clo, long chi,
+__global__ void __launch_bounds__(VB) k_update_xr_cheb(const __grid_constant__ MassInv<NLD> mi, int rev, long c0, long c1, long clo, long chi,
                                                        const double *__restrict__ detJ, const double *__restrict__ p,
                                                        const double *__restrict__ Ap, double *__restrict__ x,
                                                        double *__restrict__ r, double *__restrict__ z1, double inv_theta,
@@ -325,7 +333,9 @@ __global__ void __launch_bounds__(VB) k_update_xr_cheb(const __grid_constant__ M
     if (ctrl->done) return;
     const double alpha = Scur[0] / (SpAp[0] + SpAp[1]);
     double acc[1] = {0.0};
-    for (long c = (long)blockIdx.x * VB + threadIdx.x; c < n_cells; c += (long)gridDim.x * VB) {
+    long c, cstep;
+    sg_sweep_begin(c0, c1, VB, rev, c, cstep);
+    for (; c >= c0 && c < c1; c += cstep) {
         double pk[NLD], ak[NLD], xk[NLD], rk[NLD], zk[NLD];
         ld_row<NLD>(p + c * NLD, pk);
         ld_row<NLD>(Ap + c * NLD, ak);
@@ -353,22 +363,24 @@ __global__ void k_pcg_check(PcgCtrl *ctrl, const double *Snext, double tol2, int
 }
 
 // p = z + beta p, beta = Snext[0]/Scur[0]  (first == 1: p = z)
-__global__ void __launch_bounds__(VB) k_axpy_p(long n, const double *__restrict__ z, double *__restrict__ p, const double *Scur,
-                                               const double *Snext, int first, const PcgCtrl *ctrl) {
+__global__ void __launch_bounds__(VB) k_axpy_p(long n, int rev, const double *__restrict__ z, double *__restrict__ p, const double *Scur,
+                                               const double *Snext, int first, const PcgCtrl *ctrl) {   // z, p: first row of the range
     if (ctrl->done) return;
     const double beta = first ? 0.0 : Snext[0] / Scur[0];
     const long n2 = ((((uintptr_t)z | (uintptr_t)p) & 15) == 0) ? n >> 1 : 0;   // workspace slices start at odd dofs when n is odd
     const double2 *z2 = reinterpret_cast<const double2 *>(z);
     double2 *p2 = reinterpret_cast<double2 *>(p);
-    for (long i = (long)blockIdx.x * VB + threadIdx.x; i < n2; i += (long)gridDim.x * VB) {
+    long i, istep;
+    sg_sweep_begin(0, n2, VB, rev, i, istep);
+    for (; i >= 0 && i < n2; i += istep) {
         const double2 a = z2[i];
         double2 q = first ? make_double2(0.0, 0.0) : p2[i];
         q.x = a.x + beta * q.x;
         q.y = a.y + beta * q.y;
         p2[i] = q;
     }
-    for (long i = 2 * n2 + (long)blockIdx.x * VB + threadIdx.x; i < n; i += (long)gridDim.x * VB)
-        p[i] = z[i] + (first ? 0.0 : beta * p[i]);
+    for (long j = 2 * n2 + (long)blockIdx.x * VB + threadIdx.x; j < n; j += (long)gridDim.x * VB)
+        p[j] = z[j] + (first ? 0.0 : beta * p[j]);
 }
 
 // deterministic pseudo-random start vector in (-1, 1) from the GLOBAL dof index (same field for every partition)
@@ -458,15 +470,14 @@ struct sg_thermal_solver {
     cudaGraphExec_t batch_graph;
     const double *graph_T, *graph_x;
     int use_graphs;
-    int overlap;       // SG_OVERLAP=1: overlap the peer-memory halo exchange with the interior cells.  Off by default:
-                       // measured slower on 2 B200 (27.7 vs 26.4 ms/step on C3) — the second launch per operator
-                       // application costs more than the rank-to-rank skew it hides
 };
 
 namespace {
 
+// Cross-rank sum of `count` doubles the kernel launched just before has reduced.  On the peer-memory path that kernel's
+// last block already did it (SgRed::peer, sg_grid_reduce), so this is a no-op; NCCL otherwise.
 int allreduce(sg_thermal_solver *s, double *ptr, int count, cudaStream_t st) {
-    if (s->ctx->nranks == 1) return SG_OK;
+    if (s->ctx->nranks == 1 || s->red.peer) return SG_OK;
     if (s->halo && sg_peer_ready(s->halo->peer)) return sg_peer_allreduce(s->halo->peer, ptr, count, st);
     SG_CHECK_NCCL(sg_nccl()->AllReduce(ptr, ptr, (size_t)count, ncclDouble, ncclSum, s->ctx->comm, st));
     return SG_OK;
@@ -482,6 +493,15 @@ int read_scalars(sg_thermal_solver *s, int first, int count, cudaStream_t st) {
     return SG_OK;
 }
 
+// Start the ghost-row exchange of a solver vector.  Peer path: one put kernel, *wait describes what the consumer has to
+// wait for (inside its kernel where supported).  NCCL path: grouped send/recv, complete in stream order.
+int halo_start(sg_thermal_solver *s, double *vec, SgHaloWait *wait, cudaStream_t st) {
+    memset(wait, 0, sizeof(*wait));
+    if (!s->halo) return SG_OK;
+    if (sg_peer_ready(s->halo->peer)) return sg_peer_put(s->halo->peer, s->halo->n, s->halo->seg, vec, wait, st);
+    return sg_halo_forward(s->halo, vec, 1, st);
+}
+
 template <int NLD>
 MassInv<NLD> mass_inv_of(const sg_thermal_solver *s) {
     MassInv<NLD> mi;
@@ -491,7 +511,7 @@ MassInv<NLD> mass_inv_of(const sg_thermal_solver *s) {
 
 template <int NLD>
 int blk_init(sg_thermal_solver *s, const double *b, double *x, cudaStream_t st) {
-    k_pcg_init_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, b, x, s->r,
+    k_pcg_init_blk<NLD><<<vgrid(s->chi - s->clo), VB, 0, st>>>(mass_inv_of<NLD>(s), sg_next_sweep_dir(), s->clo, s->chi, s->clo, s->chi, s->detJ, b, x, s->r,
                                                          s->p, s->red, s->S, s->ctrl);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
@@ -499,7 +519,7 @@ int blk_init(sg_thermal_solver *s, const double *b, double *x, cudaStream_t st) 
 }
 template <int NLD>
 int blk_update_xr(sg_thermal_solver *s, double *x, const double *Scur, double *Snext, cudaStream_t st) {
-    k_update_xr_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, s->p, s->Ap,
+    k_update_xr_blk<NLD><<<vgrid(s->chi - s->clo), VB, 0, st>>>(mass_inv_of<NLD>(s), sg_next_sweep_dir(), s->clo, s->chi, s->clo, s->chi, s->detJ, s->p, s->Ap,
                                                           x, s->r, s->red, Scur, s->S + 4, Snext, s->ctrl);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
@@ -507,7 +527,7 @@ int blk_update_xr(sg_thermal_solver *s, double *x, const double *Scur, double *S
 }
 template <int NLD>
 int blk_update_p(sg_thermal_solver *s, const double *Scur, const double *Snext, cudaStream_t st) {
-    k_update_p_blk<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->detJ, s->r, s->p, Scur, Snext,
+    k_update_p_blk<NLD><<<vgrid(s->chi - s->clo), VB, 0, st>>>(mass_inv_of<NLD>(s), sg_next_sweep_dir(), s->clo, s->chi, s->detJ, s->r, s->p, Scur, Snext,
                                                          s->ctrl);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
@@ -526,7 +546,7 @@ int blk_update_p(sg_thermal_solver *s, const double *Scur, const double *Snext, 
 
 template <int NLD>
 int blk_init_cheb(sg_thermal_solver *s, const double *b, double *x, double inv_theta, cudaStream_t st) {
-    k_pcg_init_cheb<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, b, x, s->r,
+    k_pcg_init_cheb<NLD><<<vgrid(s->chi - s->clo), VB, 0, st>>>(mass_inv_of<NLD>(s), sg_next_sweep_dir(), s->clo, s->chi, s->clo, s->chi, s->detJ, b, x, s->r,
                                                           s->zA, inv_theta, s->red, s->S + 1, s->ctrl);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
@@ -534,7 +554,7 @@ int blk_init_cheb(sg_thermal_solver *s, const double *b, double *x, double inv_t
 }
 template <int NLD>
 int blk_update_xr_cheb(sg_thermal_solver *s, double *x, double inv_theta, const double *Scur, double *Snext, cudaStream_t st) {
-    k_update_xr_cheb<NLD><<<vgrid(s->n_cells), VB, 0, st>>>(mass_inv_of<NLD>(s), s->n_cells, s->clo, s->chi, s->detJ, s->p, s->Ap,
+    k_update_xr_cheb<NLD><<<vgrid(s->chi - s->clo), VB, 0, st>>>(mass_inv_of<NLD>(s), sg_next_sweep_dir(), s->clo, s->chi, s->clo, s->chi, s->detJ, s->p, s->Ap,
                                                            x, s->r, s->zA, inv_theta, s->red, Scur, s->S + 4, Snext + 1, s->ctrl);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
@@ -563,7 +583,7 @@ int estimate_spectrum(sg_thermal_solver *s, const double *T_lin, cudaStream_t st
     int rc;
     double *S = s->S;
     double *rhs = s->zA, *xs = s->zB;
-    k_hash_fill<<<vgrid(s->n), VB, 0, st>>>(s->n, 0, s->lo, s->hi, rhs, s->red, S + 7);
+    k_hash_fill<<<vgrid(s->n), VB, 0, st>>>(s->n, 0, s->lo, s->hi, rhs, sg_red_local(s->red), S + 7);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     SG_BLK_DISPATCH(blk_init, s, rhs, xs, st);
@@ -578,8 +598,9 @@ int estimate_spectrum(sg_thermal_solver *s, const double *T_lin, cudaStream_t st
     int m = 0;
     for (int it = 0; it < LANCZOS; ++it) {
         double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
-        if (s->halo && (rc = sg_halo_forward(s->halo, s->p, 1, st))) return rc;
-        if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, nullptr, st))) return rc;
+        SgHaloWait hw;
+        if ((rc = halo_start(s, s->p, &hw, st))) return rc;
+        if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, nullptr, st, 0, &hw))) return rc;
         if ((rc = allreduce(s, S + 4, 2, st))) return rc;
         SG_BLK_DISPATCH(blk_update_xr, s, xs, Scur, Snext, st);
         if (rc) return rc;
@@ -684,31 +705,17 @@ int pcg_run_cheb(sg_thermal_solver *s, const double *T_lin, const double *b, dou
     const int *skip = &s->ctrl->done;
     // z = q_k(M^-1 J) M^-1 r from z1 (in zA); the result's address depends on the parity of k
     double *zfinal = (k % 2 == 0) ? s->zA : s->zB;
-    // Optional (SG_OVERLAP=1, see sg_thermal_solver::overlap): the ghost rows of the input vector are pushed to the
-    // neighbours, the cells WITHOUT ghost neighbours (all but the two boundary columns) are processed while the
-    // neighbours' rows travel, and only the boundary strips wait for them.
-    const bool overlap = s->halo && sg_peer_ready(s->halo->peer) && sg_thermal_can_split(s->op) && s->overlap;
-    auto exchange_and = [&](double *vec, auto &&launch) -> int {     // launch(part) -> rc
-        int r2;
-        if (!s->halo) return launch(SG_PART_ALL);
-        if (!overlap) {
-            if ((r2 = sg_halo_forward(s->halo, vec, 1, st))) return r2;
-            return launch(SG_PART_ALL);
-        }
-        if ((r2 = sg_peer_halo_push(s->halo->peer, s->halo->n, s->halo->seg, vec, st))) return r2;
-        if ((r2 = launch(SG_PART_INTERIOR))) return r2;
-        if ((r2 = sg_peer_halo_pull(s->halo->peer, s->halo->n, s->halo->seg, vec, st))) return r2;
-        return launch(SG_PART_BOUNDARY);
-    };
+    // Partitioned mesh: the ghost rows of every input vector are put straight into the neighbours' vectors (one small
+    // kernel) and the consuming kernel waits for them only before its two boundary strips (peer.cu).
     auto precondition = [&](double *Srz) -> int {
         double *zin = s->zA, *zother = s->zB;
         for (int j = 0; j < k; ++j) {
             // z_{j+1} overwrites z_{j-1} (which lives in `zother`; for j = 0 there is no z_0 and zother is free)
-            const int r2 = exchange_and(zin, [&](int part) {
-                SgChebStep cs{zin, s->r, j == 0 ? nullptr : zother, zother, ca[j], cb[j], j == k - 1 ? 1 : 0, part};
-                return sg_thermal_cheb_step(s->op, cs, s->red, Srz, skip, st);
-            });
+            SgHaloWait hw;
+            int r2 = halo_start(s, zin, &hw, st);
             if (r2) return r2;
+            SgChebStep cs{zin, s->r, j == 0 ? nullptr : zother, zother, ca[j], cb[j], j == k - 1 ? 1 : 0, &hw};
+            if ((r2 = sg_thermal_cheb_step(s->op, cs, s->red, Srz, skip, st))) return r2;
             double *t = zin;
             zin = zother;
             zother = t;
@@ -718,7 +725,7 @@ int pcg_run_cheb(sg_thermal_solver *s, const double *T_lin, const double *b, dou
     if (!done) {
         if ((rc = sg_thermal_linearize(s->op, T_lin, st))) return rc;
         if ((rc = precondition(S))) return rc;
-        k_axpy_p<<<g, VB, 0, st>>>(s->n, zfinal, s->p, S, S, 1, s->ctrl);
+        k_axpy_p<<<g, VB, 0, st>>>(s->hi - s->lo, sg_next_sweep_dir(), zfinal + s->lo, s->p + s->lo, S, S, 1, s->ctrl);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
     }
@@ -726,10 +733,9 @@ int pcg_run_cheb(sg_thermal_solver *s, const double *T_lin, const double *b, dou
         const int nb = (max_it - it < CHEB_BATCH) ? max_it - it : CHEB_BATCH;
         for (int q = 0; q < nb; ++q, ++it) {
             double *Scur = S + 2 * (it & 1), *Snext = S + 2 * ((it + 1) & 1);
-            if ((rc = exchange_and(s->p, [&](int part) {
-                     return sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, skip, st, 0, part);
-                 })))
-                return rc;
+            SgHaloWait hw;
+            if ((rc = halo_start(s, s->p, &hw, st))) return rc;
+            if ((rc = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, skip, st, 0, &hw))) return rc;
             if ((rc = allreduce(s, S + 4, 2, st))) return rc;
             SG_BLK_DISPATCH(blk_update_xr_cheb, s, x, inv_theta, Scur, Snext, st);
             if (rc) return rc;
@@ -737,7 +743,7 @@ int pcg_run_cheb(sg_thermal_solver *s, const double *T_lin, const double *b, dou
             k_pcg_check<<<1, 1, 0, st>>>(s->ctrl, Snext, tol2, it);
             SG_CHECK_CUDA(cudaGetLastError());
             if ((rc = precondition(Snext))) return rc;
-            k_axpy_p<<<g, VB, 0, st>>>(s->n, zfinal, s->p, Scur, Snext, 0, s->ctrl);
+            k_axpy_p<<<g, VB, 0, st>>>(s->hi - s->lo, sg_next_sweep_dir(), zfinal + s->lo, s->p + s->lo, Scur, Snext, 0, s->ctrl);
             SG_CHECK_CUDA(cudaGetLastError());
             sg_count_launch(2);
         }
@@ -796,8 +802,8 @@ int sg_halo_plan_destroy(sg_halo_plan *plan) {
 
 // Peer-memory path: returns 1 and fills handle64 when this plan can use it (at most one neighbour below and one
 // above this rank), 0 otherwise.  The caller gathers the 64-byte handles of all ranks and calls sg_halo_peer_open.
-int sg_halo_peer_alloc(sg_halo_plan *plan, void *handle64) {
-    SG_REQUIRE(plan && handle64, "sg_halo_peer_alloc: NULL argument");
+int sg_halo_peer_alloc(sg_halo_plan *plan, void *handle64, int64_t workspace_doubles) {
+    SG_REQUIRE(plan && handle64 && workspace_doubles >= 0, "sg_halo_peer_alloc: bad argument");
     if (plan->ctx->nranks < 2 || plan->n > 2) return 0;
     int below = 0, above = 0;
     int64_t mx = 0;
@@ -808,7 +814,7 @@ int sg_halo_peer_alloc(sg_halo_plan *plan, void *handle64) {
     }
     if (below > 1 || above > 1) return 0;
     if (plan->peer) return 0;
-    const int rc = sg_peer_create(plan->ctx, (size_t)mx, &plan->peer, handle64);
+    const int rc = sg_peer_create(plan->ctx, (size_t)mx, (size_t)workspace_doubles, &plan->peer, handle64);
     if (rc != SG_OK) {
         plan->peer = nullptr;
         return rc;
@@ -817,15 +823,15 @@ int sg_halo_peer_alloc(sg_halo_plan *plan, void *handle64) {
 }
 
 // handles == NULL: some rank could not allocate; drop the peer path everywhere (NCCL stays in use).
-int sg_halo_peer_open(sg_halo_plan *plan, const void *handles) {
+int sg_halo_peer_open(sg_halo_plan *plan, const void *handles, const int64_t *layout3) {
     SG_REQUIRE(plan, "sg_halo_peer_open: NULL plan");
     if (!plan->peer) return SG_OK;
-    if (!handles) {
+    if (!handles || !layout3) {
         sg_peer_destroy(plan->peer);
         plan->peer = nullptr;
         return SG_OK;
     }
-    const int rc = sg_peer_open(plan->peer, handles);
+    const int rc = sg_peer_open(plan->peer, handles, layout3);
     if (rc != SG_OK) {
         sg_peer_destroy(plan->peer);
         plan->peer = nullptr;
@@ -834,6 +840,8 @@ int sg_halo_peer_open(sg_halo_plan *plan, const void *handles) {
 }
 
 int sg_halo_uses_peer_memory(const sg_halo_plan *plan) { return plan && sg_peer_ready(plan->peer) ? 1 : 0; }
+
+double *sg_halo_peer_workspace(const sg_halo_plan *plan) { return plan ? sg_peer_workspace(plan->peer) : nullptr; }
 
 int sg_halo_forward(sg_halo_plan *plan, double *vec, int32_t bs, void *stream) {
     SG_REQUIRE(plan && vec && bs >= 1, "sg_halo_forward: bad argument");
@@ -896,6 +904,9 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     s->cheb_failed = 0;
     s->red.partials = nullptr;
     s->red.counter = nullptr;
+    s->red.peer = nullptr;
+    s->red.ar_ptr = nullptr;
+    s->red.ar_count = 0;
     s->S = nullptr;
     s->S_host = nullptr;
     s->ctrl = s->ctrl_host = nullptr;
@@ -904,9 +915,8 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     s->batch_graph = nullptr;
     s->graph_T = s->graph_x = nullptr;
     {
-        const char *ng = getenv("SG_NO_GRAPHS"), *ov = getenv("SG_OVERLAP");
+        const char *ng = getenv("SG_NO_GRAPHS");
         s->use_graphs = !(ng && ng[0] == '1');
-        s->overlap = ov && ov[0] == '1';
     }
     cudaError_t e = cudaMalloc(&s->red.partials, sizeof(double) * (SG_MAX_BLOCKS * 2 + 2));
     if (e == cudaSuccess) e = cudaMalloc(&s->red.counter, sizeof(unsigned));
@@ -925,6 +935,9 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
         sg_thermal_solver_destroy(s);
         return SG_E_CUDA;
     }
+    // peer-memory path: all-reduces run inside the reducing kernels; the direct halo put needs the workspace to be the
+    // IPC-visible one (sg_halo_peer_workspace) — any other workspace still works through the mailboxes
+    if (halo && sg_peer_ready(halo->peer)) s->red.peer = sg_peer_red_dev(halo->peer);
     *out = s;
     return SG_OK;
 }
@@ -1000,7 +1013,7 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
         SG_BLK_DISPATCH(blk_init, s, b, x, st);
         if (rc) return rc;
     } else {
-        k_pcg_init<<<g, VB, 0, st>>>(n, lo, hi, b, s->dinv, x, s->r, s->p, s->red, S, s->ctrl);
+        k_pcg_init<<<g, VB, 0, st>>>(lo, hi, lo, hi, b, s->dinv, x, s->r, s->p, s->red, S, s->ctrl);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
     }
@@ -1027,15 +1040,16 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
     auto enqueue_iteration = [&](int parity) -> int {
         double *Scur = S + 2 * parity, *Snext = S + 2 * (1 - parity);
         int r2;
-        if (s->halo && (r2 = sg_halo_forward(s->halo, s->p, 1, st))) return r2;
-        if ((r2 = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, &s->ctrl->done, st, !s->blk_nld))) return r2;
+        SgHaloWait hw;
+        if ((r2 = halo_start(s, s->p, &hw, st))) return r2;
+        if ((r2 = sg_thermal_apply_dot(s->op, T_lin, s->p, s->Ap, s->red, S + 4, &s->ctrl->done, st, !s->blk_nld, &hw))) return r2;
         if ((r2 = allreduce(s, S + 4, 2, st))) return r2;
         if (s->blk_nld) {
             int rc;
             SG_BLK_DISPATCH(blk_update_xr, s, x, Scur, Snext, st);
             if (rc) return rc;
         } else {
-            k_update_xr<<<g, VB, 0, st>>>(n, lo, hi, s->p, s->Ap, s->dinv, x, s->r, s->red, Scur, S + 4, Snext, s->ctrl);
+            k_update_xr<<<g, VB, 0, st>>>(lo, hi, lo, hi, s->p, s->Ap, s->dinv, x, s->r, s->red, Scur, S + 4, Snext, s->ctrl);
             SG_CHECK_CUDA(cudaGetLastError());
             sg_count_launch();
         }
@@ -1045,7 +1059,7 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
             SG_BLK_DISPATCH(blk_update_p, s, Scur, Snext, st);
             if (rc) return rc;
         } else {
-            k_update_p<<<g, VB, 0, st>>>(n, s->r, s->dinv, s->p, s->Ap, Scur, Snext, s->ctrl);
+            k_update_p<<<g, VB, 0, st>>>(n, lo, hi, s->r, s->dinv, s->p, s->Ap, Scur, Snext, s->ctrl);
             SG_CHECK_CUDA(cudaGetLastError());
             sg_count_launch();
         }
@@ -1145,7 +1159,7 @@ int sg_thermal_timestep(sg_thermal_solver *s, double *T, const double *T_prev, c
         F_prev = s->last_rhs_norm;
         lin_total += lin_it;
         if (rc) return rc;
-        k_newton_update<<<g, VB, 0, st>>>(n, s->lo, s->hi, T, s->dx, s->red, s->S + 6);  // T <- T - dx
+        k_newton_update<<<g, VB, 0, st>>>(s->lo, s->hi, s->lo, s->hi, T, s->dx, s->red, s->S + 6);  // T <- T - dx (owned rows)
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
         if ((rc = allreduce(s, s->S + 6, 1, st))) return rc;

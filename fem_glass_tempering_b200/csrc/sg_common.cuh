@@ -33,11 +33,46 @@ struct SgOpInfo {
 };
 void sg_op_info(const sg_thermal_op *op, SgOpInfo *info);
 
+// NVLink peer-memory all-reduce performed INSIDE the reducing kernel (peer.cu owns the memory): the last block of
+// sg_grid_reduce writes its <= 4 totals + a sequence tag into slot [rank] of every rank's communication block, waits for
+// all tags of this round, and sums the slots in rank order — deterministic and bit-identical on every rank.  The
+// sequence number lives in device memory (every rank runs the same reducing kernels in the same order), slots are
+// double-buffered by its parity (a rank can be at most one reduction ahead of the slowest one).
+constexpr int SG_PEER_MAX_RANKS = 16;
+constexpr int SG_PEER_RED_VALS = 4;
+struct SgPeerRedDev {
+    char *base[SG_PEER_MAX_RANKS];   // every rank's block (base[rank] is local)
+    size_t tags_off, vals_off;        // [2 parities][SG_PEER_MAX_RANKS] u64 / [2][SG_PEER_MAX_RANKS][SG_PEER_RED_VALS] f64
+    int rank, nranks;
+    unsigned long long *seq;          // local device counter of the reductions done so far
+    int *err;                         // mapped host memory: set when a wait timed out
+};
+
 // Grid-wide deterministic reduction scratch: per-block partials + a completion counter (see sg_grid_reduce).
 constexpr int SG_MAX_BLOCKS = 1184;  // 8 * 148 resident blocks; kernels that reduce are grid-stride beyond that
 struct SgRed {
     double *partials;   // [SG_MAX_BLOCKS * 2]
     unsigned *counter;  // zero between kernels
+    // multi-GPU: when set, the last block all-reduces ar_count doubles at ar_ptr over the ranks after storing its totals
+    // (ar_ptr == NULL: the totals just stored).  ar_ptr may cover a value an EARLIER kernel of the stream left next to them.
+    const SgPeerRedDev *peer;
+    double *ar_ptr;
+    int ar_count;
+};
+inline SgRed sg_red_local(SgRed r) {   // the same scratch without the cross-rank step
+    r.peer = nullptr;
+    r.ar_ptr = nullptr;
+    r.ar_count = 0;
+    return r;
+}
+
+// Ghost rows written directly into this rank's vector by its slab neighbours (peer.cu sg_peer_put): the consumer kernel
+// waits until flag[i] >= seq before it touches cells/rows that read ghost values.  n == 0: nothing to wait for.
+struct SgHaloWait {
+    const unsigned long long *flag[2];
+    unsigned long long seq;
+    int *err;      // mapped host memory
+    int n;
 };
 
 // y = J(T_lin) x fused with the owned-dof dot product: dot2[0] + dot2[1] = sum over owned dofs of x*y
@@ -45,13 +80,10 @@ struct SgRed {
 // Must precede sg_thermal_apply_dot whenever T_lin changed (refreshes the linearised boundary matrices).
 int sg_thermal_linearize(sg_thermal_op *op, const double *T_lin, cudaStream_t st);
 // y_is_zero: the caller guarantees y == 0 on entry (CG spaces scatter into y; saves the memset launch).
-// part (DG class kernels on a partitioned mesh, see sg_thermal_can_split): SG_PART_ALL, or SG_PART_INTERIOR (cells
-// without ghost neighbours: may run before the halo has arrived) followed by SG_PART_BOUNDARY (the rest; ADDS its share
-// of the reduction to dot2).
-enum { SG_PART_ALL = 0, SG_PART_INTERIOR = 1, SG_PART_BOUNDARY = 2 };
-bool sg_thermal_can_split(const sg_thermal_op *op);
+// wait (partitioned mesh): ghost rows of x are still travelling; the kernels that support it process the cells/rows that
+// read no ghost value first and wait inside the kernel, the others are preceded by a one-warp wait kernel.
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
-                         const int *skip, cudaStream_t st, int y_is_zero = 0, int part = SG_PART_ALL);
+                         const int *skip, cudaStream_t st, int y_is_zero = 0, const SgHaloWait *wait = nullptr);
 
 // One fused Chebyshev step of the polynomial preconditioner (DG + class tables only, see dg_cheb_step):
 // z_out = z_in + a (z_in - z_prev) + b M^-1 (r - J z_in); z_prev == NULL means 0 (first step); z_out may alias
@@ -61,7 +93,7 @@ struct SgChebStep {
     double *z_out;
     double a, b;
     int last;
-    int part;   // SG_PART_*
+    const SgHaloWait *wait;   // ghost rows of z_in in flight (NULL: none)
 };
 bool sg_thermal_has_cheb(const sg_thermal_op *op);
 bool sg_thermal_profiling(const sg_thermal_op *op);   // event pairs around the kernels are being recorded
@@ -69,16 +101,22 @@ int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, dou
 
 // peer.cu: NVLink peer-memory halo exchange and small all-reduce (replaces NCCL on the solver's data path)
 struct SgPeer;
-int sg_peer_create(sg_ctx *ctx, size_t mailbox_doubles, SgPeer **out, void *handle64);
-int sg_peer_open(SgPeer *p, const void *handles /* nranks x 64 bytes */);
+int sg_peer_create(sg_ctx *ctx, size_t mailbox_doubles, size_t workspace_doubles, SgPeer **out, void *handle64);
+// handles: nranks x 64 bytes; layout: per rank {vector stride (dofs), ghost offset of the rows received from below, from above}
+int sg_peer_open(SgPeer *p, const void *handles, const int64_t *layout3);
 int sg_peer_destroy(SgPeer *p);
 bool sg_peer_ready(const SgPeer *p);
 size_t sg_peer_mailbox_doubles(const SgPeer *p);
+double *sg_peer_workspace(const SgPeer *p);          // IPC-visible solver workspace inside the communication block
+const SgPeerRedDev *sg_peer_red_dev(const SgPeer *p); // device copy of the all-reduce descriptor (for SgRed::peer)
 int sg_peer_check(SgPeer *p);
+// mailbox path (any vector, e.g. the caller's temperature): push into the neighbour's mailbox, pull into the ghost rows
 int sg_peer_halo_forward(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, cudaStream_t st);
-// the two halves of a forward exchange, so that work that needs no ghost values can run between them
-int sg_peer_halo_push(SgPeer *p, int n_seg, const sg_halo_segment *seg, const double *vec, cudaStream_t st);
-int sg_peer_halo_pull(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, cudaStream_t st);
+// direct path (vectors inside the IPC workspace): ONE kernel stores the boundary rows straight into the neighbour's ghost
+// rows of the same vector and raises its flag; *wait tells the consumer what to wait for.  Returns SG_OK and wait->n = 0
+// after falling back to the mailbox path (vector outside the workspace).
+int sg_peer_put(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, SgHaloWait *wait, cudaStream_t st);
+int sg_peer_wait(SgPeer *p, const SgHaloWait &wait, cudaStream_t st);   // one-warp kernel for consumers without an in-kernel wait
 int sg_peer_allreduce(SgPeer *p, double *vals, int count, cudaStream_t st);
 
 // classify.cu: equivalence classes of 64-bit keys.  cls_out[i] = class of keys[i] in [0, *n_cls),
@@ -91,7 +129,7 @@ struct SgStencil;
 int sg_stencil_build(sg_ctx *ctx, const int32_t *dofmap, int64_t n_cells, int n_ld, int64_t cell_lo, int64_t cell_hi,
                      const uint16_t *cls16, const double *tab, int S, int64_t n_rows, SgStencil **out);
 int sg_stencil_apply(const SgStencil *s, const double *x, double *y, int64_t own_lo, int64_t own_hi, SgRed red, double *dot2,
-                     const int *skip, cudaStream_t st);
+                     const int *skip, cudaStream_t st, const SgHaloWait *wait = nullptr);
 void sg_stencil_destroy(SgStencil *s);
 void sg_stencil_info(const SgStencil *s, int32_t *n_classes, int32_t *n_entries, int32_t *max_nnz);
 
@@ -170,6 +208,30 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 }  // namespace sgptx
 
+// ------------------------------------------------------------------ sweep direction
+// Consecutive streaming kernels of the solver alternate the direction in which they sweep their arrays: each then starts
+// on the part the previous kernel touched last, which is what the 126 MB L2 still holds (the vectors are 157 MB each on
+// config 3).  Grid-stride loop over [lo, hi): ascending, or - rev - the same (block, thread) -> element map walked from
+// the last grid-stride iteration down to the first, so per-block partial sums cover the same elements either way.
+__device__ __forceinline__ void sg_sweep_begin(long lo, long hi, int tb, int rev, long &c, long &step) {
+    step = (long)gridDim.x * tb;
+    c = lo + (long)blockIdx.x * tb + threadIdx.x;
+    if (rev && c < hi) {
+        c += ((hi - 1 - c) / step) * step;
+        step = -step;
+    }
+}
+__device__ __forceinline__ void sg_sweep_begin_i(int lo, int hi, int tb, int rev, int &c, int &step) {
+    step = (int)gridDim.x * tb;
+    c = lo + (int)blockIdx.x * tb + (int)threadIdx.x;
+    if (rev && c < hi) {
+        c += ((hi - 1 - c) / step) * step;
+        step = -step;
+    }
+}
+// host: direction of the next streaming launch (alternates; SG_SERPENTINE=0 keeps every sweep ascending)
+int sg_next_sweep_dir();
+
 // ------------------------------------------------------------------ reductions
 __device__ __forceinline__ double sg_warp_sum(double v) {
 #pragma unroll
@@ -190,11 +252,73 @@ __device__ __forceinline__ double sg_block_sum(double v, double *scratch) {
     return v;
 }
 
+// Bounded spin on a flag another GPU (or another block) raises; false on expiry (about 20 s).
+__device__ __forceinline__ bool sg_spin_until(const unsigned long long *flag, unsigned long long seq) {
+    const volatile unsigned long long *f = flag;
+    const long long t0 = clock64();
+    while (*f < seq) {
+        if (clock64() - t0 > 40000000000ll) return false;
+        __nanosleep(32);
+    }
+    return true;
+}
+
+// Block-level wait for ghost rows (SgHaloWait); every thread of the block must call it.  Not inlined: it runs once per
+// block and must not cost the hot loops of the operator kernels any registers.
+static __device__ __noinline__ void sg_halo_wait_block(const SgHaloWait &w) {
+    if (w.n == 0) return;
+    if (threadIdx.x < (unsigned)w.n) {
+        const unsigned long long *f = threadIdx.x == 0 ? w.flag[0] : w.flag[1];   // no dynamic indexing of the parameter struct
+        if (!sg_spin_until(f, w.seq)) *w.err = 1;
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// All-reduce of count <= SG_PEER_RED_VALS doubles at vals over the ranks, executed by warp 0 of ONE block per rank.
+__device__ __forceinline__ void sg_peer_allreduce_warp(const SgPeerRedDev &a, double *vals, int count) {
+    const int t = threadIdx.x;
+    unsigned long long seq = 0;
+    if (t == 0) seq = *a.seq + 1ull;
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    const int par = (int)(seq & 1ull);
+    if (t < a.nranks) {
+        double *v = reinterpret_cast<double *>(a.base[t] + a.vals_off) + ((size_t)par * SG_PEER_MAX_RANKS + a.rank) * SG_PEER_RED_VALS;
+        for (int k = 0; k < count; ++k) reinterpret_cast<volatile double *>(v)[k] = vals[k];
+        __threadfence_system();
+        unsigned long long *tag = reinterpret_cast<unsigned long long *>(a.base[t] + a.tags_off) + (size_t)par * SG_PEER_MAX_RANKS + a.rank;
+        *reinterpret_cast<volatile unsigned long long *>(tag) = seq;
+    }
+    bool ok = true;
+    if (t < a.nranks) {
+        const unsigned long long *tag =
+            reinterpret_cast<const unsigned long long *>(a.base[a.rank] + a.tags_off) + (size_t)par * SG_PEER_MAX_RANKS + t;
+        ok = sg_spin_until(tag, seq);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    if (t == 0) {
+        if (!ok) {
+            *a.err = 1;
+        } else {
+            const volatile double *v =
+                reinterpret_cast<const volatile double *>(a.base[a.rank] + a.vals_off) + (size_t)par * SG_PEER_MAX_RANKS * SG_PEER_RED_VALS;
+            for (int k = 0; k < count; ++k) {
+                double s = 0.0;
+                for (int r = 0; r < a.nranks; ++r) s += v[(size_t)r * SG_PEER_RED_VALS + k];   // fixed rank order on every rank
+                vals[k] = s;
+            }
+        }
+        *a.seq = seq;
+        __threadfence_system();
+    }
+}
+
 // Sum NR per-thread values over the grid; the LAST block to finish adds the per-block partials in block
-// order (deterministic) and stores the totals in out[0..NR).  Must be reached by every thread of every
-// block; gridDim.x <= SG_MAX_BLOCKS.
+// order (deterministic) and stores the totals in out[0..NR); with red.peer set it then all-reduces them over the ranks
+// (see SgRed).  Must be reached by every thread of every block; gridDim.x <= SG_MAX_BLOCKS.
 template <int NR>
-__device__ __forceinline__ void sg_grid_reduce(double (&v)[NR], const SgRed red, double *out, const bool accumulate = false) {
+__device__ __forceinline__ void sg_grid_reduce(double (&v)[NR], const SgRed red, double *out) {
     __shared__ double scratch[32];
     __shared__ bool is_last;
 #pragma unroll
@@ -215,8 +339,12 @@ __device__ __forceinline__ void sg_grid_reduce(double (&v)[NR], const SgRed red,
             double s = 0.0;
             for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += red.partials[b * NR + k];
             s = sg_block_sum(s, scratch);
-            if (threadIdx.x == 0) out[k] = accumulate ? out[k] + s : s;   // accumulate: second launch over another cell range
+            if (threadIdx.x == 0) out[k] = s;
         }
         if (threadIdx.x == 0) *red.counter = 0u;
+        if (red.peer) {
+            __syncthreads();   // out[] stored by thread 0 is visible to warp 0
+            if (threadIdx.x < 32) sg_peer_allreduce_warp(*red.peer, red.ar_ptr ? red.ar_ptr : out, red.ar_count ? red.ar_count : NR);
+        }
     }
 }

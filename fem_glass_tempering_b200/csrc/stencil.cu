@@ -40,6 +40,7 @@ struct __align__(16) Entry {
 
 struct StDev {
     long n_rows, own_lo, own_hi;
+    long safe_lo, safe_hi;   // rows [safe_lo, safe_hi) read no ghost row: processed first, the rest after the halo wait
     const uint16_t *rcls;
     const int32_t *ptr;   // [n_classes + 1]
     const Entry *ent;     // [n_entries]
@@ -142,7 +143,7 @@ __global__ void k_narrow16(long n, const int32_t *__restrict__ in, uint16_t *__r
 // come from L2, so the loads in flight per warp set the pace); the sum itself stays in entry order for every U.
 template <bool SMEM, int U, int MINB>
 __global__ void __launch_bounds__(STB, MINB) k_stencil_apply(const StDev sd, const double *__restrict__ x, double *__restrict__ y,
-                                                            SgRed red, double *dot_out, const int *skip) {
+                                                            SgRed red, double *dot_out, const int *skip, const SgHaloWait hw) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     if (skip && *skip) return;
     const Entry *ent = sd.ent;
@@ -157,33 +158,39 @@ __global__ void __launch_bounds__(STB, MINB) k_stencil_apply(const StDev sd, con
         ptr = s_ptr;
     }
     double dsum[2] = {0.0, 0.0};
-    for (long row = (long)blockIdx.x * STB + threadIdx.x; row < sd.n_rows; row += (long)gridDim.x * STB) {
-        const int c = sd.rcls[row];
-        const int p1 = ptr[c + 1];
-        int k = ptr[c];
-        const double *xr = x + row;
-        double acc = 0.0;
-        for (; k + U <= p1; k += U) {
-            Entry e[U];
-            double xv[U];
+#pragma unroll 1
+    for (int rg = 0; rg < 3; ++rg) {
+        const long lo = rg == 0 ? sd.safe_lo : (rg == 1 ? 0 : sd.safe_hi);
+        const long hi = rg == 0 ? sd.safe_hi : (rg == 1 ? sd.safe_lo : sd.n_rows);
+        if (rg == 1) sg_halo_wait_block(hw);   // rows next to the slab faces read the neighbours' ghost rows
+        for (long row = lo + (long)blockIdx.x * STB + threadIdx.x; row < hi; row += (long)gridDim.x * STB) {
+            const int c = sd.rcls[row];
+            const int p1 = ptr[c + 1];
+            int k = ptr[c];
+            const double *xr = x + row;
+            double acc = 0.0;
+            for (; k + U <= p1; k += U) {
+                Entry e[U];
+                double xv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) e[u] = ent[k + u];
+                for (int u = 0; u < U; ++u) e[u] = ent[k + u];
 #pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = __ldg(xr + e[u].off);
+                for (int u = 0; u < U; ++u) xv[u] = __ldg(xr + e[u].off);
 #pragma unroll
-            for (int u = 0; u < U; ++u) acc = fma(e[u].coef, xv[u], acc);
+                for (int u = 0; u < U; ++u) acc = fma(e[u].coef, xv[u], acc);
+            }
+            for (; k < p1; ++k) {
+                const Entry e = ent[k];
+                acc = fma(e.coef, __ldg(xr + e.off), acc);
+            }
+            y[row] = acc;
+            if (row >= sd.own_lo && row < sd.own_hi) dsum[0] += __ldg(xr) * acc;
         }
-        for (; k < p1; ++k) {
-            const Entry e = ent[k];
-            acc = fma(e.coef, __ldg(xr + e.off), acc);
-        }
-        y[row] = acc;
-        if (row >= sd.own_lo && row < sd.own_hi) dsum[0] += __ldg(xr) * acc;
     }
     sg_grid_reduce<2>(dsum, red, dot_out);
 }
 
-using StencilKernel = void (*)(const StDev, const double *, double *, SgRed, double *, const int *);
+using StencilKernel = void (*)(const StDev, const double *, double *, SgRed, double *, const int *, const SgHaloWait);
 struct Variant {
     StencilKernel smem, global;
     const char *what;
@@ -222,6 +229,7 @@ struct SgStencil {
     int grid;
     size_t smem;   // bytes of the shared-memory copy of the class lists; 0: read through L1
     int max_nnz;
+    long max_off;   // largest |column offset| of any class row
     StencilKernel kernel;
 };
 
@@ -276,6 +284,8 @@ int sg_stencil_build(sg_ctx *ctx, const int32_t *dofmap, int64_t n_cells, int n_
     }
     std::vector<Entry> ent((size_t)std::max(ptr[R], 1));
     for (int c = 0; c < R; ++c) std::copy(wide.begin() + (size_t)c * MAX_NNZ, wide.begin() + (size_t)c * MAX_NNZ + nnz[c], ent.begin() + ptr[c]);
+    long long max_off = 0;
+    for (int i = 0; i < ptr[R]; ++i) max_off = std::max(max_off, ent[i].off < 0 ? -ent[i].off : ent[i].off);
 
     SgStencil *s = new SgStencil();
     memset(s, 0, sizeof(*s));
@@ -306,6 +316,7 @@ int sg_stencil_build(sg_ctx *ctx, const int32_t *dofmap, int64_t n_cells, int n_
     if (grid > SG_MAX_BLOCKS) grid = SG_MAX_BLOCKS;
     s->grid = (int)grid;
     s->max_nnz = max_nnz;
+    s->max_off = (long)max_off;
     s->dev.n_rows = n_rows;
     s->dev.own_lo = 0;
     s->dev.own_hi = n_rows;
@@ -319,11 +330,19 @@ int sg_stencil_build(sg_ctx *ctx, const int32_t *dofmap, int64_t n_cells, int n_
 }
 
 int sg_stencil_apply(const SgStencil *s, const double *x, double *y, int64_t own_lo, int64_t own_hi, SgRed red, double *dot2,
-                     const int *skip, cudaStream_t st) {
+                     const int *skip, cudaStream_t st, const SgHaloWait *wait) {
     StDev sd = s->dev;
     sd.own_lo = own_lo;
     sd.own_hi = own_hi;
-    s->kernel<<<s->grid, STB, s->smem, st>>>(sd, x, y, red, dot2, skip);
+    SgHaloWait hw{};
+    sd.safe_lo = 0;
+    sd.safe_hi = sd.n_rows;
+    if (wait && wait->n) {
+        hw = *wait;
+        if (own_lo > 0) sd.safe_lo = std::min<long>(sd.n_rows, own_lo + s->max_off);
+        if (own_hi < sd.n_rows) sd.safe_hi = std::max<long>(sd.safe_lo, own_hi - s->max_off);
+    }
+    s->kernel<<<s->grid, STB, s->smem, st>>>(sd, x, y, red, dot2, skip, hw);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;

@@ -588,14 +588,6 @@ __global__ void __launch_bounds__(TB) k_bfacet_mats(const OpDev op, const double
     for (int k = 0; k < NFDP; ++k) bmat[b * NFDP + k] = B[k];
 }
 
-// fraction of the pairs (c, c + stride) of the paired work decomposition whose class words agree
-__global__ void k_pair_score(const uint64_t *cls, long lo, long groups, long stride, unsigned long long *matches) {
-    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= groups * stride) return;
-    const long g = q / stride, r = q - g * stride, c0 = lo + g * 2 * stride + r;
-    if (cls[c0] == cls[c0 + stride]) atomicAdd(matches, 1ull);
-}
-
 // DG partition: owned cells with a neighbour outside [lo, hi) (a ghost cell).  They sit at the two ends of the owned
 // range (x-slabs): lowB = one past the last such cell of the lower half, highB = the first one of the upper half.
 __global__ void k_split_range(int nnb, long nc, long lo, long hi, const int32_t *nbr, unsigned long long *lowB, unsigned long long *highB) {
@@ -624,16 +616,21 @@ struct ClsDev {
     // exterior facets handled inside the DG class kernel (P1): nbr holds -2 - b for exterior facet b and
     // bmat[b] the packed symmetric matrix  dt*0.001*int (4 sigma eps T^3 + htc) phi_k phi_l ds  over the facet's dofs
     const double *bmat;
-    // two cells per thread (dg_cell_apply2): c and c + pair_stride are processed together; 0 = off
-    long pair_stride, pair_groups;
     // CG: exterior facets applied by the same kernel after the cells (bmat != NULL)
     long n_bf;
     const int32_t *bf_cell, *bf_facet;
-    // DG, partitioned mesh: a launch may cover a second cell range (the two boundary strips) and add its share of the
-    // reduction to what an earlier launch over the interior cells left in dot_out
-    long cell_lo2, cell_hi2;
-    int accumulate;
+    // DG, partitioned mesh: owned cells [split_lo, split_hi) have no ghost neighbour.  The kernels process them first and
+    // wait for the neighbours' ghost rows (SgHaloWait) only before the two boundary strips [cell_lo, split_lo) and
+    // [split_hi, cell_hi), so the exchange hides behind the interior.  split_lo == cell_lo, split_hi == cell_hi otherwise.
+    long split_lo, split_hi;
+    int rev;   // sweep direction of this launch (sg_sweep_begin)
 };
+
+// The three cell ranges of a class-kernel launch in processing order: interior, lower strip, upper strip.
+__device__ __forceinline__ void cls_range(const ClsDev &cd, int rg, long &lo, long &hi) {
+    lo = rg == 0 ? cd.split_lo : (rg == 1 ? cd.cell_lo : cd.split_hi);
+    hi = rg == 0 ? cd.split_hi : (rg == 1 ? cd.split_lo : cd.cell_hi);
+}
 
 constexpr int CB = 256;  // threads per block of the class kernels
 
@@ -728,14 +725,14 @@ __device__ __forceinline__ void dg_exterior_facet(const ClsDev &cd, const int f,
 // Element vector of DG cell c from the class tables: loads the class word, the neighbour ids, the cell's row
 // xk and the neighbours' rows of x, returns yk = A_self x_K + sum_f A_nb x_N (+ exterior-facet matrices).
 template <int NLD, int NNB, int P, bool WIDE, bool BND>
-__device__ __forceinline__ void dg_cell_apply(const ClsDev &cd, const double *s_tab, const double *s_nb, const long c,
+__device__ __forceinline__ void dg_cell_apply(const ClsDev &cd, const double *s_tab, const double *s_nb, const int c,
                                               const double *__restrict__ x, double (&xk)[NLD], double (&yk)[NLD]) {
-    const long nc = cd.n_cells;
+    const int nc = (int)cd.n_cells;
     const uint64_t w = cd.cls64[c];
     int nb[NNB];
 #pragma unroll
-    for (int f = 0; f < NNB; ++f) nb[f] = cd.nbr[(long)f * nc + c];
-    load_row<NLD, WIDE>(x + c * NLD, xk);
+    for (int f = 0; f < NNB; ++f) nb[f] = cd.nbr[(size_t)f * nc + c];
+    load_row<NLD, WIDE>(x + (size_t)c * NLD, xk);
     double xn[NNB][NLD];
 #pragma unroll
     for (int f = 0; f < NNB; ++f) {
@@ -759,94 +756,6 @@ __device__ __forceinline__ void dg_cell_apply(const ClsDev &cd, const double *s_
     }
 }
 
-// Two right-hand sides against ONE table read: acc0 += A x0, acc1 += A x1.
-template <int NLD>
-__device__ __forceinline__ void smem_matvec_acc2(const double *__restrict__ A, const double (&x0)[NLD], const double (&x1)[NLD],
-                                                 double (&acc0)[NLD], double (&acc1)[NLD]) {
-#pragma unroll
-    for (int i = 0; i < NLD; ++i) {
-        double a0 = acc0[i], a1 = acc1[i];
-        if constexpr (NLD % 2 == 0) {
-            const double2 *row = reinterpret_cast<const double2 *>(A + i * NLD);
-#pragma unroll
-            for (int j = 0; j < NLD / 2; ++j) {
-                const double2 t = row[j];
-                a0 += t.x * x0[2 * j];
-                a1 += t.x * x1[2 * j];
-                a0 += t.y * x0[2 * j + 1];
-                a1 += t.y * x1[2 * j + 1];
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NLD; ++j) {
-                const double t = A[i * NLD + j];
-                a0 += t * x0[j];
-                a1 += t * x1[j];
-            }
-        }
-        acc0[i] = a0;
-        acc1[i] = a1;
-    }
-}
-
-// Two cells per thread (c1 = c0 + pair stride: the same Kuhn type one tile-pair further, mesh.py): when their class
-// words agree — everywhere except next to some boundaries — every shared-memory table entry is read once and used
-// for both, which halves the shared-memory wavefronts that bound the single-cell kernel.
-template <int NLD, int NNB, int P, bool WIDE, bool BND>
-__device__ __forceinline__ void dg_cell_apply2(const ClsDev &cd, const double *s_tab, const double *s_nb, const long c0, const long c1,
-                                               const double *__restrict__ x, double (&xk0)[NLD], double (&yk0)[NLD],
-                                               double (&xk1)[NLD], double (&yk1)[NLD]) {
-    const long nc = cd.n_cells;
-    const uint64_t w = cd.cls64[c0];
-    if (w != cd.cls64[c1]) {
-        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, x, xk0, yk0);
-        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c1, x, xk1, yk1);
-        return;
-    }
-    int nb0[NNB], nb1[NNB];
-#pragma unroll
-    for (int f = 0; f < NNB; ++f) {
-        nb0[f] = cd.nbr[(long)f * nc + c0];
-        nb1[f] = cd.nbr[(long)f * nc + c1];
-    }
-    load_row<NLD, WIDE>(x + c0 * NLD, xk0);
-    load_row<NLD, WIDE>(x + c1 * NLD, xk1);
-#pragma unroll
-    for (int i = 0; i < NLD; ++i) yk0[i] = yk1[i] = 0.0;
-    smem_matvec_acc2<NLD>(s_tab + (int)(w & 0xFFFFull) * cd.S, xk0, xk1, yk0, yk1);
-#pragma unroll
-    for (int f = 0; f < NNB; ++f) {
-        const int u = (int)((w >> (16 + 12 * f)) & 0xFFFull);
-        if (u) {   // equal class words: facet f is interior for both cells
-            double xa[NLD], xb[NLD];
-            load_row<NLD, WIDE>(x + (long)nb0[f] * NLD, xa);
-            load_row<NLD, WIDE>(x + (long)nb1[f] * NLD, xb);
-            smem_matvec_acc2<NLD>(s_nb + (u - 1) * cd.S, xa, xb, yk0, yk1);
-        }
-        if constexpr (BND) {
-            if (nb0[f] < -1) dg_exterior_facet<NLD, NNB, P>(cd, f, nb0[f], xk0, yk0);
-            if (nb1[f] < -1) dg_exterior_facet<NLD, NNB, P>(cd, f, nb1[f], xk1, yk1);
-        }
-    }
-}
-
-// Work item -> cells of the paired kernels: groups of 2*stride cells, item (g, r) -> c0 = lo + g*2*stride + r and
-// c1 = c0 + stride; the cells behind the last full group are single items (c1 = -1).
-__device__ __forceinline__ void pair_cells(const ClsDev &cd, const long item, long &c0, long &c1) {
-    const long st = cd.pair_stride, paired = cd.pair_groups * st;
-    if (item < paired) {
-        const long g = item / st, r = item - g * st;
-        c0 = cd.cell_lo + g * 2 * st + r;
-        c1 = c0 + st;
-    } else {
-        c0 = cd.cell_lo + cd.pair_groups * 2 * st + (item - paired);
-        c1 = -1;
-    }
-}
-__device__ __forceinline__ long pair_items(const ClsDev &cd) {
-    return cd.pair_groups * cd.pair_stride + (cd.cell_hi - cd.cell_lo - cd.pair_groups * 2 * cd.pair_stride);
-}
-
 __device__ __forceinline__ void load_class_tables(const ClsDev &cd, double *s_tab, int ntab) {
     for (int i = threadIdx.x; i < ntab; i += CB) s_tab[i] = cd.tab[i];
     __syncthreads();
@@ -854,48 +763,33 @@ __device__ __forceinline__ void load_class_tables(const ClsDev &cd, double *s_ta
 
 // DG fast apply: persistent grid-stride blocks, class tables in shared memory, fused x.y reduction.
 // A warp handles 32 consecutive cells; when these share their classes (the plate meshes number the cells
-// in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.  PAIR: two cells per
-// thread sharing the table reads (dg_cell_apply2).
-template <int NLD, int NNB, int P, bool WIDE, bool BND, bool PAIR = false>
-__global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
-                                                                   SgRed red, double *dot_out, const int *skip) {
+// in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.
+template <int NLD, int NNB, int P, bool WIDE, bool BND, bool HALO>
+__global__ void __launch_bounds__(CB, 3) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
+                                                        SgRed red, double *dot_out, const int *skip, const SgHaloWait hw) {
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
     load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
     const double *s_nb = s_tab + cd.n_self * cd.S;
     double dsum[2] = {0.0, 0.0};   // [1] stays 0: slot of the separate exterior-facet kernel (overwritten by it when it runs)
-    if constexpr (PAIR) {
-        const long items = pair_items(cd);
-        for (long it = (long)blockIdx.x * CB + threadIdx.x; it < items; it += (long)gridDim.x * CB) {
-            long c0, c1;
-            pair_cells(cd, it, c0, c1);
-            double xk0[NLD], yk0[NLD], xk1[NLD], yk1[NLD];
-            if (c1 >= 0) {
-                dg_cell_apply2<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, c1, x, xk0, yk0, xk1, yk1);
-                store_row<NLD, WIDE>(y + c1 * NLD, yk1);
-#pragma unroll
-                for (int i = 0; i < NLD; ++i) dsum[0] += xk1[i] * yk1[i];
-            } else {
-                dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, x, xk0, yk0);
-            }
-            store_row<NLD, WIDE>(y + c0 * NLD, yk0);
-#pragma unroll
-            for (int i = 0; i < NLD; ++i) dsum[0] += xk0[i] * yk0[i];
-        }
-    } else {
 #pragma unroll 1
-        for (int rg = 0; rg < 2; ++rg) {
-            const long lo = rg ? cd.cell_lo2 : cd.cell_lo, hi = rg ? cd.cell_hi2 : cd.cell_hi;
-            for (long c = lo + (long)blockIdx.x * CB + threadIdx.x; c < hi; c += (long)gridDim.x * CB) {
-                double xk[NLD], yk[NLD];
-                dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
-                store_row<NLD, WIDE>(y + c * NLD, yk);
+    for (int rg = 0; rg < (HALO ? 3 : 1); ++rg) {
+        long lo = cd.cell_lo, hi = cd.cell_hi;
+        if constexpr (HALO) {
+            cls_range(cd, rg, lo, hi);
+            if (rg == 1) sg_halo_wait_block(hw);   // the strips read the neighbours' ghost rows
+        }
+        int c, step;
+        sg_sweep_begin_i((int)lo, (int)hi, CB, cd.rev, c, step);
+        for (; c >= (int)lo && c < (int)hi; c += step) {
+            double xk[NLD], yk[NLD];
+            dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
+            store_row<NLD, WIDE>(y + (size_t)c * NLD, yk);
 #pragma unroll
-                for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
-            }
+            for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
         }
     }
-    sg_grid_reduce<2>(dsum, red, dot_out, cd.accumulate != 0);
+    sg_grid_reduce<2>(dsum, red, dot_out);
 }
 
 // Residual from the class tables: F_K = (cell + interior-facet part of J) T  -  |detJ| Mhat T_prev  -  dt f |detJ| load.
@@ -974,10 +868,10 @@ struct ChebDev {
 };
 
 template <int NLD, bool WIDE, bool FIRST, bool LAST>
-__device__ __forceinline__ void cheb_update(const ChebDev &ch, const long c, const double (&zk)[NLD], double (&Jz)[NLD], double &dsum) {
+__device__ __forceinline__ void cheb_update(const ChebDev &ch, const int c, const double (&zk)[NLD], double (&Jz)[NLD], double &dsum) {
     double rk[NLD], zp[NLD];
-    load_row<NLD, WIDE>(ch.r + c * NLD, rk);
-    if (!FIRST) load_row<NLD, WIDE>(ch.z_prev + c * NLD, zp);
+    load_row<NLD, WIDE>(ch.r + (size_t)c * NLD, rk);
+    if (!FIRST) load_row<NLD, WIDE>(ch.z_prev + (size_t)c * NLD, zp);
     const double idet = ch.b / ch.detJ[c];
 #pragma unroll
     for (int i = 0; i < NLD; ++i) Jz[i] = rk[i] - Jz[i];
@@ -989,47 +883,37 @@ __device__ __forceinline__ void cheb_update(const ChebDev &ch, const long c, con
         const double dprev = FIRST ? zk[i] : zk[i] - zp[i];
         zp[i] = zk[i] + (ch.a * dprev + idet * m);
     }
-    store_row<NLD, WIDE>(ch.z_out + c * NLD, zp);
+    store_row<NLD, WIDE>(ch.z_out + (size_t)c * NLD, zp);
     if (LAST) {
 #pragma unroll
         for (int i = 0; i < NLD; ++i) dsum += rk[i] * zp[i];
     }
 }
 
-template <int NLD, int NNB, int P, bool WIDE, bool BND, bool FIRST, bool LAST, bool PAIR = false>
-__global__ void __launch_bounds__(CB, PAIR ? 2 : 3) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
-                                                                 SgRed red, double *dot_out, const int *skip) {
+template <int NLD, int NNB, int P, bool WIDE, bool BND, bool FIRST, bool LAST, bool HALO>
+__global__ void __launch_bounds__(CB, 3) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
+                                                      SgRed red, double *dot_out, const int *skip, const SgHaloWait hw) {
     extern __shared__ __align__(16) double s_tab[];
     if (skip && *skip) return;
     load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
     const double *s_nb = s_tab + cd.n_self * cd.S;
     double dsum[1] = {0.0};
-    if constexpr (PAIR) {
-        const long items = pair_items(cd);
-        for (long it = (long)blockIdx.x * CB + threadIdx.x; it < items; it += (long)gridDim.x * CB) {
-            long c0, c1;
-            pair_cells(cd, it, c0, c1);
-            double zk0[NLD], Jz0[NLD], zk1[NLD], Jz1[NLD];
-            if (c1 >= 0) {
-                dg_cell_apply2<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, c1, z, zk0, Jz0, zk1, Jz1);
-                cheb_update<NLD, WIDE, FIRST, LAST>(ch, c1, zk1, Jz1, dsum[0]);
-            } else {
-                dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c0, z, zk0, Jz0);
-            }
-            cheb_update<NLD, WIDE, FIRST, LAST>(ch, c0, zk0, Jz0, dsum[0]);
-        }
-    } else {
 #pragma unroll 1
-        for (int rg = 0; rg < 2; ++rg) {
-            const long lo = rg ? cd.cell_lo2 : cd.cell_lo, hi = rg ? cd.cell_hi2 : cd.cell_hi;
-            for (long c = lo + (long)blockIdx.x * CB + threadIdx.x; c < hi; c += (long)gridDim.x * CB) {
-                double zk[NLD], Jz[NLD];
-                dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
-                cheb_update<NLD, WIDE, FIRST, LAST>(ch, c, zk, Jz, dsum[0]);
-            }
+    for (int rg = 0; rg < (HALO ? 3 : 1); ++rg) {
+        long lo = cd.cell_lo, hi = cd.cell_hi;
+        if constexpr (HALO) {
+            cls_range(cd, rg, lo, hi);
+            if (rg == 1) sg_halo_wait_block(hw);   // the strips read the neighbours' ghost rows of z
+        }
+        int c, step;
+        sg_sweep_begin_i((int)lo, (int)hi, CB, cd.rev, c, step);
+        for (; c >= (int)lo && c < (int)hi; c += step) {
+            double zk[NLD], Jz[NLD];
+            dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
+            cheb_update<NLD, WIDE, FIRST, LAST>(ch, c, zk, Jz, dsum[0]);
         }
     }
-    if (LAST) sg_grid_reduce<1>(dsum, red, dot_out, cd.accumulate != 0);
+    if (LAST) sg_grid_reduce<1>(dsum, red, dot_out);
 }
 
 // Exterior facets of a CG space from their linearised matrices: y += B_F x_F (RED.ADD), dsum += x_F . (B_F x_F) over the
@@ -1154,12 +1038,11 @@ struct sg_thermal_op {
     ClsDev cls;
     void *cls_words;       // cls64 / cls16 storage
     double *cls_tab;
-    int cls_grid, cls_grid_pair;
+    int cls_grid;
     size_t cls_smem;
     int32_t n_geom_classes;
     SgRed own_red;         // reduction scratch of sg_thermal_jac_apply (solver-less use of the fast path)
-    long split_lo, split_hi;   // DG: owned cells [split_lo, split_hi) have no ghost neighbour (split_lo >= split_hi: no split)
-    int part;              // set by sg_thermal_apply_dot: SG_PART_*
+    const SgHaloWait *wait; // set by sg_thermal_apply_dot: ghost rows of x in flight (NULL: none)
     int y_is_zero;         // set by sg_thermal_apply_dot: the caller guarantees y == 0 on entry (CG scatter needs no memset)
     int32_t *nbr_ext;      // DG P1: neighbour ids with exterior facets encoded (see ClsDev::bmat)
     double *bmat;
@@ -1203,31 +1086,6 @@ struct ProfScope {  // CUDA-event pair around the apply cell kernel when profili
     }
 };
 
-// ClsDev and grid of one part of a split launch (SG_PART_*)
-inline ClsDev part_view(const sg_thermal_op *op, int part, int *grid) {
-    ClsDev cd = op->cls;
-    cd.cell_lo2 = cd.cell_hi2 = 0;
-    cd.accumulate = 0;
-    long ncell = cd.cell_hi - cd.cell_lo;
-    if (part == SG_PART_INTERIOR) {
-        cd.cell_lo = op->split_lo;
-        cd.cell_hi = op->split_hi;
-        ncell = cd.cell_hi - cd.cell_lo;
-    } else if (part == SG_PART_BOUNDARY) {
-        cd.cell_lo2 = op->split_hi;
-        cd.cell_hi2 = cd.cell_hi;
-        cd.cell_hi = op->split_lo;
-        cd.accumulate = 1;
-        const long n1 = cd.cell_hi - cd.cell_lo, n2 = cd.cell_hi2 - cd.cell_lo2;
-        ncell = n1 > n2 ? n1 : n2;
-    }
-    long g = (ncell + CB - 1) / CB;
-    if (g < 1) g = 1;
-    if (g > op->cls_grid) g = op->cls_grid;
-    *grid = (int)g;
-    return cd;
-}
-
 // dot2 != nullptr (MODE_APPLY only): also produce dot2[0] + dot2[1] = x.y over the owned dofs.
 template <int D, int P, bool DG>
 int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const double *x, const double *xprev, double *y,
@@ -1249,30 +1107,43 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         // the class kernels always reduce x.y; without a consumer it lands in a scratch slot
         double *dst = dot2 ? dot2 : red.partials + 2 * SG_MAX_BLOCKS;
         {
+        int rc_wait = SG_OK;
+        (void)rc_wait;
         ProfScope ps(op, mode, st);
         const bool wide = (((uintptr_t)x | (uintptr_t)y) & 31) == 0;
+        const SgHaloWait none{}, hw = op->wait ? *op->wait : none;
         if constexpr (DG) {
-            if (op->cls.pair_stride > 0 && wide && op->bmat && op->part == SG_PART_ALL) {
-                dg_class_apply<NLD, D + 1, P, true, true, true><<<op->cls_grid_pair, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
-            } else {
-                auto k = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true> : dg_class_apply<NLD, D + 1, P, false, true>)
-                                  : (wide ? dg_class_apply<NLD, D + 1, P, true, false> : dg_class_apply<NLD, D + 1, P, false, false>);
-                int grid = op->cls_grid;
-                const ClsDev cdv = part_view(op, op->part, &grid);
-                k<<<grid, CB, op->cls_smem, st>>>(cdv, x, y, red, dst, skip);
-            }
+            auto k0 = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true, false> : dg_class_apply<NLD, D + 1, P, false, true, false>)
+                               : (wide ? dg_class_apply<NLD, D + 1, P, true, false, false> : dg_class_apply<NLD, D + 1, P, false, false, false>);
+            auto k1 = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true, true> : dg_class_apply<NLD, D + 1, P, false, true, true>)
+                               : (wide ? dg_class_apply<NLD, D + 1, P, true, false, true> : dg_class_apply<NLD, D + 1, P, false, false, true>);
+            auto k = hw.n ? k1 : k0;     // the variant with the in-kernel halo wait only on a partitioned mesh
+            if (hw.n) SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
+            ClsDev cdv = op->cls;
+            cdv.rev = dot2 ? sg_next_sweep_dir() : 0;     // solver launches alternate the sweep direction
+            k<<<op->cls_grid, CB, op->cls_smem, st>>>(cdv, x, y, red, dst, skip, hw);
         } else if (op->stencil) {
-            // gather form: plain stores of every row, no zeroing of y needed
-            const int rc = sg_stencil_apply(op->stencil, x, y, op->d.own_lo, op->d.own_hi, red, dst, skip, st);
+            // gather form: plain stores of every row, no zeroing of y needed.  With exterior facets following in their own
+            // launch, the cross-rank sum of both parts of x.Ax is done by THAT kernel (it covers dst[0] and dst[1]).
+            const bool bf_follows = op->bmat && dv.n_bf > 0;
+            const int rc = sg_stencil_apply(op->stencil, x, y, op->d.own_lo, op->d.own_hi, bf_follows ? sg_red_local(red) : red, dst, skip, st,
+                                            &hw);
             if (rc) return rc;
-        } else
+        } else {
+            if (hw.n && (rc_wait = sg_peer_wait(nullptr, hw, st))) return rc_wait;
             cg_class_apply<D, P><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, x, y, red, dst, skip);
+        }
         SG_CHECK_CUDA(cudaGetLastError());
         if (DG || !op->stencil) sg_count_launch();
         }
         if constexpr (!DG) {
             if (op->stencil && op->bmat && dv.n_bf > 0) {
-                cg_bfacet_apply<D, P><<<capped_grid(dv.n_bf, CB), CB, 0, st>>>(op->cls, x, y, red, dst + 1, skip);
+                SgRed rb = red;
+                if (rb.peer) {
+                    rb.ar_ptr = dst;
+                    rb.ar_count = 2;
+                }
+                cg_bfacet_apply<D, P><<<capped_grid(dv.n_bf, CB), CB, 0, st>>>(op->cls, x, y, rb, dst + 1, skip);
                 SG_CHECK_CUDA(cudaGetLastError());
                 sg_count_launch();
             }
@@ -1296,6 +1167,10 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
     } else if (ncell > 0) {
+        if (mode == MODE_APPLY && op->wait && op->wait->n) {
+            const int rcw = sg_peer_wait(nullptr, *op->wait, st);
+            if (rcw) return rcw;
+        }
         ProfScope ps(op, mode, st);
         if (mode == MODE_APPLY) cell_kernel<D, P, DG, MODE_APPLY><<<gc, TB, 0, st>>>(tab, dv, x, nullptr, y);
         if (mode == MODE_RESID) cell_kernel<D, P, DG, MODE_RESID><<<gc, TB, 0, st>>>(tab, dv, x, xprev, y);
@@ -1309,7 +1184,7 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
     } else if (fast && op->bmat) {
         // CG: cg_class_apply applied the exterior facets in the same launch
     } else if (dv.n_bf > 0 || bdot) {
-        if (mode == MODE_APPLY && bdot) bfacet_kernel<D, P, DG, MODE_APPLY, true><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, dot2 + 1, skip);
+        if (mode == MODE_APPLY && bdot) bfacet_kernel<D, P, DG, MODE_APPLY, true><<<gb, TB, 0, st>>>(dv, Tlin, x, y, sg_red_local(red), dot2 + 1, skip);
         if (mode == MODE_APPLY && !bdot) bfacet_kernel<D, P, DG, MODE_APPLY, false><<<gb, TB, 0, st>>>(dv, Tlin, x, y, red, nullptr, skip);
         if (mode == MODE_RESID) bfacet_kernel<D, P, DG, MODE_RESID, false><<<gb, TB, 0, st>>>(dv, x, nullptr, y, red, nullptr, nullptr);
         if (mode == MODE_DIAG) bfacet_kernel<D, P, DG, MODE_DIAG, false><<<gb, TB, 0, st>>>(dv, Tlin, nullptr, y, red, nullptr, nullptr);
@@ -1351,28 +1226,34 @@ int cheb_step_t(const sg_thermal_op *op, const SgChebStep &cs, SgRed red, double
         for (int i = 0; i < NLD * NLD; ++i) ch.minv[i] = op->mass_inv[i];
         const uintptr_t al = (uintptr_t)cs.z_in | (uintptr_t)cs.r | (uintptr_t)cs.z_prev | (uintptr_t)cs.z_out;
         const bool wide = (al & 31) == 0, bnd = op->bmat != nullptr, first = cs.z_prev == nullptr, last = cs.last != 0;
-        using K = void (*)(const ClsDev, const ChebDev, const double *, SgRed, double *, const int *);
-        // [wide][bnd][first][last]
+        using K = void (*)(const ClsDev, const ChebDev, const double *, SgRed, double *, const int *, const SgHaloWait);
+        // [wide][bnd][first][last], without / with the in-kernel halo wait
         static const K table[2][2][2][2] = {
-            {{{dg_cheb_step<NLD, NNB, P, false, false, false, false>, dg_cheb_step<NLD, NNB, P, false, false, false, true>},
-              {dg_cheb_step<NLD, NNB, P, false, false, true, false>, dg_cheb_step<NLD, NNB, P, false, false, true, true>}},
-             {{dg_cheb_step<NLD, NNB, P, false, true, false, false>, dg_cheb_step<NLD, NNB, P, false, true, false, true>},
-              {dg_cheb_step<NLD, NNB, P, false, true, true, false>, dg_cheb_step<NLD, NNB, P, false, true, true, true>}}},
-            {{{dg_cheb_step<NLD, NNB, P, true, false, false, false>, dg_cheb_step<NLD, NNB, P, true, false, false, true>},
-              {dg_cheb_step<NLD, NNB, P, true, false, true, false>, dg_cheb_step<NLD, NNB, P, true, false, true, true>}},
-             {{dg_cheb_step<NLD, NNB, P, true, true, false, false>, dg_cheb_step<NLD, NNB, P, true, true, false, true>},
-              {dg_cheb_step<NLD, NNB, P, true, true, true, false>, dg_cheb_step<NLD, NNB, P, true, true, true, true>}}}};
-        static const K pair_table[2][2] = {
-            {dg_cheb_step<NLD, NNB, P, true, true, false, false, true>, dg_cheb_step<NLD, NNB, P, true, true, false, true, true>},
-            {dg_cheb_step<NLD, NNB, P, true, true, true, false, true>, dg_cheb_step<NLD, NNB, P, true, true, true, true, true>}};
-        const bool pair = op->cls.pair_stride > 0 && wide && bnd && cs.part == SG_PART_ALL;
-        const K k = pair ? pair_table[first][last] : table[wide][bnd][first][last];
+            {{{dg_cheb_step<NLD, NNB, P, false, false, false, false, false>, dg_cheb_step<NLD, NNB, P, false, false, false, true, false>},
+              {dg_cheb_step<NLD, NNB, P, false, false, true, false, false>, dg_cheb_step<NLD, NNB, P, false, false, true, true, false>}},
+             {{dg_cheb_step<NLD, NNB, P, false, true, false, false, false>, dg_cheb_step<NLD, NNB, P, false, true, false, true, false>},
+              {dg_cheb_step<NLD, NNB, P, false, true, true, false, false>, dg_cheb_step<NLD, NNB, P, false, true, true, true, false>}}},
+            {{{dg_cheb_step<NLD, NNB, P, true, false, false, false, false>, dg_cheb_step<NLD, NNB, P, true, false, false, true, false>},
+              {dg_cheb_step<NLD, NNB, P, true, false, true, false, false>, dg_cheb_step<NLD, NNB, P, true, false, true, true, false>}},
+             {{dg_cheb_step<NLD, NNB, P, true, true, false, false, false>, dg_cheb_step<NLD, NNB, P, true, true, false, true, false>},
+              {dg_cheb_step<NLD, NNB, P, true, true, true, false, false>, dg_cheb_step<NLD, NNB, P, true, true, true, true, false>}}}};
+        static const K table_halo[2][2][2][2] = {
+            {{{dg_cheb_step<NLD, NNB, P, false, false, false, false, true>, dg_cheb_step<NLD, NNB, P, false, false, false, true, true>},
+              {dg_cheb_step<NLD, NNB, P, false, false, true, false, true>, dg_cheb_step<NLD, NNB, P, false, false, true, true, true>}},
+             {{dg_cheb_step<NLD, NNB, P, false, true, false, false, true>, dg_cheb_step<NLD, NNB, P, false, true, false, true, true>},
+              {dg_cheb_step<NLD, NNB, P, false, true, true, false, true>, dg_cheb_step<NLD, NNB, P, false, true, true, true, true>}}},
+            {{{dg_cheb_step<NLD, NNB, P, true, false, false, false, true>, dg_cheb_step<NLD, NNB, P, true, false, false, true, true>},
+              {dg_cheb_step<NLD, NNB, P, true, false, true, false, true>, dg_cheb_step<NLD, NNB, P, true, false, true, true, true>}},
+             {{dg_cheb_step<NLD, NNB, P, true, true, false, false, true>, dg_cheb_step<NLD, NNB, P, true, true, false, true, true>},
+              {dg_cheb_step<NLD, NNB, P, true, true, true, false, true>, dg_cheb_step<NLD, NNB, P, true, true, true, true, true>}}}};
+        const SgHaloWait none{}, hw = cs.wait ? *cs.wait : none;
+        const K k = hw.n ? table_halo[wide][bnd][first][last] : table[wide][bnd][first][last];
         SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
-        int grid = op->cls_grid;
-        const ClsDev cd = part_view(op, cs.part, &grid);
         {
             ProfScope ps(op, MODE_APPLY, st, 1);
-            k<<<pair ? op->cls_grid_pair : grid, CB, op->cls_smem, st>>>(cd, ch, cs.z_in, red, dot_out, skip);
+            ClsDev cdv = op->cls;
+            cdv.rev = sg_next_sweep_dir();
+            k<<<op->cls_grid, CB, op->cls_smem, st>>>(cdv, ch, cs.z_in, red, dot_out, skip, hw);
         }
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
@@ -1517,11 +1398,11 @@ int build_classes_t(sg_thermal_op *op) {
     int per_sm = 0;
     if (DG) {
         constexpr int NB = D + 1;
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, NB, P, true, true>, CB, smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, NB, P, true, true, false>, CB, smem));
     } else {
         SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_apply<D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_class_apply<D, P>, CB, smem));
@@ -1552,9 +1433,9 @@ int build_classes_t(sg_thermal_op *op) {
     cd.n_self = NS;
     cd.n_nb = NF;
     cd.S = S;
-    cd.cell_lo2 = cd.cell_hi2 = 0;
-    cd.accumulate = 0;
-    op->split_lo = op->split_hi = 0;
+    cd.split_lo = dv.cell_lo;
+    cd.split_hi = dv.cell_hi;
+    cd.rev = 0;
     if (DG && (dv.cell_lo > 0 || dv.cell_hi < nc)) {
         DevBuf b2;
         SG_CHECK_CUDA(cudaMalloc(&b2.p, 2 * sizeof(unsigned long long)));
@@ -1565,55 +1446,17 @@ int build_classes_t(sg_thermal_op *op) {
                                                                b2.as<unsigned long long>() + 1);
         unsigned long long res[2];
         SG_CHECK_CUDA(cudaMemcpy(res, b2.p, sizeof(res), cudaMemcpyDeviceToHost));
-        // worth splitting only if the interior is the bulk of the work
-        if ((long)res[1] - (long)res[0] > nown / 2) {
-            op->split_lo = (long)res[0];
-            op->split_hi = (long)res[1];
+        if ((long)res[1] >= (long)res[0]) {     // interior first, strips (which wait for the ghost rows) last
+            cd.split_lo = (long)res[0];
+            cd.split_hi = (long)res[1];
+        } else {                                 // every owned cell touches a ghost: wait before anything
+            cd.split_lo = cd.split_hi = dv.cell_lo;
         }
     }
     cd.bmat = nullptr;
     cd.n_bf = dv.n_bf;
     cd.bf_cell = dv.bf_cell;
     cd.bf_facet = dv.bf_facet;
-    cd.pair_stride = cd.pair_groups = 0;
-    op->cls_grid_pair = 0;
-    if (DG && NLD % 4 == 0 && (op->d.flags & SG_THERMAL_PAIRS)) {
-        // two cells per thread: find the stride at which cells repeat their class word (tile-ordered plates: one
-        // tile-pair = 32 * n_types cells); needs a clear majority of matching pairs to pay off
-        const long ncell = dv.cell_hi - dv.cell_lo;
-        const long cand[] = {32, 64, 96, 128, 192, 256, 384, 512, 768};
-        DevBuf cnt;
-        SG_CHECK_CUDA(cudaMalloc(&cnt.p, sizeof(unsigned long long)));
-        double best = 0.0;
-        long best_stride = 0;
-        for (long stp : cand) {
-            const long groups = ncell / (2 * stp);
-            if (groups < 8) continue;
-            SG_CHECK_CUDA(cudaMemset(cnt.p, 0, sizeof(unsigned long long)));
-            k_pair_score<<<(unsigned)((groups * stp + 255) / 256), 256>>>((const uint64_t *)op->cls_words, dv.cell_lo, groups, stp,
-                                                                          cnt.as<unsigned long long>());
-            unsigned long long m = 0;
-            SG_CHECK_CUDA(cudaMemcpy(&m, cnt.p, sizeof(m), cudaMemcpyDeviceToHost));
-            const double score = (double)m / (double)(groups * stp);
-            if (score > best + 1e-9) {
-                best = score;
-                best_stride = stp;
-            }
-        }
-        if (best >= 0.75) {
-            cd.pair_stride = best_stride;
-            cd.pair_groups = ncell / (2 * best_stride);
-            int per_sm_pair = 0;
-            SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, D + 1, P, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pair, dg_class_apply<NLD, D + 1, P, true, true, true>, CB, smem));
-            const long items = cd.pair_groups * best_stride + (ncell - cd.pair_groups * 2 * best_stride);
-            long gp = (long)(per_sm_pair > 0 ? per_sm_pair : 1) * op->ctx->sm_count;
-            const long needp = (items + CB - 1) / CB;
-            if (gp > needp) gp = needp;
-            if (gp > SG_MAX_BLOCKS) gp = SG_MAX_BLOCKS;
-            op->cls_grid_pair = (int)gp;
-        }
-    }
     if (dv.n_bf > 0) {
         // exterior facets from per-facet linearised boundary matrices (sg_thermal_linearize); DG applies them inside
         // the class kernel through its own copy of the neighbour ids with the exterior facets encoded
@@ -1708,19 +1551,13 @@ int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, dou
     return op->cheb_step(op, cs, red, dot_out, skip, st);
 }
 
-bool sg_thermal_can_split(const sg_thermal_op *op) {
-    return op->d.family == 1 && op->cls.tab != nullptr && op->cls.pair_stride == 0 && op->split_hi > op->split_lo &&
-           (op->bmat != nullptr || op->d.n_bfacets == 0);
-}
-
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,
-                         const int *skip, cudaStream_t st, int y_is_zero, int part) {
-    SG_REQUIRE(part == SG_PART_ALL || sg_thermal_can_split(op), "sg_thermal_apply_dot: this operator cannot be split");
+                         const int *skip, cudaStream_t st, int y_is_zero, const SgHaloWait *wait) {
     op->y_is_zero = y_is_zero;
-    op->part = part;
+    op->wait = wait;
     const int rc = op->launch(op, MODE_APPLY, T_lin, x, nullptr, y, red, dot2, skip, st);
     op->y_is_zero = 0;
-    op->part = SG_PART_ALL;
+    op->wait = nullptr;
     return rc;
 }
 
@@ -1761,6 +1598,7 @@ int sg_thermal_op_create(sg_ctx *ctx, const sg_thermal_desc *d, sg_thermal_op **
     SG_REQUIRE(d->family == 0 || d->family == 1, "sg_thermal_op_create: family must be 0 (CG) or 1 (DG)");
     SG_REQUIRE(d->n_cells >= 0 && d->cell_lo >= 0 && d->cell_lo <= d->cell_hi && d->cell_hi <= d->n_cells,
                "sg_thermal_op_create: bad cell range");
+    SG_REQUIRE(d->n_cells < (int64_t)0x7fffffff, "sg_thermal_op_create: cell ids are 32-bit (int32 neighbour ids / dofmap)");
     SG_REQUIRE(d->own_lo >= 0 && d->own_lo <= d->own_hi && d->own_hi <= d->n_dofs, "sg_thermal_op_create: bad owned dof range");
     SG_REQUIRE(d->own_cell_lo >= 0 && d->own_cell_lo <= d->own_cell_hi && d->own_cell_hi <= d->n_cells,
                "sg_thermal_op_create: bad owned cell range");

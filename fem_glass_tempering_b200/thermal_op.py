@@ -34,8 +34,7 @@ class ThermalOperator:
     """
 
     def __init__(self, ctx: _lib.Context, space: fe.ScalarSpace, params: dict, dt: float, partition: dict | None = None,
-                 use_classes: bool = True, cheb_degree: int | None = None, use_pairs: bool | None = None,
-                 use_stencil: bool | None = None):
+                 use_classes: bool = True, cheb_degree: int | None = None, use_stencil: bool | None = None):
         import torch
         self.ctx, self.space, self.dt = ctx, space, float(dt)
         mesh, d = space.mesh, space.mesh.dim
@@ -80,9 +79,6 @@ class ThermalOperator:
         desc.n_cells, desc.cell_lo, desc.cell_hi = nc, part.get("cell_lo", 0), part.get("cell_hi", nc)
         desc.n_dofs, desc.own_lo, desc.own_hi = space.n_nodes, part.get("own_lo", 0), part.get("own_hi", space.n_nodes)
         desc.own_cell_lo, desc.own_cell_hi = part.get("own_cell_lo", desc.cell_lo), part.get("own_cell_hi", desc.cell_hi)
-        if use_pairs is None:
-            import os
-            use_pairs = os.environ.get("SG_PAIRS", "0") == "1"      # two cells per thread: measured slower, opt-in
         if use_stencil is None:
             # CG: gather form of the apply where rows repeat (csrc/stencil.cu).  It needs a second small launch for the
             # exterior facets, so meshes whose kernels are launch-latency bound anyway (config 2: 334 k rows, 4 us
@@ -90,8 +86,8 @@ class ThermalOperator:
             import os
             env = os.environ
             use_stencil = (env.get("SG_NO_STENCIL", "0") != "1") and (env.get("SG_STENCIL", "0") == "1" or space.n_nodes >= STENCIL_MIN_ROWS)
-        # SG_THERMAL_NO_CLASSES, SG_THERMAL_PAIRS, SG_THERMAL_NO_STENCIL
-        desc.flags = (0 if use_classes else 1) | (4 if use_pairs else 0) | (0 if use_stencil else 8)
+        # SG_THERMAL_NO_CLASSES, SG_THERMAL_NO_STENCIL
+        desc.flags = (0 if use_classes else 1) | (0 if use_stencil else 8)
         for name in ("dofmap", "geom", "nbr", "nbinfo", "bf_cell", "bf_facet", "bf_area"):
             setattr(desc, name, _lib.ptr(keep.get(name)))
         desc.n_bfacets = nbf
@@ -134,12 +130,18 @@ class ThermalOperator:
             _lib.check(L.sg_halo_plan_create(ctx.handle, len(segs), arr, C.byref(hh)))
             self.halo = hh
         self.peer_memory = False
+        nws = max(int(L.sg_thermal_solver_workspace_doubles(self.handle)), 1)
+        ws_ptr = None
         if ctx.nranks > 1:
-            self._setup_peer_memory(L)
-        nws = L.sg_thermal_solver_workspace_doubles(self.handle)
-        self.workspace = torch.zeros(max(int(nws), 1), dtype=torch.float64, device=dev)
+            ws_ptr = self._setup_peer_memory(L, nws, segs)
+        if ws_ptr:
+            self.workspace = None                   # the vectors live in the IPC-exported communication block (direct halo puts)
+        else:
+            self.workspace = torch.zeros(nws, dtype=torch.float64, device=dev)
+            ws_ptr = self.workspace.data_ptr()
+        self._ws_ptr, self._ws_doubles = int(ws_ptr), nws
         sh = C.c_void_p()
-        _lib.check(L.sg_thermal_solver_create(self.handle, self.workspace.data_ptr(), self.halo, C.byref(sh)))
+        _lib.check(L.sg_thermal_solver_create(self.handle, ws_ptr, self.halo, C.byref(sh)))
         self.solver = sh
         self.opts = NewtonOptsC(1e-12, 1e-10, 50, 1e-12, 0.0, 10000, 1e-3)
         self.chebyshev_degree = 0
@@ -151,17 +153,20 @@ class ThermalOperator:
             self.set_chebyshev(cheb_degree)
         self.last_stats = None
 
-    def _setup_peer_memory(self, L) -> None:
+    def _setup_peer_memory(self, L, workspace_doubles: int, segs):
         """NVLink peer-memory transport of the halo / small all-reduces (sg_halo_peer_alloc/open): every rank exports one
-        communication block, the 64-byte IPC handles travel through torch.distributed.  Collective over all ranks;
-        SG_NO_PEER=1 keeps NCCL on the data path."""
+        communication block that also holds the solver workspace; the 64-byte IPC handles and each rank's vector layout
+        (stride, where the rows from below / above land) travel through torch.distributed.  Collective over all ranks;
+        SG_NO_PEER=1 keeps NCCL on the data path.  Returns the workspace pointer inside the block, or None."""
         import os
         import torch.distributed as dist
         handle = C.create_string_buffer(64)
         rc = 0
         if self.halo is not None and os.environ.get("SG_NO_PEER", "0") != "1":
-            rc = L.sg_halo_peer_alloc(self.halo, handle)
-        mine = handle.raw if rc == 1 else None
+            rc = L.sg_halo_peer_alloc(self.halo, handle, workspace_doubles)
+        below = next((ro for peer, so, sc, ro, rcn in segs if peer < self.ctx.rank), 0)
+        above = next((ro for peer, so, sc, ro, rcn in segs if peer > self.ctx.rank), 0)
+        mine = (handle.raw, (int(self.n_dofs), int(below), int(above))) if rc == 1 else None
         everyone = [None] * self.ctx.nranks
         dist.all_gather_object(everyone, mine)
         # every rank runs the same two collectives, also one without a halo plan (it reports False and
@@ -169,17 +174,19 @@ class ThermalOperator:
         ok = False
         if self.halo is not None:
             if all(h is not None for h in everyone):
-                blob = C.create_string_buffer(b"".join(everyone), 64 * self.ctx.nranks)
-                ok = L.sg_halo_peer_open(self.halo, blob) == 0
+                blob = C.create_string_buffer(b"".join(h[0] for h in everyone), 64 * self.ctx.nranks)
+                layout = (C.c_int64 * (3 * self.ctx.nranks))(*[v for h in everyone for v in h[1]])
+                ok = L.sg_halo_peer_open(self.halo, blob, layout) == 0
             else:
-                L.sg_halo_peer_open(self.halo, None)
+                L.sg_halo_peer_open(self.halo, None, None)
         flags = [None] * self.ctx.nranks
         dist.all_gather_object(flags, bool(ok and L.sg_halo_uses_peer_memory(self.halo)))
         if self.halo is None:
-            return
+            return None
         if not all(flags):                       # one rank could not map a neighbour: nobody uses the peer path
-            L.sg_halo_peer_open(self.halo, None)
+            L.sg_halo_peer_open(self.halo, None, None)
         self.peer_memory = bool(L.sg_halo_uses_peer_memory(self.halo))
+        return L.sg_halo_peer_workspace(self.halo) if self.peer_memory else None
 
     # -- raw operator calls (asynchronous on the current stream) ---------------------------------
     def residual(self, T, T_prev, out):
@@ -254,9 +261,18 @@ class ThermalOperator:
 
     def prepare_preconditioner(self, T_lin):
         n = self.n_dofs
-        dinv = self.workspace[5 * n: 6 * n]
+        dinv = self.workspace_view(5)
         self.jac_diag(T_lin, dinv)
         dinv.reciprocal_()
+
+    def workspace_view(self, k: int):
+        """Vector k of the solver workspace (b, dx, r, p, Ap, dinv, zA, zB) as a torch tensor (tests, diagnostics)."""
+        import torch
+        n = self.n_dofs
+        if self.workspace is not None:
+            return self.workspace[k * n:(k + 1) * n]
+        from ._lib import tensor_from_ptr
+        return tensor_from_ptr(self._ws_ptr + 8 * k * n, n, torch.device("cuda", self.ctx.device))
 
     def timestep(self, T, T_prev) -> NewtonStatsC:
         """Newton solve of F(T) = 0 in place on T (NewtonSolver.solve, ThermoViscoProblem.py:389)."""

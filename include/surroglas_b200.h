@@ -181,9 +181,6 @@ typedef struct {
 enum {
     SG_THERMAL_NO_CLASSES = 1,      /* never use the local-matrix class tables (general per-cell-geometry kernel only) */
     SG_THERMAL_GENERAL_RESIDUAL = 2,/* evaluate the residual with the per-cell-geometry kernel even when the tables exist */
-    SG_THERMAL_PAIRS = 4,           /* DG class kernels: two cells per thread sharing the shared-memory table reads.  Off by
-                                       default: measured SLOWER on B200 (Chebyshev step 211 vs 183 us on C3; 128 registers halve
-                                       the resident warps), kept for experiments */
     SG_THERMAL_NO_STENCIL = 8       /* CG spaces: never use the row-stencil form of the Jacobian apply (see
                                        sg_thermal_stencil_info); the cell-centric class kernel scatters instead */
 };
@@ -230,13 +227,20 @@ int sg_halo_plan_create(sg_ctx *ctx, int32_t n_segments, const sg_halo_segment *
 int sg_halo_plan_destroy(sg_halo_plan *plan);
 int sg_halo_forward(sg_halo_plan *plan, double *vec, int32_t block_size, void *stream);
 /* Optional NVLink peer-memory transport for block_size 1 exchanges and the solver's 1-2 double all-reduces (one
- * process per GPU, all on one NVSwitch domain): boundary rows are stored straight into the neighbour's memory and
- * published with a sequence flag; no NCCL launch on the data path.  sg_halo_peer_alloc returns 1 and a 64-byte
+ * process per GPU, all on one NVSwitch domain; replaces PETSc's MPI halo + MPI_Allreduce inside KSP cg, TVP:339-346):
+ * every rank allocates ONE IPC-exported block holding flags, all-reduce slots, mailboxes and - when workspace_doubles > 0
+ * - the solver's vector workspace.  Vectors inside that workspace are exchanged by storing the boundary rows straight
+ * into the neighbour's ghost rows (one kernel, no receive-side copy; the consuming operator kernel waits for the flag
+ * before its boundary strips only), any other vector goes through the mailboxes; the all-reduces run inside the last
+ * block of the reducing kernels.  No NCCL launch on the data path.  sg_halo_peer_alloc returns 1 and a 64-byte
  * cudaIpcMemHandle_t when the plan qualifies (0 otherwise, <0 on error); the host gathers the handles of ALL ranks
- * (rank order, 64 bytes each) and passes them to sg_halo_peer_open, or NULL if any rank returned 0.  Waits are
- * bounded: a neighbour that never arrives turns into SG_E_NCCL at the next host synchronisation, not a hang. */
-int sg_halo_peer_alloc(sg_halo_plan *plan, void *handle64);
-int sg_halo_peer_open(sg_halo_plan *plan, const void *handles);
+ * (rank order, 64 bytes each) and, per rank, three int64 {vector stride = n_dofs, recv_offset of the rows arriving from
+ * the rank below, recv_offset of the rows arriving from above} and passes both tables to sg_halo_peer_open, or NULLs
+ * if any rank returned 0.  sg_halo_peer_workspace returns the workspace to hand to sg_thermal_solver_create (NULL: none).
+ * Waits are bounded: a neighbour that never arrives turns into SG_E_NCCL at the next host synchronisation, not a hang. */
+int sg_halo_peer_alloc(sg_halo_plan *plan, void *handle64, int64_t workspace_doubles);
+int sg_halo_peer_open(sg_halo_plan *plan, const void *handles, const int64_t *layout3);
+double *sg_halo_peer_workspace(const sg_halo_plan *plan);
 int sg_halo_uses_peer_memory(const sg_halo_plan *plan);
 
 /* Newton + Jacobi-PCG time-step solver (NewtonSolver.solve, TVP:334-346,389). */

@@ -6,7 +6,7 @@
 Every rank steps its x-slab of a plate through ThermoViscoProblem (halo exchange + all-reduced PCG scalars through
 the library's NCCL communicator); rank 0 additionally steps the WHOLE plate on its GPU with a single-rank context
 and compares temperature / fictive temperature / stress on every rank's owned nodes.  Tolerances: T, Tf 1e-10
-relative (north_star); stress 1e-8 of max (bounded by the conditioning of the reference's formula).
+relative (north_star); stress 1e-9 of max (bounded by the conditioning of the reference's formula).
 Prints one line 'MULTIGPU_CHECK OK ...' on rank 0 and exits non-zero on failure."""
 import os
 import sys
@@ -113,7 +113,7 @@ def main():
                 if fin.any():
                     worst["sigma"] = max(worst["sigma"], np.max(np.abs(a[fin] - b[fin])) / np.max(np.abs(b[fin])))
             tiles = bool((seen == 1).all())
-            good = tiles and worst["T"] <= 1e-10 and worst["Tf"] <= 1e-10 and worst["sigma"] <= 1e-8
+            good = tiles and worst["T"] <= 1e-10 and worst["Tf"] <= 1e-10 and worst["sigma"] <= 1e-9
             ok = ok and good
             report.append(f"{fam}{deg} d={dim} n={n}: owned ranges tile={tiles} relerr T={worst['T']:.1e} Tf={worst['Tf']:.1e} "
                           f"sigma={worst['sigma']:.1e} its(ref)={ref.solver.last_stats.newton_its}/{ref.solver.last_stats.lin_its} "

@@ -221,34 +221,6 @@ def test_chebyshev_is_not_offered_for_cg_spaces(sg_ctx):
     assert op.chebyshev_degree == 0 and not op.set_chebyshev(3)
 
 
-@pytest.mark.parametrize("dims", [(20, 16, 8), (9, 8, 8), (8, 8, 4)])
-def test_two_cells_per_thread_kernels_match_single(sg_ctx, dims):
-    """DG1 3-D class kernels with two cells per thread (pairs one tile-pair apart sharing the table reads, plus the
-    unpaired tail and pairs whose classes differ) against the one-cell-per-thread kernels and the oracle."""
-    m = msh.box_mesh(*dims, *(float(k) for k in dims))
-    space = fe.ScalarSpace(m, "DG", 1)
-    n = space.n_nodes
-    rng = np.random.default_rng(4)
-    T = 700 + 100 * rng.random(n)
-    x = rng.standard_normal(n)
-    b = rng.standard_normal(n)
-    out = {}
-    for pairs in (True, False):
-        op = ThermalOperator(sg_ctx, space, MAIN_PARAMS, 0.1, use_pairs=pairs, cheb_degree=3)
-        y = torch.empty(n, dtype=torch.float64, device="cuda:0")
-        op.jac_apply(dev(T), dev(x), y)
-        xd = torch.zeros(n, dtype=torch.float64, device="cuda:0")
-        its, res = op.pcg(dev(T), dev(b), xd, rtol=1e-12)
-        out[pairs] = (y.cpu().numpy(), xd.cpu().numpy(), its)
-    assert np.max(np.abs(out[True][0] - out[False][0])) <= 1e-13 * np.max(np.abs(out[False][0]))
-    assert np.max(np.abs(out[True][1] - out[False][1])) <= 1e-10 * np.max(np.abs(out[False][1]))
-    assert abs(out[True][2] - out[False][2]) <= 1
-    if dims == (8, 8, 4):
-        orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "DG", 1, MAIN_PARAMS, 0.1)
-        yo = orc.jacobian(T) @ x
-        assert np.max(np.abs(out[True][0] - yo)) <= 1e-12 * np.max(np.abs(yo))
-
-
 @pytest.mark.parametrize("dim,family,degree", [(2, "CG", 2), (3, "CG", 2), (3, "DG", 1), (1, "DG", 1)])
 def test_cuda_graph_batches_match_plain_launches(sg_ctx, dim, family, degree, monkeypatch):
     """The plain PCG replays batches of 8 iterations as a CUDA graph on the solver's own stream; SG_NO_GRAPHS=1 launches
