@@ -470,6 +470,13 @@ struct sg_thermal_solver {
     cudaGraphExec_t batch_graph;
     const double *graph_T, *graph_x;
     int use_graphs;
+    // Direct halo puts run on a side stream: the put of exchange e waits (event) for the kernel that produced its rows and
+    // the consumer - which only needs the NEIGHBOUR's put, awaited inside the kernel - starts at once, so neither the put's
+    // launch nor its transfer sits on the solver's critical path.  The next exchange first makes the solver stream wait for
+    // put e (long finished by then): a later kernel may overwrite the rows it read.
+    cudaStream_t side;
+    cudaEvent_t ev_produced, ev_put;
+    int put_pending;
 };
 
 namespace {
@@ -483,9 +490,15 @@ int allreduce(sg_thermal_solver *s, double *ptr, int count, cudaStream_t st) {
     return SG_OK;
 }
 
+int halo_drain(sg_thermal_solver *s, cudaStream_t st);
+
 int read_scalars(sg_thermal_solver *s, int first, int count, cudaStream_t st) {
     (void)first;
     (void)count;
+    {
+        const int rcd = halo_drain(s, st);
+        if (rcd) return rcd;
+    }
     k_mirror<<<1, 32, 0, st>>>(s->S, s->ctrl, s->S_host, s->ctrl_host);
     SG_CHECK_CUDA(cudaGetLastError());
     SG_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -498,8 +511,26 @@ int read_scalars(sg_thermal_solver *s, int first, int count, cudaStream_t st) {
 int halo_start(sg_thermal_solver *s, double *vec, SgHaloWait *wait, cudaStream_t st) {
     memset(wait, 0, sizeof(*wait));
     if (!s->halo) return SG_OK;
-    if (sg_peer_ready(s->halo->peer)) return sg_peer_put(s->halo->peer, s->halo->n, s->halo->seg, vec, wait, st);
-    return sg_halo_forward(s->halo, vec, 1, st);
+    if (!sg_peer_ready(s->halo->peer)) return sg_halo_forward(s->halo, vec, 1, st);
+    if (!s->side || !sg_peer_in_workspace(s->halo->peer, vec))
+        return sg_peer_put(s->halo->peer, s->halo->n, s->halo->seg, vec, wait, st);
+    if (s->put_pending) SG_CHECK_CUDA(cudaStreamWaitEvent(st, s->ev_put, 0));      // the previous put has read its rows
+    SG_CHECK_CUDA(cudaEventRecord(s->ev_produced, st));
+    SG_CHECK_CUDA(cudaStreamWaitEvent(s->side, s->ev_produced, 0));
+    const int rc = sg_peer_put(s->halo->peer, s->halo->n, s->halo->seg, vec, wait, s->side);
+    if (rc) return rc;
+    SG_CHECK_CUDA(cudaEventRecord(s->ev_put, s->side));
+    s->put_pending = 1;
+    return SG_OK;
+}
+
+// Before anything outside the iteration touches the workspace: the last side-stream put must have finished.
+int halo_drain(sg_thermal_solver *s, cudaStream_t st) {
+    if (s->put_pending) {
+        SG_CHECK_CUDA(cudaStreamWaitEvent(st, s->ev_put, 0));
+        s->put_pending = 0;
+    }
+    return SG_OK;
 }
 
 template <int NLD>
@@ -911,6 +942,9 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     s->S_host = nullptr;
     s->ctrl = s->ctrl_host = nullptr;
     s->own = nullptr;
+    s->side = nullptr;
+    s->ev_produced = s->ev_put = nullptr;
+    s->put_pending = 0;
     s->ev_in = s->ev_out = nullptr;
     s->batch_graph = nullptr;
     s->graph_T = s->graph_x = nullptr;
@@ -937,7 +971,24 @@ int sg_thermal_solver_create(sg_thermal_op *op, double *workspace, sg_halo_plan 
     }
     // peer-memory path: all-reduces run inside the reducing kernels; the direct halo put needs the workspace to be the
     // IPC-visible one (sg_halo_peer_workspace) — any other workspace still works through the mailboxes
-    if (halo && sg_peer_ready(halo->peer)) s->red.peer = sg_peer_red_dev(halo->peer);
+    if (halo && sg_peer_ready(halo->peer)) {
+        s->red.peer = sg_peer_red_dev(halo->peer);
+        const char *ns = getenv("SG_NO_SIDE_STREAM");
+        if (!(ns && ns[0] == '1')) {
+            // highest priority: when a producer kernel retires, the pending put's blocks are dispatched before the blocks of
+            // the (persistent, SM-filling) consumer kernel launched right behind it on the solver stream
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            cudaError_t e2 = cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, prio_hi);
+            if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&s->ev_produced, cudaEventDisableTiming);
+            if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&s->ev_put, cudaEventDisableTiming);
+            if (e2 != cudaSuccess) {
+                sg_set_error("sg_thermal_solver_create: %s", cudaGetErrorString(e2));
+                sg_thermal_solver_destroy(s);
+                return SG_E_CUDA;
+            }
+        }
+    }
     *out = s;
     return SG_OK;
 }
@@ -953,6 +1004,12 @@ int sg_thermal_solver_destroy(sg_thermal_solver *s) {
         cudaStreamSynchronize(s->own);
         cudaStreamDestroy(s->own);
     }
+    if (s->side) {
+        cudaStreamSynchronize(s->side);
+        cudaStreamDestroy(s->side);
+    }
+    if (s->ev_produced) cudaEventDestroy(s->ev_produced);
+    if (s->ev_put) cudaEventDestroy(s->ev_put);
     if (s->ev_in) cudaEventDestroy(s->ev_in);
     if (s->ev_out) cudaEventDestroy(s->ev_out);
     if (s->ctrl) cudaFree(s->ctrl);

@@ -63,18 +63,21 @@ struct PushArgs {
     unsigned long long seq;
 };
 
-// also the direct put: only dst/flag differ
-__global__ void __launch_bounds__(256) k_halo_push(const PushArgs a) {
-    const PushSeg s = a.seg[blockIdx.y];
+// also the direct put: only dst/flag differ.  128-thread blocks of <= 32 registers: 4096 registers is what the persistent
+// operator kernels (3 blocks x 256 threads x 80 registers) leave free on an SM, so a put launched on the high-priority
+// side stream runs NEXT TO the consumer kernel instead of waiting for its blocks to retire.
+constexpr int PTB = 128;
+__global__ void __launch_bounds__(PTB, 16) k_halo_push(const PushArgs a) {
+    const PushSeg s = blockIdx.y == 0 ? a.seg[0] : a.seg[1];   // no dynamic indexing of the parameter struct (no local copy)
     if (s.count <= 0) return;
     if ((((uintptr_t)s.src | (uintptr_t)s.dst) & 15) == 0) {
         const long n2 = s.count >> 1;
         const double2 *src2 = reinterpret_cast<const double2 *>(s.src);
         double2 *dst2 = reinterpret_cast<double2 *>(s.dst);
-        for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n2; i += (long)gridDim.x * 256) dst2[i] = src2[i];
+        for (long i = (long)blockIdx.x * PTB + threadIdx.x; i < n2; i += (long)gridDim.x * PTB) dst2[i] = src2[i];
         if ((s.count & 1) && blockIdx.x == 0 && threadIdx.x == 0) s.dst[s.count - 1] = s.src[s.count - 1];
     } else {   // ranges that start at an odd dof (small CG planes)
-        for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < s.count; i += (long)gridDim.x * 256) s.dst[i] = s.src[i];
+        for (long i = (long)blockIdx.x * PTB + threadIdx.x; i < s.count; i += (long)gridDim.x * PTB) s.dst[i] = s.src[i];
     }
     __threadfence_system();
     __syncthreads();
@@ -247,7 +250,7 @@ int sg_peer_check(SgPeer *p) {
 }
 
 // segments: at most one neighbour below and one above this rank (x-slab partition)
-static dim3 halo_grid(int n_seg, const sg_halo_segment *seg) {
+static dim3 halo_grid(int n_seg, const sg_halo_segment *seg, int push_scale = 1) {
     long maxcount = 0;
     for (int i = 0; i < n_seg && i < 2; ++i) {
         if (seg[i].send_count > maxcount) maxcount = seg[i].send_count;
@@ -256,6 +259,7 @@ static dim3 halo_grid(int n_seg, const sg_halo_segment *seg) {
     long gx = (maxcount / 2 + 255) / 256;
     if (gx < 1) gx = 1;
     if (gx > 64) gx = 64;
+    gx *= push_scale;
     return dim3((unsigned)gx, (unsigned)(n_seg < 2 ? (n_seg < 1 ? 1 : n_seg) : 2));
 }
 
@@ -279,7 +283,7 @@ static int sg_peer_halo_push(SgPeer *p, int n_seg, const sg_halo_segment *seg, c
     }
     pa.counters = p->counters;
     pa.seq = seq;
-    k_halo_push<<<halo_grid(n_seg, seg), 256, 0, st>>>(pa);
+    k_halo_push<<<halo_grid(n_seg, seg, 256 / PTB), PTB, 0, st>>>(pa);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;
@@ -313,12 +317,18 @@ int sg_peer_halo_forward(SgPeer *p, int n_seg, const sg_halo_segment *seg, doubl
     return rc ? rc : sg_peer_halo_pull(p, n_seg, seg, vec, st);
 }
 
+bool sg_peer_in_workspace(const SgPeer *p, const double *vec) {
+    const double *ws = sg_peer_workspace(p);
+    const int64_t stride = p ? p->stride[p->ctx->rank] : 0;
+    return ws && stride > 0 && vec >= ws && vec < ws + p->workspace_doubles && ((vec - ws) % stride) == 0;
+}
+
 int sg_peer_put(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, SgHaloWait *wait, cudaStream_t st) {
     memset(wait, 0, sizeof(*wait));
     const int rank = p->ctx->rank;
     double *ws = sg_peer_workspace(p);
     const int64_t stride = p->stride[rank];
-    const bool inside = ws && stride > 0 && vec >= ws && vec < ws + p->workspace_doubles && ((vec - ws) % stride) == 0;
+    const bool inside = sg_peer_in_workspace(p, vec);
     if (!inside) return sg_peer_halo_forward(p, n_seg, seg, vec, st);     // mailbox path: complete on return (stream order)
     const int64_t slot = (vec - ws) / stride;
     const unsigned long long seq = ++p->direct_seq;
@@ -344,7 +354,7 @@ int sg_peer_put(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, S
     wait->err = p->err_host;
     pa.counters = p->counters;
     pa.seq = seq;
-    k_halo_push<<<halo_grid(n_seg, seg), 256, 0, st>>>(pa);
+    k_halo_push<<<halo_grid(n_seg, seg, 256 / PTB), PTB, 0, st>>>(pa);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;

@@ -115,6 +115,7 @@ int sg_peer_halo_forward(SgPeer *p, int n_seg, const sg_halo_segment *seg, doubl
 // direct path (vectors inside the IPC workspace): ONE kernel stores the boundary rows straight into the neighbour's ghost
 // rows of the same vector and raises its flag; *wait tells the consumer what to wait for.  Returns SG_OK and wait->n = 0
 // after falling back to the mailbox path (vector outside the workspace).
+bool sg_peer_in_workspace(const SgPeer *p, const double *vec);
 int sg_peer_put(SgPeer *p, int n_seg, const sg_halo_segment *seg, double *vec, SgHaloWait *wait, cudaStream_t st);
 int sg_peer_wait(SgPeer *p, const SgHaloWait &wait, cudaStream_t st);   // one-warp kernel for consumers without an in-kernel wait
 int sg_peer_allreduce(SgPeer *p, double *vals, int count, cudaStream_t st);
@@ -252,11 +253,17 @@ __device__ __forceinline__ double sg_block_sum(double v, double *scratch) {
     return v;
 }
 
-// Bounded spin on a flag another GPU (or another block) raises; false on expiry (about 20 s).
+// Bounded spin on a flag another GPU raises after fencing its data stores; false on expiry (about 20 s).  The flag is read
+// with ld.acquire.sys: everything the writer published before the flag is visible to loads that follow — no
+// system-scope fence (MEMBAR.SC.SYS costs microseconds per block when 444 blocks issue it at the end of a kernel).
+__device__ __forceinline__ unsigned long long sg_ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ bool sg_spin_until(const unsigned long long *flag, unsigned long long seq) {
-    const volatile unsigned long long *f = flag;
     const long long t0 = clock64();
-    while (*f < seq) {
+    while (sg_ld_acquire_sys(flag) < seq) {
         if (clock64() - t0 > 40000000000ll) return false;
         __nanosleep(32);
     }
@@ -264,13 +271,24 @@ __device__ __forceinline__ bool sg_spin_until(const unsigned long long *flag, un
 }
 
 // Block-level wait for ghost rows (SgHaloWait); every thread of the block must call it.  Not inlined: it runs once per
-// block and must not cost the hot loops of the operator kernels any registers.
+// block and must not cost the hot loops of the operator kernels any registers.  The acquire by threads 0/1 reaches the
+// rest of the block through the barrier; the block has not read a ghost row before (interior cells come first) and L1 is
+// invalid at kernel start, so no stale line can be hit.
 static __device__ __noinline__ void sg_halo_wait_block(const SgHaloWait &w) {
     if (w.n == 0) return;
     if (threadIdx.x < (unsigned)w.n) {
         const unsigned long long *f = threadIdx.x == 0 ? w.flag[0] : w.flag[1];   // no dynamic indexing of the parameter struct
         if (!sg_spin_until(f, w.seq)) *w.err = 1;
-        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// The same wait inlined (a handful of instructions after the main sweep of the class kernels).
+__device__ __forceinline__ void sg_halo_wait_inline(const SgHaloWait &w) {
+    if (threadIdx.x == 0) {
+        bool ok = sg_spin_until(w.flag[0], w.seq);
+        if (w.n > 1) ok = sg_spin_until(w.flag[1], w.seq) && ok;
+        if (!ok) *w.err = 1;
     }
     __syncthreads();
 }
@@ -296,19 +314,17 @@ __device__ __forceinline__ void sg_peer_allreduce_warp(const SgPeerRedDev &a, do
         ok = sg_spin_until(tag, seq);
     }
     ok = __all_sync(0xffffffffu, ok);
-    __threadfence_system();
+    // every lane reads the slot whose tag IT acquired; lane 0 adds them in rank order (bit-identical on every rank)
+    const volatile double *v =
+        reinterpret_cast<const volatile double *>(a.base[a.rank] + a.vals_off) + ((size_t)par * SG_PEER_MAX_RANKS + (t < a.nranks ? t : 0)) * SG_PEER_RED_VALS;
+    for (int k = 0; k < count; ++k) {
+        const double mine = (ok && t < a.nranks) ? v[k] : 0.0;
+        double s = 0.0;
+        for (int r = 0; r < a.nranks; ++r) s += __shfl_sync(0xffffffffu, mine, r);
+        if (t == 0 && ok) vals[k] = s;
+    }
     if (t == 0) {
-        if (!ok) {
-            *a.err = 1;
-        } else {
-            const volatile double *v =
-                reinterpret_cast<const volatile double *>(a.base[a.rank] + a.vals_off) + (size_t)par * SG_PEER_MAX_RANKS * SG_PEER_RED_VALS;
-            for (int k = 0; k < count; ++k) {
-                double s = 0.0;
-                for (int r = 0; r < a.nranks; ++r) s += v[(size_t)r * SG_PEER_RED_VALS + k];   // fixed rank order on every rank
-                vals[k] = s;
-            }
-        }
+        if (!ok) *a.err = 1;
         *a.seq = seq;
         __threadfence_system();
     }

@@ -158,34 +158,40 @@ __global__ void __launch_bounds__(STB, MINB) k_stencil_apply(const StDev sd, con
         ptr = s_ptr;
     }
     double dsum[2] = {0.0, 0.0};
-#pragma unroll 1
-    for (int rg = 0; rg < 3; ++rg) {
-        const long lo = rg == 0 ? sd.safe_lo : (rg == 1 ? 0 : sd.safe_hi);
-        const long hi = rg == 0 ? sd.safe_hi : (rg == 1 ? sd.safe_lo : sd.n_rows);
-        if (rg == 1) sg_halo_wait_block(hw);   // rows next to the slab faces read the neighbours' ghost rows
-        for (long row = lo + (long)blockIdx.x * STB + threadIdx.x; row < hi; row += (long)gridDim.x * STB) {
-            const int c = sd.rcls[row];
-            const int p1 = ptr[c + 1];
-            int k = ptr[c];
-            const double *xr = x + row;
-            double acc = 0.0;
-            for (; k + U <= p1; k += U) {
-                Entry e[U];
-                double xv[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) e[u] = ent[k + u];
-#pragma unroll
-                for (int u = 0; u < U; ++u) xv[u] = __ldg(xr + e[u].off);
-#pragma unroll
-                for (int u = 0; u < U; ++u) acc = fma(e[u].coef, xv[u], acc);
-            }
-            for (; k < p1; ++k) {
-                const Entry e = ent[k];
-                acc = fma(e.coef, __ldg(xr + e.off), acc);
-            }
-            y[row] = acc;
-            if (row >= sd.own_lo && row < sd.own_hi) dsum[0] += __ldg(xr) * acc;
+    // one sweep over idx in [0, n_rows): the rows that read no ghost value first, the rows next to the slab faces at the end
+    // of the index space (only blocks in their last iteration wait for the neighbours' puts)
+    const long n_safe = sd.safe_hi - sd.safe_lo;
+    bool waited = hw.n == 0;
+    for (long base = (long)blockIdx.x * STB; base < sd.n_rows; base += (long)gridDim.x * STB) {
+        if (!waited && base + STB > n_safe) {     // block-uniform; blocks whose rows are all safe never wait and retire
+            sg_halo_wait_block(hw);
+            waited = true;
         }
+        const long idx = base + threadIdx.x;
+        if (idx >= sd.n_rows) continue;
+        const long j = idx - n_safe;
+        const long row = idx < n_safe ? sd.safe_lo + idx : (j < sd.safe_lo ? j : sd.safe_hi + (j - sd.safe_lo));
+        const int c = sd.rcls[row];
+        const int p1 = ptr[c + 1];
+        int k = ptr[c];
+        const double *xr = x + row;
+        double acc = 0.0;
+        for (; k + U <= p1; k += U) {
+            Entry e[U];
+            double xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) e[u] = ent[k + u];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = __ldg(xr + e[u].off);
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc = fma(e[u].coef, xv[u], acc);
+        }
+        for (; k < p1; ++k) {
+            const Entry e = ent[k];
+            acc = fma(e.coef, __ldg(xr + e.off), acc);
+        }
+        y[row] = acc;
+        if (row >= sd.own_lo && row < sd.own_hi) dsum[0] += __ldg(xr) * acc;
     }
     sg_grid_reduce<2>(dsum, red, dot_out);
 }

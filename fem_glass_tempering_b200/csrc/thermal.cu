@@ -626,12 +626,6 @@ struct ClsDev {
     int rev;   // sweep direction of this launch (sg_sweep_begin)
 };
 
-// The three cell ranges of a class-kernel launch in processing order: interior, lower strip, upper strip.
-__device__ __forceinline__ void cls_range(const ClsDev &cd, int rg, long &lo, long &hi) {
-    lo = rg == 0 ? cd.split_lo : (rg == 1 ? cd.cell_lo : cd.split_hi);
-    hi = rg == 0 ? cd.split_hi : (rg == 1 ? cd.split_lo : cd.cell_hi);
-}
-
 constexpr int CB = 256;  // threads per block of the class kernels
 
 struct __align__(32) Row4 {
@@ -764,7 +758,7 @@ __device__ __forceinline__ void load_class_tables(const ClsDev &cd, double *s_ta
 // DG fast apply: persistent grid-stride blocks, class tables in shared memory, fused x.y reduction.
 // A warp handles 32 consecutive cells; when these share their classes (the plate meshes number the cells
 // in class-uniform tiles of 32, mesh.py) every table read is a shared-memory broadcast.
-template <int NLD, int NNB, int P, bool WIDE, bool BND, bool HALO>
+template <int NLD, int NNB, int P, bool WIDE, bool BND>
 __global__ void __launch_bounds__(CB, 3) dg_class_apply(const ClsDev cd, const double *__restrict__ x, double *__restrict__ y,
                                                         SgRed red, double *dot_out, const int *skip, const SgHaloWait hw) {
     extern __shared__ __align__(16) double s_tab[];
@@ -772,22 +766,28 @@ __global__ void __launch_bounds__(CB, 3) dg_class_apply(const ClsDev cd, const d
     load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
     const double *s_nb = s_tab + cd.n_self * cd.S;
     double dsum[2] = {0.0, 0.0};   // [1] stays 0: slot of the separate exterior-facet kernel (overwritten by it when it runs)
-#pragma unroll 1
-    for (int rg = 0; rg < (HALO ? 3 : 1); ++rg) {
-        long lo = cd.cell_lo, hi = cd.cell_hi;
-        if constexpr (HALO) {
-            cls_range(cd, rg, lo, hi);
-            if (rg == 1) sg_halo_wait_block(hw);   // the strips read the neighbours' ghost rows
+    // ONE grid-stride sweep over idx in [0, cell_hi - cell_lo): the interior cells first (ascending or, rev, descending) and -
+    // partitioned mesh - the two boundary strips, the only cells that read ghost rows, at the END of the index space: a
+    // block waits for the neighbours' puts only in the iteration that reaches the strips, blocks that never reach them
+    // retire (so this rank's own put can always be scheduled), and the strips fill the last partial wave instead of adding
+    // a second tail.  Unpartitioned: split == cell range, no strips, no wait.
+    const int n_tot = (int)(cd.cell_hi - cd.cell_lo), n_int = (int)(cd.split_hi - cd.split_lo), n_lo = (int)(cd.split_lo - cd.cell_lo);
+    bool waited = hw.n == 0;
+    for (int base = (int)blockIdx.x * CB; base < n_tot; base += (int)gridDim.x * CB) {
+        if (!waited && base + CB > n_int) {
+            sg_halo_wait_inline(hw);
+            waited = true;
         }
-        int c, step;
-        sg_sweep_begin_i((int)lo, (int)hi, CB, cd.rev, c, step);
-        for (; c >= (int)lo && c < (int)hi; c += step) {
-            double xk[NLD], yk[NLD];
-            dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
-            store_row<NLD, WIDE>(y + (size_t)c * NLD, yk);
+        const int idx = base + (int)threadIdx.x;
+        if (idx >= n_tot) continue;
+        const int j = idx - n_int;
+        const int c = j < 0 ? (cd.rev ? (int)cd.split_hi - 1 - idx : (int)cd.split_lo + idx)
+                            : (j < n_lo ? (int)cd.cell_lo + j : (int)cd.split_hi + (j - n_lo));
+        double xk[NLD], yk[NLD];
+        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, x, xk, yk);
+        store_row<NLD, WIDE>(y + (size_t)c * NLD, yk);
 #pragma unroll
-            for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
-        }
+        for (int i = 0; i < NLD; ++i) dsum[0] += xk[i] * yk[i];
     }
     sg_grid_reduce<2>(dsum, red, dot_out);
 }
@@ -890,7 +890,7 @@ __device__ __forceinline__ void cheb_update(const ChebDev &ch, const int c, cons
     }
 }
 
-template <int NLD, int NNB, int P, bool WIDE, bool BND, bool FIRST, bool LAST, bool HALO>
+template <int NLD, int NNB, int P, bool WIDE, bool BND, bool FIRST, bool LAST>
 __global__ void __launch_bounds__(CB, 3) dg_cheb_step(const ClsDev cd, const __grid_constant__ ChebDev ch, const double *__restrict__ z,
                                                       SgRed red, double *dot_out, const int *skip, const SgHaloWait hw) {
     extern __shared__ __align__(16) double s_tab[];
@@ -898,20 +898,26 @@ __global__ void __launch_bounds__(CB, 3) dg_cheb_step(const ClsDev cd, const __g
     load_class_tables(cd, s_tab, (cd.n_self + cd.n_nb) * cd.S);
     const double *s_nb = s_tab + cd.n_self * cd.S;
     double dsum[1] = {0.0};
-#pragma unroll 1
-    for (int rg = 0; rg < (HALO ? 3 : 1); ++rg) {
-        long lo = cd.cell_lo, hi = cd.cell_hi;
-        if constexpr (HALO) {
-            cls_range(cd, rg, lo, hi);
-            if (rg == 1) sg_halo_wait_block(hw);   // the strips read the neighbours' ghost rows of z
+    // ONE grid-stride sweep over idx in [0, cell_hi - cell_lo): the interior cells first (ascending or, rev, descending) and -
+    // partitioned mesh - the two boundary strips, the only cells that read ghost rows, at the END of the index space: a
+    // block waits for the neighbours' puts only in the iteration that reaches the strips, blocks that never reach them
+    // retire (so this rank's own put can always be scheduled), and the strips fill the last partial wave instead of adding
+    // a second tail.  Unpartitioned: split == cell range, no strips, no wait.
+    const int n_tot = (int)(cd.cell_hi - cd.cell_lo), n_int = (int)(cd.split_hi - cd.split_lo), n_lo = (int)(cd.split_lo - cd.cell_lo);
+    bool waited = hw.n == 0;
+    for (int base = (int)blockIdx.x * CB; base < n_tot; base += (int)gridDim.x * CB) {
+        if (!waited && base + CB > n_int) {
+            sg_halo_wait_inline(hw);
+            waited = true;
         }
-        int c, step;
-        sg_sweep_begin_i((int)lo, (int)hi, CB, cd.rev, c, step);
-        for (; c >= (int)lo && c < (int)hi; c += step) {
-            double zk[NLD], Jz[NLD];
-            dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
-            cheb_update<NLD, WIDE, FIRST, LAST>(ch, c, zk, Jz, dsum[0]);
-        }
+        const int idx = base + (int)threadIdx.x;
+        if (idx >= n_tot) continue;
+        const int j = idx - n_int;
+        const int c = j < 0 ? (cd.rev ? (int)cd.split_hi - 1 - idx : (int)cd.split_lo + idx)
+                            : (j < n_lo ? (int)cd.cell_lo + j : (int)cd.split_hi + (j - n_lo));
+        double zk[NLD], Jz[NLD];
+        dg_cell_apply<NLD, NNB, P, WIDE, BND>(cd, s_tab, s_nb, c, z, zk, Jz);
+        cheb_update<NLD, WIDE, FIRST, LAST>(ch, c, zk, Jz, dsum[0]);
     }
     if (LAST) sg_grid_reduce<1>(dsum, red, dot_out);
 }
@@ -1061,6 +1067,14 @@ struct sg_thermal_op {
 
 namespace {
 
+inline bool inkernel_wait() {
+    static const bool on = [] {
+        const char *e = getenv("SG_NO_INKERNEL_WAIT");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 inline unsigned capped_grid(long n, int tb) {
     long g = (n + tb - 1) / tb;
     if (g < 1) g = 1;
@@ -1111,14 +1125,14 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         (void)rc_wait;
         ProfScope ps(op, mode, st);
         const bool wide = (((uintptr_t)x | (uintptr_t)y) & 31) == 0;
-        const SgHaloWait none{}, hw = op->wait ? *op->wait : none;
+        SgHaloWait none{}, hw = op->wait ? *op->wait : none;
+        if (hw.n && !inkernel_wait()) {     // measurement switch: one-warp wait kernel + the plain kernel
+            if ((rc_wait = sg_peer_wait(nullptr, hw, st))) return rc_wait;
+            hw = none;
+        }
         if constexpr (DG) {
-            auto k0 = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true, false> : dg_class_apply<NLD, D + 1, P, false, true, false>)
-                               : (wide ? dg_class_apply<NLD, D + 1, P, true, false, false> : dg_class_apply<NLD, D + 1, P, false, false, false>);
-            auto k1 = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true, true> : dg_class_apply<NLD, D + 1, P, false, true, true>)
-                               : (wide ? dg_class_apply<NLD, D + 1, P, true, false, true> : dg_class_apply<NLD, D + 1, P, false, false, true>);
-            auto k = hw.n ? k1 : k0;     // the variant with the in-kernel halo wait only on a partitioned mesh
-            if (hw.n) SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
+            auto k = op->bmat ? (wide ? dg_class_apply<NLD, D + 1, P, true, true> : dg_class_apply<NLD, D + 1, P, false, true>)
+                              : (wide ? dg_class_apply<NLD, D + 1, P, true, false> : dg_class_apply<NLD, D + 1, P, false, false>);
             ClsDev cdv = op->cls;
             cdv.rev = dot2 ? sg_next_sweep_dir() : 0;     // solver launches alternate the sweep direction
             k<<<op->cls_grid, CB, op->cls_smem, st>>>(cdv, x, y, red, dst, skip, hw);
@@ -1227,27 +1241,23 @@ int cheb_step_t(const sg_thermal_op *op, const SgChebStep &cs, SgRed red, double
         const uintptr_t al = (uintptr_t)cs.z_in | (uintptr_t)cs.r | (uintptr_t)cs.z_prev | (uintptr_t)cs.z_out;
         const bool wide = (al & 31) == 0, bnd = op->bmat != nullptr, first = cs.z_prev == nullptr, last = cs.last != 0;
         using K = void (*)(const ClsDev, const ChebDev, const double *, SgRed, double *, const int *, const SgHaloWait);
-        // [wide][bnd][first][last], without / with the in-kernel halo wait
+        // [wide][bnd][first][last]
         static const K table[2][2][2][2] = {
-            {{{dg_cheb_step<NLD, NNB, P, false, false, false, false, false>, dg_cheb_step<NLD, NNB, P, false, false, false, true, false>},
-              {dg_cheb_step<NLD, NNB, P, false, false, true, false, false>, dg_cheb_step<NLD, NNB, P, false, false, true, true, false>}},
-             {{dg_cheb_step<NLD, NNB, P, false, true, false, false, false>, dg_cheb_step<NLD, NNB, P, false, true, false, true, false>},
-              {dg_cheb_step<NLD, NNB, P, false, true, true, false, false>, dg_cheb_step<NLD, NNB, P, false, true, true, true, false>}}},
-            {{{dg_cheb_step<NLD, NNB, P, true, false, false, false, false>, dg_cheb_step<NLD, NNB, P, true, false, false, true, false>},
-              {dg_cheb_step<NLD, NNB, P, true, false, true, false, false>, dg_cheb_step<NLD, NNB, P, true, false, true, true, false>}},
-             {{dg_cheb_step<NLD, NNB, P, true, true, false, false, false>, dg_cheb_step<NLD, NNB, P, true, true, false, true, false>},
-              {dg_cheb_step<NLD, NNB, P, true, true, true, false, false>, dg_cheb_step<NLD, NNB, P, true, true, true, true, false>}}}};
-        static const K table_halo[2][2][2][2] = {
-            {{{dg_cheb_step<NLD, NNB, P, false, false, false, false, true>, dg_cheb_step<NLD, NNB, P, false, false, false, true, true>},
-              {dg_cheb_step<NLD, NNB, P, false, false, true, false, true>, dg_cheb_step<NLD, NNB, P, false, false, true, true, true>}},
-             {{dg_cheb_step<NLD, NNB, P, false, true, false, false, true>, dg_cheb_step<NLD, NNB, P, false, true, false, true, true>},
-              {dg_cheb_step<NLD, NNB, P, false, true, true, false, true>, dg_cheb_step<NLD, NNB, P, false, true, true, true, true>}}},
-            {{{dg_cheb_step<NLD, NNB, P, true, false, false, false, true>, dg_cheb_step<NLD, NNB, P, true, false, false, true, true>},
-              {dg_cheb_step<NLD, NNB, P, true, false, true, false, true>, dg_cheb_step<NLD, NNB, P, true, false, true, true, true>}},
-             {{dg_cheb_step<NLD, NNB, P, true, true, false, false, true>, dg_cheb_step<NLD, NNB, P, true, true, false, true, true>},
-              {dg_cheb_step<NLD, NNB, P, true, true, true, false, true>, dg_cheb_step<NLD, NNB, P, true, true, true, true, true>}}}};
-        const SgHaloWait none{}, hw = cs.wait ? *cs.wait : none;
-        const K k = hw.n ? table_halo[wide][bnd][first][last] : table[wide][bnd][first][last];
+            {{{dg_cheb_step<NLD, NNB, P, false, false, false, false>, dg_cheb_step<NLD, NNB, P, false, false, false, true>},
+              {dg_cheb_step<NLD, NNB, P, false, false, true, false>, dg_cheb_step<NLD, NNB, P, false, false, true, true>}},
+             {{dg_cheb_step<NLD, NNB, P, false, true, false, false>, dg_cheb_step<NLD, NNB, P, false, true, false, true>},
+              {dg_cheb_step<NLD, NNB, P, false, true, true, false>, dg_cheb_step<NLD, NNB, P, false, true, true, true>}}},
+            {{{dg_cheb_step<NLD, NNB, P, true, false, false, false>, dg_cheb_step<NLD, NNB, P, true, false, false, true>},
+              {dg_cheb_step<NLD, NNB, P, true, false, true, false>, dg_cheb_step<NLD, NNB, P, true, false, true, true>}},
+             {{dg_cheb_step<NLD, NNB, P, true, true, false, false>, dg_cheb_step<NLD, NNB, P, true, true, false, true>},
+              {dg_cheb_step<NLD, NNB, P, true, true, true, false>, dg_cheb_step<NLD, NNB, P, true, true, true, true>}}}};
+        SgHaloWait none{}, hw = cs.wait ? *cs.wait : none;
+        if (hw.n && !inkernel_wait()) {
+            const int rcw = sg_peer_wait(nullptr, hw, st);
+            if (rcw) return rcw;
+            hw = none;
+        }
+        const K k = table[wide][bnd][first][last];
         SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
         {
             ProfScope ps(op, MODE_APPLY, st, 1);
@@ -1398,11 +1408,11 @@ int build_classes_t(sg_thermal_op *op) {
     int per_sm = 0;
     if (DG) {
         constexpr int NB = D + 1;
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, NB, P, true, true, false>, CB, smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaFuncSetAttribute(dg_class_apply<NLD, NB, P, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dg_class_apply<NLD, NB, P, true, true>, CB, smem));
     } else {
         SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_apply<D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_class_apply<D, P>, CB, smem));

@@ -163,7 +163,7 @@ class ThermalOperator:
         handle = C.create_string_buffer(64)
         rc = 0
         if self.halo is not None and os.environ.get("SG_NO_PEER", "0") != "1":
-            rc = L.sg_halo_peer_alloc(self.halo, handle, workspace_doubles)
+            rc = L.sg_halo_peer_alloc(self.halo, handle, 0 if os.environ.get("SG_NO_PEER_WS", "0") == "1" else workspace_doubles)
         below = next((ro for peer, so, sc, ro, rcn in segs if peer < self.ctx.rank), 0)
         above = next((ro for peer, so, sc, ro, rcn in segs if peer > self.ctx.rank), 0)
         mine = (handle.raw, (int(self.n_dofs), int(below), int(above))) if rc == 1 else None
