@@ -415,25 +415,7 @@ inline unsigned vgrid(long n) {
 
 }  // namespace
 
-// Tolerance policy of one PCG solve: the |r|^2 target as a function of |b|^2, which is only known after
-// the first reduction.  Returning >= |b|^2 means "nothing to do": zero iterations, x = 0.
-struct PcgTol {
-    double rtol, atol;   // plain solve: |r| <= max(rtol |b|, atol).  Inexact Newton: the FINAL target of the time step
-    bool forcing;        // inexact Newton (Eisenstat-Walker choice 2)
-    double eta1, gamma;  // eta_k = min(eta1, gamma (|F_k| / |F_{k-1}|)^2)
-    double F_prev;       // |F_{k-1}| (0 for the first Newton iteration)
-    double target;       // final absolute target fixed by the first iteration (0 while unknown)
-    double tol2(double rr0) const {
-        if (!forcing) return fmax(rtol * rtol * rr0, atol * atol);
-        const double nb = sqrt(rr0);
-        const double tgt = target > 0.0 ? target : fmax(atol, rtol * nb);
-        if (target > 0.0 && nb <= tgt) return rr0;   // the nonlinear residual already meets the target: dx = 0
-        double eta = eta1;
-        if (F_prev > 0.0) eta = fmin(eta1, gamma * (nb / F_prev) * (nb / F_prev));
-        const double tol = fmax(eta * nb, 0.5 * tgt);
-        return tol * tol;
-    }
-};
+using PcgTol = SgPcgPolicy;
 
 struct sg_halo_plan {
     sg_ctx *ctx;
@@ -1066,6 +1048,29 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
     const unsigned g = vgrid(n);
     double *S = s->S;
     int rc;
+    if (!s->blk_nld && s->ctx->nranks == 1 && !sg_thermal_profiling(s->op)) {
+        // small CG problem in gather form: the whole solve is ONE persistent cooperative kernel (stencil.cu k_cg_persistent)
+        rc = sg_thermal_pcg_persistent(s->op, T_lin, b, s->dinv, x, s->r, tp, max_it, S + 1, &s->ctrl->done, &s->ctrl->iters, &s->ctrl->rr, st);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            if ((rc = read_scalars(s, 0, 8, st))) return rc;
+            const double rr0 = s->S_host[1], rr = s->ctrl_host->rr;
+            const int done = s->ctrl_host->done;
+            s->last_rhs_norm = sqrt(rr0 > 0.0 ? rr0 : 0.0);
+            if (iters) *iters = s->ctrl_host->iters;
+            if (rel_res) *rel_res = rr0 > 0.0 ? sqrt(rr / rr0) : 0.0;
+            if (done == 2 || !isfinite(rr) || !isfinite(rr0)) {
+                sg_set_error("sg_pcg_solve (persistent): residual became non-finite at iteration %d", s->ctrl_host->iters);
+                return SG_E_NOCONV;
+            }
+            if (!done) {
+                sg_set_error("sg_pcg_solve (persistent): no convergence in %d iterations (relative residual %.3e)", s->ctrl_host->iters,
+                             rr0 > 0 ? sqrt(rr / rr0) : 0.0);
+                return SG_E_NOCONV;
+            }
+            return SG_OK;
+        }
+    }
     if (s->blk_nld) {
         SG_BLK_DISPATCH(blk_init, s, b, x, st);
         if (rc) return rc;

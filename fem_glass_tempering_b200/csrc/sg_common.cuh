@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -99,6 +100,36 @@ bool sg_thermal_has_cheb(const sg_thermal_op *op);
 bool sg_thermal_profiling(const sg_thermal_op *op);   // event pairs around the kernels are being recorded
 int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
 
+// Tolerance policy of one PCG solve: the |r|^2 target as a function of |b|^2, which is only known after the first
+// reduction.  Returning >= |b|^2 means "nothing to do": zero iterations, x = 0.
+struct SgPcgPolicy {
+    double rtol, atol;   // plain solve: |r| <= max(rtol |b|, atol).  Inexact Newton: the FINAL target of the time step
+    bool forcing;        // inexact Newton (Eisenstat-Walker choice 2)
+    double eta1, gamma;  // eta_k = min(eta1, gamma (|F_k| / |F_{k-1}|)^2)
+    double F_prev;       // |F_{k-1}| (0 for the first Newton iteration)
+    double target;       // final absolute target fixed by the first iteration (0 while unknown)
+    __host__ __device__ double tol2(double rr0) const {
+        if (!forcing) return fmax(rtol * rtol * rr0, atol * atol);
+        const double nb = sqrt(rr0);
+        const double tgt = target > 0.0 ? target : fmax(atol, rtol * nb);
+        if (target > 0.0 && nb <= tgt) return rr0;   // the nonlinear residual already meets the target: dx = 0
+        double eta = eta1;
+        if (F_prev > 0.0) eta = fmin(eta1, gamma * (nb / F_prev) * (nb / F_prev));
+        const double tol = fmax(eta * nb, 0.5 * tgt);
+        return tol * tol;
+    }
+};
+
+// stencil.cu / thermal.cu: the whole Jacobi-PCG solve of a small CG problem in ONE persistent cooperative kernel (see
+// k_cg_persistent).  sg_thermal_pcg_persistent returns 1 when it ran (results in *rr0, ctrl fields, x), 0 when this
+// operator / size does not qualify (caller runs the multi-kernel iteration), < 0 on error.
+struct SgStencil;
+int sg_stencil_pcg(SgStencil *s, int sm_count, const double *b, const double *dinv, double *x, double *work, const SgPcgPolicy &pol, int max_it,
+                   double *rr0_out, int *ctrl_done, int *ctrl_iters, double *ctrl_rr, cudaStream_t st);
+int sg_thermal_pcg_persistent(sg_thermal_op *op, const double *T_lin, const double *b, const double *dinv, double *x, double *work,
+                              const SgPcgPolicy &pol, int max_it, double *rr0_out, int *ctrl_done, int *ctrl_iters, double *ctrl_rr,
+                              cudaStream_t st);
+
 // peer.cu: NVLink peer-memory halo exchange and small all-reduce (replaces NCCL on the solver's data path)
 struct SgPeer;
 int sg_peer_create(sg_ctx *ctx, size_t mailbox_doubles, size_t workspace_doubles, SgPeer **out, void *handle64);
@@ -124,6 +155,8 @@ int sg_peer_allreduce(SgPeer *p, double *vals, int count, cudaStream_t st);
 // rep_out[k] = index of one member of class k; both are cudaMalloc'ed here and freed by the caller.
 int sg_classify_u64(const uint64_t *keys_dev, int64_t n, int32_t **cls_out, int32_t *n_cls, int32_t **rep_out);
 
+int sg_exclusive_scan_i32(int32_t *data_dev, int64_t n, int64_t *total);
+
 // stencil.cu: row-stencil classes of a CG operator (gather form of the Jacobian apply).  *out stays NULL (and SG_OK is
 // returned) when the mesh has no small set of repeating rows.  dot2[0] = x.y over the rows [own_lo, own_hi), dot2[1] = 0.
 struct SgStencil;
@@ -131,6 +164,10 @@ int sg_stencil_build(sg_ctx *ctx, const int32_t *dofmap, int64_t n_cells, int n_
                      const uint16_t *cls16, const double *tab, int S, int64_t n_rows, SgStencil **out);
 int sg_stencil_apply(const SgStencil *s, const double *x, double *y, int64_t own_lo, int64_t own_hi, SgRed red, double *dot2,
                      const int *skip, cudaStream_t st, const SgHaloWait *wait = nullptr);
+int sg_stencil_attach_boundary(SgStencil *s, const int32_t *dofmap, int64_t n_cells, int64_t cell_lo, int64_t cell_hi, int64_t n_bf,
+                               const int32_t *bf_cell, const int32_t *bf_facet, int nfd, const int *facet_dofs, const double *bmat,
+                               int *attached);
+int sg_stencil_refresh_boundary(const SgStencil *s, cudaStream_t st);
 void sg_stencil_destroy(SgStencil *s);
 void sg_stencil_info(const SgStencil *s, int32_t *n_classes, int32_t *n_entries, int32_t *max_nnz);
 

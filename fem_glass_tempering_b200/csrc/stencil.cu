@@ -30,7 +30,7 @@ constexpr int STB = 256;          // threads per block of the apply
 constexpr int MAX_NLD = 10;       // P2 tetrahedron
 constexpr int MAX_CONTRIB = 128;  // (cell, local row) pairs of one representative row
 constexpr int MAX_NNZ = 192;      // entries of one class row
-constexpr int MAX_CLASSES = 8192;
+constexpr int MAX_CLASSES = 8192;   // < 2^15: bit 15 of the 16-bit row class flags rows on an exterior facet
 constexpr size_t MAX_SMEM_TABLE = 48 * 1024;
 
 struct __align__(16) Entry {
@@ -45,7 +45,49 @@ struct StDev {
     const int32_t *ptr;   // [n_classes + 1]
     const Entry *ent;     // [n_entries]
     int n_classes, n_entries;
+    // Exterior (Robin + radiation) facets in gather form, so that the apply is ONE launch with no atomics: rows that lie on
+    // an exterior facet carry bit 15 in rcls; brow_of[row] indexes their list of (facet b, local facet dof k) pairs, and
+    // the row adds  sum_l B_b[k][l] x[dof(b, l)]  from the facets' linearised matrices bmat (refreshed once per Newton
+    // iteration by sg_thermal_linearize).  bmat == NULL: no boundary part.
+    const int32_t *brow_of, *blist, *bcnt, *bf_cell, *bf_facet, *dofmap;
+    const int32_t *bcols, *bncol;   // per boundary row: its distinct columns [BND_MAXC] and their number
+    const double *bvals;            // per boundary row: the assembled entries, refreshed from bmat once per linearisation
+    long n_brows;                   // bcols / bvals are ENTRY-major: [BND_MAXC][n_brows]
+    const double *bmat;
+    long nc;
+    int nfd, maxf;
+    const int32_t *fd;    // [4][6] local dofs of the facets (thermal.cu facet_dof), device memory
 };
+
+constexpr int ROW_BND = 0x8000;
+constexpr int BND_MAXF = 16;      // exterior facets per row (Kuhn P2 plate corner: 6)
+constexpr int BND_MAXC = 32;      // distinct columns of a boundary row's exterior-facet part (P2 surface vertex: 19)
+
+// boundary part of row `row` (see StDev): the row's assembled exterior-facet entries; CG_LOADS: read x through L2
+// (persistent kernel: x changes during the launch)
+template <bool CG_LOADS = false>
+__device__ __forceinline__ double stencil_boundary_row(const StDev &sd, const long row, const double *x) {
+    const int j = sd.brow_of[row];
+    const int n = sd.bncol[j];
+    const long nb = sd.n_brows;
+    double acc = 0.0;
+    for (int i0 = 0; i0 < n; i0 += 8) {            // 8 loads in flight (L2 round trips in the persistent kernel); sum in entry order
+        const int m = n - i0 < 8 ? n - i0 : 8;
+        int32_t c[8];
+        double v[8], xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            c[u] = u < m ? sd.bcols[(long)(i0 + u) * nb + j] : 0;
+            v[u] = u < m ? sd.bvals[(long)(i0 + u) * nb + j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = u < m ? (CG_LOADS ? __ldcg(x + c[u]) : x[c[u]]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (u < m) acc = fma(v[u], xv[u], acc);
+    }
+    return acc;
+}
 
 __device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v) {
     h ^= v + 0x9E3779B97F4A7C15ull;
@@ -164,14 +206,14 @@ __global__ void __launch_bounds__(STB, MINB) k_stencil_apply(const StDev sd, con
     bool waited = hw.n == 0;
     for (long base = (long)blockIdx.x * STB; base < sd.n_rows; base += (long)gridDim.x * STB) {
         if (!waited && base + STB > n_safe) {     // block-uniform; blocks whose rows are all safe never wait and retire
-            sg_halo_wait_block(hw);
+            sg_halo_wait_inline(hw);
             waited = true;
         }
         const long idx = base + threadIdx.x;
         if (idx >= sd.n_rows) continue;
         const long j = idx - n_safe;
         const long row = idx < n_safe ? sd.safe_lo + idx : (j < sd.safe_lo ? j : sd.safe_hi + (j - sd.safe_lo));
-        const int c = sd.rcls[row];
+        const int cw = sd.rcls[row], c = cw & (ROW_BND - 1);
         const int p1 = ptr[c + 1];
         int k = ptr[c];
         const double *xr = x + row;
@@ -190,10 +232,329 @@ __global__ void __launch_bounds__(STB, MINB) k_stencil_apply(const StDev sd, con
             const Entry e = ent[k];
             acc = fma(e.coef, __ldg(xr + e.off), acc);
         }
+        if ((cw & ROW_BND) && sd.bmat) acc += stencil_boundary_row(sd, row, x);
         y[row] = acc;
         if (row >= sd.own_lo && row < sd.own_hi) dsum[0] += __ldg(xr) * acc;
     }
     sg_grid_reduce<2>(dsum, red, dot_out);
+}
+
+// ---- boundary rows: mark, number, collect
+__global__ void k_bnd_mark(long n_bf, const int32_t *__restrict__ bf_cell, const int32_t *__restrict__ bf_facet,
+                           const int32_t *__restrict__ dofmap, long nc, long cell_lo, long cell_hi, int nfd, const StDev sd, int32_t *flag) {
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bf) return;
+    const long cell = bf_cell[b];
+    if (cell < cell_lo || cell >= cell_hi) return;
+    const int f = bf_facet[b];
+    for (int k = 0; k < nfd; ++k) flag[dofmap[(long)sd.fd[f * 6 + k] * nc + cell]] = 1;
+}
+// pos = exclusive scan of flag: boundary rows are numbered in ROW ORDER, so that consecutive boundary rows (one warp of
+// the apply) read consecutive entries of the entry-major bcols/bvals arrays
+__global__ void k_bnd_number(long n, const int32_t *__restrict__ flag, const int32_t *__restrict__ pos, int32_t *brow_of) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) brow_of[i] = flag[i] ? pos[i] : -1;
+}
+__global__ void k_bnd_collect(long n_bf, const int32_t *__restrict__ bf_cell, const int32_t *__restrict__ bf_facet,
+                              const int32_t *__restrict__ dofmap, long nc, long cell_lo, long cell_hi, int nfd, const StDev sd,
+                              const int32_t *__restrict__ brow_of, int32_t *bcnt, int32_t *blist, unsigned *overflow) {
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bf) return;
+    const long cell = bf_cell[b];
+    if (cell < cell_lo || cell >= cell_hi) return;
+    const int f = bf_facet[b];
+    for (int k = 0; k < nfd; ++k) {
+        const int j = brow_of[dofmap[(long)sd.fd[f * 6 + k] * nc + cell]];
+        const int slot = atomicAdd(&bcnt[j], 1);
+        if (slot < BND_MAXF) blist[(long)j * BND_MAXF + slot] = (int)(b * 8 + k);
+        else atomicExch(overflow, 1u);
+    }
+}
+__global__ void k_bnd_sort_flag(long n_brows, int32_t *bcnt, int32_t *blist) {      // fixed summation order per row
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_brows) return;
+    const int n = bcnt[j] < BND_MAXF ? bcnt[j] : BND_MAXF;
+    int32_t *l = blist + j * BND_MAXF;
+    for (int i = 1; i < n; ++i) {
+        const int32_t v = l[i];
+        int q = i - 1;
+        for (; q >= 0 && l[q] > v; --q) l[q + 1] = l[q];
+        l[q + 1] = v;
+    }
+}
+// distinct columns of every boundary row, in order of first appearance over its (sorted) facet list
+__global__ void k_bnd_columns(long n_brows, const StDev sd, int32_t *bcols, int32_t *bncol, unsigned *overflow) {
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_brows) return;
+    const int n = sd.bcnt[j];
+    int32_t cols[BND_MAXC];
+    int nc = 0;
+    for (int e = 0; e < n; ++e) {
+        const int pk = sd.blist[j * BND_MAXF + e];
+        const int b = pk >> 3;
+        const long cell = sd.bf_cell[b];
+        const int f = sd.bf_facet[b];
+        for (int l = 0; l < sd.nfd; ++l) {
+            const int32_t col = sd.dofmap[(long)sd.fd[f * 6 + l] * sd.nc + cell];
+            int q = 0;
+            while (q < nc && cols[q] != col) ++q;
+            if (q == nc) {
+                if (nc == BND_MAXC) {
+                    atomicExch(overflow, 1u);
+                    continue;
+                }
+                cols[nc++] = col;
+            }
+        }
+    }
+    bncol[j] = nc;
+    for (int i = 0; i < nc; ++i) bcols[(long)i * n_brows + j] = cols[i];
+}
+// bvals[j][i] = sum over the row's (facet b, local dof k) pairs of B_b[k][l] with dof(b, l) == column i   (fixed order)
+__global__ void k_bnd_refresh(long n_brows, const StDev sd, double *bvals) {
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_brows) return;
+    const int n = sd.bcnt[j], nc = sd.bncol[j], nfd = sd.nfd;
+    int32_t cols[BND_MAXC];
+    double v[BND_MAXC];
+    for (int i = 0; i < nc; ++i) {
+        v[i] = 0.0;
+        cols[i] = sd.bcols[(long)i * n_brows + j];
+    }
+    for (int e = 0; e < n; ++e) {
+        const int pk = sd.blist[j * BND_MAXF + e];
+        const int b = pk >> 3, k = pk & 7;
+        const long cell = sd.bf_cell[b];
+        const int f = sd.bf_facet[b];
+        const double *B = sd.bmat + (long)b * (nfd * (nfd + 1) / 2);
+        for (int l = 0; l < nfd; ++l) {
+            const int lo = k < l ? k : l, hi = k < l ? l : k;
+            const double bkl = B[lo * nfd - lo * (lo - 1) / 2 + (hi - lo)];   // packed upper triangle, row-wise
+            const int32_t col = sd.dofmap[(long)sd.fd[f * 6 + l] * sd.nc + cell];
+            for (int i = 0; i < nc; ++i)
+                if (cols[i] == col) v[i] += bkl;
+        }
+    }
+    for (int i = 0; i < nc; ++i) bvals[(long)i * n_brows + j] = v[i];
+}
+__global__ void k_bnd_flag_rows(long n, const int32_t *__restrict__ brow_of, uint16_t *rcls) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && brow_of[i] >= 0) rcls[i] |= (uint16_t)ROW_BND;
+}
+
+// ================================================================ persistent PCG (small CG problems)
+// Config 2 (334 k rows) is latency bound: a Jacobi-PCG iteration is three ~4 us kernels and the time step needs ~240 of
+// them.  Here the WHOLE linear solve is one cooperative launch: every thread keeps its rows of x, r, p, s = Ap and 1/diag in
+// registers for the entire solve, the only vector that goes through memory (L2) is u = M^-1 r, which the neighbours' rows
+// gather, and an iteration costs two grid-wide barriers instead of three launches.  Single-reduction CG (Chronopoulos &
+// Gear 1989): with w = A u,  gamma = r.u,  delta = w.u  reduced TOGETHER,
+//     beta = gamma/gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old),
+//     p = u + beta p,  s = w + beta s,  x += alpha p,  r -= alpha s,  u = M^-1 r.
+// Reductions are deterministic (per-block partials summed in block order by every block).  The tolerance policy (plain
+// rtol/atol or the Eisenstat-Walker forcing term of the inexact Newton iteration) is evaluated on the device from |b|.
+constexpr int PTB = 512;   // threads per block of the persistent kernel: ONE block per SM (a grid barrier has <= 148 participants),
+                           // 128 registers per thread: the rows' state never spills
+
+// three block-wide sums with one shared-memory stage; result valid in every thread
+__device__ __forceinline__ void block_sum3(double (&v)[3], double (*scratch)[32], double (&tot)[3]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const double w = sg_warp_sum(v[q]);
+        if (lane == 0) scratch[q][warp] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double w = lane < nw ? scratch[q][lane] : 0.0;
+        tot[q] = sg_warp_sum(w);      // every warp adds the same nw values in the same order
+    }
+    __syncthreads();
+}
+
+struct PersistArgs {
+    StDev sd;
+    const double *b, *dinv;
+    double *x, *u;            // u: work vector [n_rows] in global memory
+    double *partials;         // [2][gridDim.x][4]
+    unsigned *bar;            // grid barrier counter, zero at launch
+    SgPcgPolicy pol;
+    int max_it;
+    long win;                 // > 0: rows are block-contiguous and u is gathered from a shared-memory window of the block's
+                              // rows +- win (= largest |column offset|); 0: rows are grid-strided and u is gathered from L2
+    int *ctrl_done, *ctrl_iters;
+    double *ctrl_rr, *rr0_out;
+    long long *dbg;           // SG_PERSIST_TIMING=1: clock cycles per phase of block 0 (measurement only)
+};
+
+// Grid-wide barrier of the persistent kernel (all blocks co-resident: cooperative launch).  Arrival is a RELEASE reduction
+// (the block's earlier stores are visible at GPU scope before the count is), the poll is a RELAXED load: an acquire load
+// makes the compiler invalidate the whole L1 (CCTL.IVALL) after every barrier, which turned every constant the rows read
+// (class ids, boundary entries, spilled registers) into an L2 round trip per iteration.  Everything another block wrote
+// is read with ld.cg (L2), and bar.sync orders the poll before the block's following loads.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen += gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        unsigned v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < gen);
+    }
+    __syncthreads();
+}
+
+// WIN: x is the block's shared-memory window (xw[j] = u[win_lo + j]); the boundary part still reads the global vector xg
+template <bool WIN>
+__device__ __forceinline__ double stencil_row(const StDev &sd, const Entry *ent, const int32_t *ptr, const long row, const int cw,
+                                              const double *x, const double *xg) {
+    const int c = cw & (ROW_BND - 1);
+    const int p1 = ptr[c + 1];
+    int k = ptr[c];
+    const double *xr = x + row;
+    double acc = 0.0;
+    // up to 16 loads in flight: the vector comes from L2 (it was written by other SMs since the last barrier, so L1 must be
+    // bypassed) and the iteration is bound by L2 round trips, not by bandwidth; the sum stays in entry order
+    for (; k < p1; k += 16) {
+        const int nloc = p1 - k < 16 ? p1 - k : 16;
+        double xv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) xv[u] = u < nloc ? (WIN ? xr[ent[k + u].off] : __ldcg(xr + ent[k + u].off)) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            if (u < nloc) acc = fma(ent[k + u].coef, xv[u], acc);
+    }
+    // the boundary columns share a cell with the row: inside the window as well (WIN: x - absolute index - is the window)
+    if ((cw & ROW_BND) && sd.bmat) acc += WIN ? stencil_boundary_row<false>(sd, row, x) : stencil_boundary_row<true>(sd, row, xg);
+    return acc;
+}
+
+template <int R, bool WIN>
+__global__ void __launch_bounds__(PTB, 1) k_cg_persistent(const __grid_constant__ PersistArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ double scratch[3][32];
+    const StDev &sd = a.sd;
+    Entry *s_ent = reinterpret_cast<Entry *>(s_raw);
+    int32_t *s_ptr = reinterpret_cast<int32_t *>(s_ent + sd.n_entries);
+    for (int i = threadIdx.x; i < sd.n_entries; i += PTB) s_ent[i] = sd.ent[i];
+    for (int i = threadIdx.x; i <= sd.n_classes; i += PTB) s_ptr[i] = sd.ptr[i];
+    __syncthreads();
+    const long n = sd.n_rows;
+    // WIN: block b owns the contiguous rows [b R PTB, (b+1) R PTB); otherwise rows are grid-strided (coalesced either way)
+    const long T = WIN ? (long)PTB : (long)gridDim.x * PTB;
+    const long t0 = WIN ? (long)blockIdx.x * R * PTB + threadIdx.x : (long)blockIdx.x * PTB + threadIdx.x;
+    // shared-memory window of u: the block's rows and a.win rows on either side (the stencil's reach)
+    double *s_win = reinterpret_cast<double *>(s_raw + ((sizeof(Entry) * (size_t)sd.n_entries + sizeof(int32_t) * (size_t)(sd.n_classes + 1) + 15) & ~(size_t)15));
+    const long blk_lo = (long)blockIdx.x * R * PTB, win_lo = blk_lo - a.win, win_n = (long)R * PTB + 2 * a.win;
+    unsigned gen = 0;
+    double x[R], r[R], p[R], s[R], di[R];
+    int cw[R];                                          // class word of each row: read once, not once per iteration
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const long row = t0 + k * T;
+        const bool in = row < n;
+        cw[k] = in ? (int)sd.rcls[row] : 0;
+        x[k] = 0.0;
+        p[k] = 0.0;
+        s[k] = 0.0;
+        r[k] = in ? a.b[row] : 0.0;
+        di[k] = in ? a.dinv[row] : 0.0;
+        if (in) a.u[row] = di[k] * r[k];
+    }
+    double gamma_old = 1.0, alpha = 1.0, tol2 = 0.0, rr = 0.0;
+    int it = 0, done = 0;
+    const bool timing = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tph[7] = {0, 0, 0, 0, 0, 0, 0}, tc = timing ? clock64() : 0;
+#define SG_PHASE(i)                                 \
+    if (timing) {                                   \
+        const long long tn = clock64();             \
+        tph[i] += tn - tc;                          \
+        tc = tn;                                    \
+    }
+    for (;; ++it) {
+        grid_barrier(a.bar, gen);                       // u complete everywhere
+        SG_PHASE(0)
+        if constexpr (WIN) {                            // one L2 round trip fills the window; the gathers then hit shared memory
+            for (long j = threadIdx.x; j < win_n; j += PTB) {
+                const long g = win_lo + j;
+                s_win[j] = (g >= 0 && g < n) ? __ldcg(a.u + g) : 0.0;
+            }
+            __syncthreads();
+        }
+        SG_PHASE(1)
+        double acc[3] = {0.0, 0.0, 0.0}, tot[3];
+        double w[R], u[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const long row = t0 + k * T;
+            w[k] = 0.0;
+            u[k] = 0.0;
+            if (row < n) {
+                u[k] = di[k] * r[k];
+                w[k] = WIN ? stencil_row<true>(sd, s_ent, s_ptr, row, cw[k], s_win - win_lo, a.u)
+                           : stencil_row<false>(sd, s_ent, s_ptr, row, cw[k], a.u, a.u);
+                acc[0] += r[k] * u[k];
+                acc[1] += w[k] * u[k];
+                acc[2] += r[k] * r[k];
+            }
+        }
+        SG_PHASE(2)
+        block_sum3(acc, scratch, tot);
+        double *part = a.partials + ((size_t)(it & 1) * gridDim.x + blockIdx.x) * 4;
+        if (threadIdx.x < 3) part[threadIdx.x] = tot[threadIdx.x == 0 ? 0 : (threadIdx.x == 1 ? 1 : 2)];
+        SG_PHASE(3)
+        grid_barrier(a.bar, gen);                       // partials complete everywhere
+        SG_PHASE(4)
+        {
+            const double *all = a.partials + (size_t)(it & 1) * gridDim.x * 4;
+            double v[3] = {0.0, 0.0, 0.0};
+            for (unsigned bq = threadIdx.x; bq < gridDim.x; bq += PTB) {   // gridDim.x <= 148 < PTB: one block's partials per thread
+                v[0] += __ldcg(all + (size_t)bq * 4);
+                v[1] += __ldcg(all + (size_t)bq * 4 + 1);
+                v[2] += __ldcg(all + (size_t)bq * 4 + 2);
+            }
+            block_sum3(v, scratch, tot);                // identical order in every block: identical totals
+        }
+        SG_PHASE(5)
+        const double gamma = tot[0], delta = tot[1];
+        rr = tot[2];
+        if (it == 0) {
+            tol2 = a.pol.tol2(rr);
+            if (blockIdx.x == 0 && threadIdx.x == 0) *a.rr0_out = rr;
+        }
+        if (!(rr > tol2) || !isfinite(rr)) {            // it == 0: x = 0 is the answer (or the right-hand side is not finite)
+            done = isfinite(rr) ? 1 : 2;
+            break;
+        }
+        if (it >= a.max_it) break;
+        const double beta = it == 0 ? 0.0 : gamma / gamma_old;
+        alpha = it == 0 ? gamma / delta : gamma / (delta - beta * gamma / alpha);
+        gamma_old = gamma;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const long row = t0 + k * T;
+            p[k] = u[k] + beta * p[k];
+            s[k] = w[k] + beta * s[k];
+            x[k] += alpha * p[k];
+            r[k] -= alpha * s[k];
+            if (row < n) a.u[row] = di[k] * r[k];
+        }
+        SG_PHASE(6)
+    }
+#undef SG_PHASE
+    if (timing)
+        for (int i = 0; i < 7; ++i) a.dbg[i] += tph[i];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const long row = t0 + k * T;
+        if (row < n) a.x[row] = x[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *a.ctrl_done = done;
+        *a.ctrl_iters = it;
+        *a.ctrl_rr = rr;
+    }
 }
 
 using StencilKernel = void (*)(const StDev, const double *, double *, SgRed, double *, const int *, const SgHaloWait);
@@ -237,6 +598,11 @@ struct SgStencil {
     int max_nnz;
     long max_off;   // largest |column offset| of any class row
     StencilKernel kernel;
+    int32_t *brow_of, *blist, *bcnt, *fd, *bcols, *bncol;   // exterior facets in gather form (sg_stencil_attach_boundary)
+    double *bvals;
+    long n_brows;
+    double *pcg_partials;                   // persistent PCG scratch (allocated at first use)
+    unsigned *pcg_bar;
 };
 
 void sg_stencil_destroy(SgStencil *s) {
@@ -244,6 +610,15 @@ void sg_stencil_destroy(SgStencil *s) {
     if (s->rcls) cudaFree(s->rcls);
     if (s->ptr) cudaFree(s->ptr);
     if (s->ent) cudaFree(s->ent);
+    if (s->brow_of) cudaFree(s->brow_of);
+    if (s->blist) cudaFree(s->blist);
+    if (s->bcnt) cudaFree(s->bcnt);
+    if (s->fd) cudaFree(s->fd);
+    if (s->bcols) cudaFree(s->bcols);
+    if (s->bncol) cudaFree(s->bncol);
+    if (s->bvals) cudaFree(s->bvals);
+    if (s->pcg_partials) cudaFree(s->pcg_partials);
+    if (s->pcg_bar) cudaFree(s->pcg_bar);
     delete s;
 }
 
@@ -349,6 +724,171 @@ int sg_stencil_apply(const SgStencil *s, const double *x, double *y, int64_t own
         if (own_hi < sd.n_rows) sd.safe_hi = std::max<long>(sd.safe_lo, own_hi - s->max_off);
     }
     s->kernel<<<s->grid, STB, s->smem, st>>>(sd, x, y, red, dot2, skip, hw);
+    SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
+    return SG_OK;
+}
+
+// Exterior facets in gather form (see StDev).  Returns SG_OK and leaves the stencil without a boundary part when a row lies on
+// more than BND_MAXF facets (the caller then keeps its separate exterior-facet kernel).
+int sg_stencil_attach_boundary(SgStencil *s, const int32_t *dofmap, int64_t n_cells, int64_t cell_lo, int64_t cell_hi, int64_t n_bf,
+                               const int32_t *bf_cell, const int32_t *bf_facet, int nfd, const int *facet_dofs /* [4][6] */,
+                               const double *bmat, int *attached) {
+    *attached = 0;
+    if (n_bf <= 0 || !bmat || nfd > 6) return SG_OK;
+    StDev sd = s->dev;
+    SG_CHECK_CUDA(cudaMalloc(&s->fd, sizeof(int32_t) * 24));
+    SG_CHECK_CUDA(cudaMemcpy(s->fd, facet_dofs, sizeof(int32_t) * 24, cudaMemcpyHostToDevice));
+    sd.fd = s->fd;
+    const long n = sd.n_rows;
+    DevBuf flag, cnt, ovf;
+    SG_CHECK_CUDA(cudaMalloc(&flag.p, sizeof(int32_t) * (size_t)n));
+    SG_CHECK_CUDA(cudaMemset(flag.p, 0, sizeof(int32_t) * (size_t)n));
+    SG_CHECK_CUDA(cudaMalloc(&cnt.p, sizeof(int32_t)));
+    SG_CHECK_CUDA(cudaMemset(cnt.p, 0, sizeof(int32_t)));
+    SG_CHECK_CUDA(cudaMalloc(&ovf.p, sizeof(unsigned)));
+    SG_CHECK_CUDA(cudaMemset(ovf.p, 0, sizeof(unsigned)));
+    const unsigned gb = (unsigned)((n_bf + 255) / 256), gr = (unsigned)((n + 255) / 256);
+    k_bnd_mark<<<gb, 256>>>(n_bf, bf_cell, bf_facet, dofmap, n_cells, cell_lo, cell_hi, nfd, sd, flag.as<int32_t>());
+    SG_CHECK_CUDA(cudaGetLastError());
+    SG_CHECK_CUDA(cudaMalloc(&s->brow_of, sizeof(int32_t) * (size_t)n));
+    DevBuf pos;
+    SG_CHECK_CUDA(cudaMalloc(&pos.p, sizeof(int32_t) * (size_t)n));
+    SG_CHECK_CUDA(cudaMemcpy(pos.p, flag.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice));
+    int64_t n_brows64 = 0;
+    {
+        const int rcs = sg_exclusive_scan_i32(pos.as<int32_t>(), n, &n_brows64);
+        if (rcs) return rcs;
+    }
+    const int32_t n_brows = (int32_t)n_brows64;
+    if (n_brows <= 0) return SG_OK;
+    k_bnd_number<<<gr, 256>>>(n, flag.as<int32_t>(), pos.as<int32_t>(), s->brow_of);
+    SG_CHECK_CUDA(cudaGetLastError());
+    SG_CHECK_CUDA(cudaMalloc(&s->bcnt, sizeof(int32_t) * (size_t)n_brows));
+    SG_CHECK_CUDA(cudaMemset(s->bcnt, 0, sizeof(int32_t) * (size_t)n_brows));
+    SG_CHECK_CUDA(cudaMalloc(&s->blist, sizeof(int32_t) * (size_t)n_brows * BND_MAXF));
+    k_bnd_collect<<<gb, 256>>>(n_bf, bf_cell, bf_facet, dofmap, n_cells, cell_lo, cell_hi, nfd, sd, s->brow_of, s->bcnt, s->blist,
+                               ovf.as<unsigned>());
+    SG_CHECK_CUDA(cudaGetLastError());
+    unsigned overflow = 0;
+    SG_CHECK_CUDA(cudaMemcpy(&overflow, ovf.p, sizeof(overflow), cudaMemcpyDeviceToHost));
+    if (overflow) return SG_OK;
+    k_bnd_sort_flag<<<(unsigned)((n_brows + 255) / 256), 256>>>(n_brows, s->bcnt, s->blist);
+    SG_CHECK_CUDA(cudaGetLastError());
+    SG_CHECK_CUDA(cudaMalloc(&s->bcols, sizeof(int32_t) * (size_t)n_brows * BND_MAXC));
+    SG_CHECK_CUDA(cudaMalloc(&s->bncol, sizeof(int32_t) * (size_t)n_brows));
+    SG_CHECK_CUDA(cudaMalloc(&s->bvals, sizeof(double) * (size_t)n_brows * BND_MAXC));
+    SG_CHECK_CUDA(cudaMemset(s->bvals, 0, sizeof(double) * (size_t)n_brows * BND_MAXC));
+    sd.blist = s->blist;
+    sd.bcnt = s->bcnt;
+    sd.bf_cell = bf_cell;
+    sd.bf_facet = bf_facet;
+    sd.dofmap = dofmap;
+    sd.nc = (long)n_cells;
+    sd.nfd = nfd;
+    k_bnd_columns<<<(unsigned)((n_brows + 255) / 256), 256>>>(n_brows, sd, s->bcols, s->bncol, ovf.as<unsigned>());
+    SG_CHECK_CUDA(cudaGetLastError());
+    SG_CHECK_CUDA(cudaMemcpy(&overflow, ovf.p, sizeof(overflow), cudaMemcpyDeviceToHost));
+    if (overflow) return SG_OK;
+    k_bnd_flag_rows<<<gr, 256>>>(n, s->brow_of, s->rcls);
+    SG_CHECK_CUDA(cudaGetLastError());
+    SG_CHECK_CUDA(cudaDeviceSynchronize());
+    s->n_brows = n_brows;
+    s->dev.bcols = s->bcols;
+    s->dev.bncol = s->bncol;
+    s->dev.bvals = s->bvals;
+    s->dev.n_brows = n_brows;
+    s->dev.fd = s->fd;
+    s->dev.brow_of = s->brow_of;
+    s->dev.blist = s->blist;
+    s->dev.bcnt = s->bcnt;
+    s->dev.bf_cell = bf_cell;
+    s->dev.bf_facet = bf_facet;
+    s->dev.dofmap = dofmap;
+    s->dev.bmat = bmat;
+    s->dev.nc = (long)n_cells;
+    s->dev.nfd = nfd;
+    s->dev.maxf = BND_MAXF;
+    *attached = 1;
+    return SG_OK;
+}
+
+template <int R>
+static int launch_persistent(SgStencil *s, int sm_count, PersistArgs &pa, cudaStream_t st) {
+    if ((long)sm_count * PTB * R < pa.sd.n_rows) return 0;            // more rows than R per thread with one block per SM
+    // window variant when the block's rows + the stencil's reach on both sides fit next to the class lists in shared memory
+    const size_t tab = (s->smem + 15) & ~(size_t)15;
+    const size_t win_bytes = sizeof(double) * ((size_t)R * PTB + 2 * (size_t)s->max_off);
+    const bool use_win = tab + win_bytes <= 160 * 1024;
+    auto k = use_win ? k_cg_persistent<R, true> : k_cg_persistent<R, false>;
+    const size_t smem = use_win ? tab + win_bytes : s->smem;
+    pa.win = use_win ? s->max_off : 0;
+    SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, PTB, smem));
+    if (per_sm < 1) return 0;
+    long grid = (pa.sd.n_rows + (long)R * PTB - 1) / ((long)R * PTB);
+    if (grid > sm_count) grid = sm_count;
+    if (!s->pcg_partials) SG_CHECK_CUDA(cudaMalloc(&s->pcg_partials, sizeof(double) * 2 * 4 * (size_t)sm_count));
+    if (!s->pcg_bar) SG_CHECK_CUDA(cudaMalloc(&s->pcg_bar, sizeof(unsigned)));
+    SG_CHECK_CUDA(cudaMemsetAsync(s->pcg_bar, 0, sizeof(unsigned), st));
+    pa.partials = s->pcg_partials;
+    pa.bar = s->pcg_bar;
+    static const bool timing = [] {
+        const char *e = getenv("SG_PERSIST_TIMING");
+        return e && e[0] == '1';
+    }();
+    static long long *dbg = nullptr;
+    if (timing && !dbg) {
+        cudaMallocManaged(&dbg, 8 * sizeof(long long));
+        memset(dbg, 0, 8 * sizeof(long long));
+    }
+    pa.dbg = timing ? dbg : nullptr;
+    if (timing) {
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "persistent PCG phases so far (cycles of block 0): barrierA %lld window %lld rows %lld blocksum %lld barrierB %lld totals %lld update %lld\n",
+                dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[5], dbg[6]);
+    }
+    void *args[] = {&pa};
+    SG_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)grid), dim3(PTB), args, smem, st));
+    sg_count_launch();
+    return 1;
+}
+
+int sg_stencil_pcg(SgStencil *s, int sm_count, const double *b, const double *dinv, double *x, double *work, const SgPcgPolicy &pol, int max_it,
+                   double *rr0_out, int *ctrl_done, int *ctrl_iters, double *ctrl_rr, cudaStream_t st) {
+    if (!s->smem) return 0;                               // class lists too large for shared memory: multi-kernel path
+    PersistArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.sd = s->dev;
+    pa.sd.own_lo = 0;
+    pa.sd.own_hi = pa.sd.n_rows;
+    pa.b = b;
+    pa.dinv = dinv;
+    pa.x = x;
+    pa.u = work;
+    pa.pol = pol;
+    pa.max_it = max_it;
+    pa.rr0_out = rr0_out;
+    pa.ctrl_done = ctrl_done;
+    pa.ctrl_iters = ctrl_iters;
+    pa.ctrl_rr = ctrl_rr;
+    // smallest rows-per-thread count that covers n with one 512-thread block per SM (B200: 75 776 threads)
+    const long n = pa.sd.n_rows, per = (long)sm_count * PTB;
+    if (n <= per * 1) return launch_persistent<1>(s, sm_count, pa, st);
+    if (n <= per * 2) return launch_persistent<2>(s, sm_count, pa, st);
+    if (n <= per * 3) return launch_persistent<3>(s, sm_count, pa, st);
+    if (n <= per * 4) return launch_persistent<4>(s, sm_count, pa, st);
+    if (n <= per * 5) return launch_persistent<5>(s, sm_count, pa, st);
+    if (n <= per * 6) return launch_persistent<6>(s, sm_count, pa, st);
+    if (n <= per * 8) return launch_persistent<8>(s, sm_count, pa, st);
+    return 0;
+}
+
+// after sg_thermal_linearize has refreshed bmat: re-assemble the boundary rows' entries
+int sg_stencil_refresh_boundary(const SgStencil *s, cudaStream_t st) {
+    if (!s->dev.bmat || s->n_brows <= 0) return SG_OK;
+    k_bnd_refresh<<<(unsigned)((s->n_brows + 127) / 128), 128, 0, st>>>(s->n_brows, s->dev, s->bvals);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;

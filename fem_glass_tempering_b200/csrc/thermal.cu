@@ -1053,6 +1053,7 @@ struct sg_thermal_op {
     int32_t *nbr_ext;      // DG P1: neighbour ids with exterior facets encoded (see ClsDev::bmat)
     double *bmat;
     SgStencil *stencil;    // CG: row-stencil classes (stencil.cu); nullptr: cell-centric cg_class_apply
+    int stencil_bnd;       // the stencil kernel also applies the exterior facets (gather form; no cg_bfacet_apply launch)
     double *diag_cells;    // CG: the cell part of diag J (M + dt alpha K does not depend on T), computed once at creation
     int (*linearize)(const sg_thermal_op *, const double *T_lin, cudaStream_t st);
     int (*cheb_step)(const sg_thermal_op *, const SgChebStep &, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
@@ -1139,7 +1140,7 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         } else if (op->stencil) {
             // gather form: plain stores of every row, no zeroing of y needed.  With exterior facets following in their own
             // launch, the cross-rank sum of both parts of x.Ax is done by THAT kernel (it covers dst[0] and dst[1]).
-            const bool bf_follows = op->bmat && dv.n_bf > 0;
+            const bool bf_follows = op->bmat && dv.n_bf > 0 && !op->stencil_bnd;
             const int rc = sg_stencil_apply(op->stencil, x, y, op->d.own_lo, op->d.own_hi, bf_follows ? sg_red_local(red) : red, dst, skip, st,
                                             &hw);
             if (rc) return rc;
@@ -1151,7 +1152,7 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
         if (DG || !op->stencil) sg_count_launch();
         }
         if constexpr (!DG) {
-            if (op->stencil && op->bmat && dv.n_bf > 0) {
+            if (op->stencil && op->bmat && dv.n_bf > 0 && !op->stencil_bnd) {
                 SgRed rb = red;
                 if (rb.peer) {
                     rb.ar_ptr = dst;
@@ -1221,6 +1222,7 @@ int linearize_t(const sg_thermal_op *op, const double *T_lin, cudaStream_t st) {
         k_bfacet_mats<D, P, DG><<<(unsigned)((op->dev.n_bf + TB - 1) / TB), TB, 0, st>>>(op->dev, T_lin, op->bmat);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
+        if (op->stencil && op->stencil_bnd) return sg_stencil_refresh_boundary(op->stencil, st);
     }
     return SG_OK;
 }
@@ -1340,6 +1342,25 @@ int build_stencil_t(sg_thermal_op *op) {
     if (!(dmax <= 1e-12 * ymax)) {   // never seen; keeps the cell-centric kernel rather than a wrong operator
         sg_stencil_destroy(st);
         return SG_OK;
+    }
+    // Exterior facets join the gather form where the solve is latency bound (small problems: one launch per apply, and the
+    // whole PCG solve in one persistent kernel).  On large meshes the facet-by-facet gather of the boundary rows (15 % of
+    // the rows of the 3-D P2 plate) costs the row kernel more than the separate 21 us cg_bfacet_apply launch it saves
+    // (measured on one GPU's share of config 4: 138 vs 77 + 21 us), so those keep the two-launch form.
+    static const long BND_IN_STENCIL_MAX_ROWS = getenv("SG_BND_IN_STENCIL_MAX_ROWS") ? atol(getenv("SG_BND_IN_STENCIL_MAX_ROWS")) : 1500000;
+    if (op->bmat && dv.n_bf > 0 && dv.n_dofs <= BND_IN_STENCIL_MAX_ROWS) {
+        constexpr int NFD = nfd_of(D, P);
+        int fdt[24] = {0};
+        for (int f = 0; f < D + 1; ++f)
+            for (int k = 0; k < NFD; ++k) fdt[f * 6 + k] = facet_dof(D, P, f, k);
+        int attached = 0;
+        rc = sg_stencil_attach_boundary(st, dv.dofmap, dv.n_cells, dv.cell_lo, dv.cell_hi, dv.n_bf, dv.bf_cell, dv.bf_facet, NFD, fdt,
+                                        op->bmat, &attached);
+        if (rc) {
+            sg_stencil_destroy(st);
+            return rc;
+        }
+        op->stencil_bnd = attached;
     }
     op->stencil = st;
     return SG_OK;
@@ -1559,6 +1580,22 @@ bool sg_thermal_has_cheb(const sg_thermal_op *op) {
 
 int sg_thermal_cheb_step(sg_thermal_op *op, const SgChebStep &cs, SgRed red, double *dot_out, const int *skip, cudaStream_t st) {
     return op->cheb_step(op, cs, red, dot_out, skip, st);
+}
+
+int sg_thermal_pcg_persistent(sg_thermal_op *op, const double *T_lin, const double *b, const double *dinv, double *x, double *work,
+                              const SgPcgPolicy &pol, int max_it, double *rr0_out, int *ctrl_done, int *ctrl_iters, double *ctrl_rr,
+                              cudaStream_t st) {
+    // CG space in gather form with the exterior facets inside the stencil kernel (or none), one rank
+    if (op->d.family != 0 || !op->stencil || op->ctx->nranks != 1) return 0;
+    if (op->dev.n_bf > 0 && !(op->bmat && op->stencil_bnd)) return 0;
+    static const bool off = [] {
+        const char *e = getenv("SG_NO_PERSISTENT");
+        return e && e[0] == '1';
+    }();
+    if (off) return 0;
+    const int rc = sg_thermal_linearize(op, T_lin, st);
+    if (rc) return rc;
+    return sg_stencil_pcg(op->stencil, op->ctx->sm_count, b, dinv, x, work, pol, max_it, rr0_out, ctrl_done, ctrl_iters, ctrl_rr, st);
 }
 
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,

@@ -21,7 +21,7 @@ def _np_ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
-STENCIL_MIN_ROWS = 1_000_000     # below this the CG apply is launch-latency bound either way (see use_stencil)
+STENCIL_MIN_ROWS = 0             # the gather form is the default wherever the library finds repeating rows (see use_stencil)
 
 
 class ThermalOperator:
@@ -80,12 +80,12 @@ class ThermalOperator:
         desc.n_dofs, desc.own_lo, desc.own_hi = space.n_nodes, part.get("own_lo", 0), part.get("own_hi", space.n_nodes)
         desc.own_cell_lo, desc.own_cell_hi = part.get("own_cell_lo", desc.cell_lo), part.get("own_cell_hi", desc.cell_hi)
         if use_stencil is None:
-            # CG: gather form of the apply where rows repeat (csrc/stencil.cu).  It needs a second small launch for the
-            # exterior facets, so meshes whose kernels are launch-latency bound anyway (config 2: 334 k rows, 4 us
-            # kernels) keep the one-launch scatter kernel; SG_STENCIL=1 / SG_NO_STENCIL=1 override.
+            # CG: gather form of the apply where rows repeat (csrc/stencil.cu): one launch, exterior facets included, no
+            # atomics; small problems (config 2) then run their whole PCG solve as one persistent kernel.
+            # SG_NO_STENCIL=1 keeps the cell-centric scatter kernel (tests compare the two forms).
             import os
             env = os.environ
-            use_stencil = (env.get("SG_NO_STENCIL", "0") != "1") and (env.get("SG_STENCIL", "0") == "1" or space.n_nodes >= STENCIL_MIN_ROWS)
+            use_stencil = (env.get("SG_NO_STENCIL", "0") != "1") and (env.get("SG_STENCIL", "1") != "0") and space.n_nodes >= STENCIL_MIN_ROWS
         # SG_THERMAL_NO_CLASSES, SG_THERMAL_NO_STENCIL
         desc.flags = (0 if use_classes else 1) | (0 if use_stencil else 8)
         for name in ("dofmap", "geom", "nbr", "nbinfo", "bf_cell", "bf_facet", "bf_area"):
