@@ -426,6 +426,23 @@ def e2e_measure(r: Runner, steps: int):
     h2d, d2h = host_in.numel() * 8, prob.host_mirror.bytes_per_capture
     r.one_step()                                                                         # warm the mirror's buffers
     src = prob.host_mirror.field(prob.last_mirror_slot, "T")
+    # what the host side can take: every rank copies 1 GiB device -> pinned host at the same time (no compute), so the
+    # e2e figure can be read against the raw concurrent D2H rate of this box
+    probe_dev = torch.empty(1 << 27, dtype=torch.float64, device=dev)
+    probe_host = torch.empty(1 << 27, dtype=torch.float64, pin_memory=True)
+    probe_host.copy_(probe_dev, non_blocking=True)
+    r.barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(2):
+        probe_host.copy_(probe_dev, non_blocking=True)
+    p1.record()
+    r.barrier()
+    tp = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+    if r.world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    raw_d2h = r.world * 2 * (1 << 30) / (float(tp.item()) * 1e-3) / 1e9
+    del probe_dev, probe_host
     r.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -440,7 +457,7 @@ def e2e_measure(r: Runner, steps: int):
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if r.world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item()), h2d, d2h
+    return float(t.item()), h2d, d2h, raw_d2h
 
 
 def parity_check(ctx, local: int, args, cheb_degree: int, eta, steps: int):
@@ -508,7 +525,7 @@ def run_gpu(args):
     m = r.timed(args.steps, args.warmup, clocks=True)
     value = m["qp_total"] * m["steps"] / (m["ms_total"] * 1e-3)
     e2e_steps = max(1, min(args.steps, 5))
-    ms_e2e, h2d, d2h = e2e_measure(r, e2e_steps)
+    ms_e2e, h2d, d2h, raw_d2h = e2e_measure(r, e2e_steps)
     e2e_value = m["qp_total"] * e2e_steps / (ms_e2e * 1e-3)
     op, prob, dim, cfg = r.op, r.prob, r.dim, r.cfg
     rf = r.rooflines(m) if rank == 0 else {}
@@ -543,6 +560,10 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "aggregate_d2h_GBs": world * d2h * e2e_steps / (ms_e2e * 1e-3) / 1e9,
+                    "raw_concurrent_d2h_GBs": raw_d2h,
+                    "host_limit_note": "raw_concurrent_d2h_GBs = all ranks copying 1 GiB device->pinned host at once with no "
+                                       "compute: the ceiling of this box's host side (PCIe root complexes / memory / IOMMU of "
+                                       "the VM) for the 2 GB of per-step output each GPU produces",
                     "what": "ThermoViscoProblem.solve_timestep with host_mirror: pinned-host T_prev in, T/phi/Tf/xi/sigma out to "
                             "pinned host buffers every step (device snapshot, D2H overlapped with the next step)"},
             "roofline": None,

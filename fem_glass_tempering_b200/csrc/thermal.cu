@@ -922,6 +922,13 @@ __global__ void __launch_bounds__(CB, 3) dg_cheb_step(const ClsDev cd, const __g
     if (LAST) sg_grid_reduce<1>(dsum, red, dot_out);
 }
 
+// Tried and rejected (measured, profiles/r2t_dmma_experiment_*.json): running the local products of class-uniform 32-cell
+// tiles on the FP64 tensor cores (mma.sync.m8n8k4.f64, X^T tile as the A operand straight from a coalesced 8-byte load,
+// the class matrix as a 16-lane B fragment: one LDS.64 per matrix per 32 cells instead of eight LDS.128 per cell).  Results
+// identical to 1e-14, but the fused Chebyshev step took 486 us instead of 163 us and the apply 286 instead of 133 us on
+// config 3: DMMA issue on sm_100a is far below the FP64 FMA pipe for these 8x8x4 products, so the shared-memory table
+// reads stay.  What the experiment left behind is the layer-grouped cell order of mesh.py (163 vs 171 us per step).
+
 // Exterior facets of a CG space from their linearised matrices: y += B_F x_F (RED.ADD), dsum += x_F . (B_F x_F) over the
 // facets of the cells [dot_lo, dot_hi).
 template <int D, int P>

@@ -274,6 +274,22 @@ def test_bench_path_combination_on_a_coercive_plate(sg_ctx):
     assert info["degree"] == 4 and info["hi"] > info["lo"] > 0.0
 
 
+@pytest.mark.parametrize("cheb", [4, 0])
+def test_layer_grouped_plate_tiles_against_the_oracle(sg_ctx, cheb):
+    """A plate whose columns hold a multiple of 32 cubes (8 x 4): mesh.py groups the bottom / interior / top layers so that
+    most 32-cell tiles share their whole local-matrix class; whole time steps against the oracle with the Chebyshev solver
+    (fused step kernel) and the plain one (apply kernel)."""
+    cfg = {"T": {"element": "DG", "degree": 1}, "sigma": {"element": "DG", "degree": 1}}
+    params = dict(MAIN_PARAMS, sip_penalty=6.0)
+    prob, orc = make_pair(sg_ctx, msh.plate_mesh(3, (5, 8, 4), (5.0, 8.0, 4.0)), cfg, params=params, materialize="minimal")
+    prob._thermal_op.set_chebyshev(cheb)
+    for step in range(5):
+        prob.solve_timestep(t=0.0)
+        orc.step()
+        compare_step(prob, orc)
+        orc.end_step()
+
+
 def test_corrected_physics_through_the_problem_api(sg_ctx):
     """model_params["physics"] = "corrected" (an extension, see ViscoelasticModel): the problem-level run equals the CPU
     statement of that scheme fed with the GPU's own temperature history; stresses carry memory and stay finite."""
