@@ -10,6 +10,13 @@ Same constructor arguments, attributes and method names as the reference.  What 
   * `previous`/`current` (and `current`/`next`) pairs that the reference keeps equal by copying
     (TVP:469,481,559-562,578-585) share one device buffer.
 There is no CPU fallback: constructing the problem without a CUDA device raises.
+
+One difference a caller of the SINGLE-PHASE methods must know: the reference's phases communicate through the stored
+Functions (each interpolate reads what the previous one wrote, TVP:456-591), whereas every phase of the fused kernel
+recomputes its inputs (xi, the strains, the Taylor factors) from T_cur / T_prev.  Editing functions["xi"] or a strain
+Function between two phase calls therefore has no effect here, and with materialize="minimal" those intermediates are
+not stored at all.  Code that needs the reference's data flow literally can replay it with
+Function.interpolate(material_model.expressions[key]) (models.PointwiseExpression reads the stored arrays).
 """
 from __future__ import annotations
 
