@@ -96,8 +96,9 @@ def _bind_thermal(L) -> None:
     """argtypes of the thermal/PCG/halo entry points (present once thermal.cu is built)."""
     if not hasattr(L, "sg_thermal_op_create"):
         return
-    from . import _lib_thermal
+    from . import _lib_mech, _lib_thermal
     _lib_thermal.bind(L)
+    _lib_mech.bind(L)
 
 
 def check(rc: int) -> None:

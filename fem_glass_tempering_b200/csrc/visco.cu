@@ -21,27 +21,12 @@
 //   * thin arrays (T, phi, xi, Tf, Tf_partial, sigma) are read/written with plain
 //     coalesced accesses: the flat index of the tile is the thread index.
 #include "sg_common.cuh"
+#include "visco_common.cuh"
 
 namespace {
 
 constexpr int VTILE = 32;      // nodes per CTA
 constexpr int VTHREADS = 256;  // threads per CTA
-
-struct VKParams {
-    int N;
-    double c_HRg;    // H / Rg            (VM:158)
-    double inv_Tb;   // 1 / Tb
-    double dt;
-    double half_dt;  // dt / 2            (VM:171)
-    double inv_d;    // 1 / dim           (VM:144)
-    double alpha_s;
-    double d_alpha;  // alpha_liquid - alpha_solid (VM:130)
-    double m[SG_MAX_TERMS], lm[SG_MAX_TERMS];
-    double g2[SG_MAX_TERMS], lg[SG_MAX_TERMS];  // g2 = 2.0 * g_n (VM:178)
-    double k[SG_MAX_TERMS], lk[SG_MAX_TERMS];
-    int mode;        // SG_VISCO_REFERENCE: the reference's expressions as executed; SG_VISCO_CORRECTED: see below
-    double chi;      // VM:15
-};
 
 struct VGather {
     int n_ld;
@@ -49,12 +34,6 @@ struct VGather {
     const uint8_t *local_point;
     const double *weights;
 };
-
-// VM:233-242   (1.0 + a) + 0.5*a^2,  a = (-xi)/lambda
-__device__ __forceinline__ double taylor3(double xi, double lambda) {
-    const double a = (-1.0 * xi) / lambda;
-    return (1.0 + a) + 0.5 * (a * a);
-}
 
 // VM:156-161 / VM:162-167
 __device__ __forceinline__ double shift_phi(const VKParams &P, double T) {
@@ -72,13 +51,6 @@ __device__ __forceinline__ double shift_phi(const VKParams &P, double T) {
 __device__ __forceinline__ double phi_eq25(const VKParams &P, double T, double Tf) {
     return exp(P.c_HRg * (P.inv_Tb - P.chi / T - (1.0 - P.chi) / Tf));
 }
-__device__ __forceinline__ void decay_fac(double xi, double lambda, double &decay, double &fac) {
-    const double x = xi / lambda;
-    const double em1 = expm1(-x);
-    decay = 1.0 + em1;
-    fac = (x != 0.0) ? (-em1) / x : 1.0;
-}
-
 __device__ __forceinline__ double gather_eval(const VGather &G, const double *__restrict__ arr, long node) {
     const double *w = G.weights + (int)G.local_point[node] * G.n_ld;
     const int32_t *dj = G.dofs + node * G.n_ld;
@@ -611,17 +583,6 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
 }
 
 }  // namespace
-
-typedef void (*visco_fast_fn)(const VKParams, const sg_visco_fields, const long);
-
-struct sg_visco_plan {
-    sg_ctx *ctx;
-    sg_visco_params p;
-    VKParams k;
-    visco_fast_fn fast;   // nullptr when (dim, n_terms) has no compiled fast path
-    uint32_t fast_smem;
-    int fast_grid;        // resident one-warp CTAs on the whole GPU
-};
 
 namespace {
 

@@ -107,6 +107,11 @@ class ThermoViscoProblem:
                                               functions_previous=self.functions_previous,
                                               functions_next=self.functions_next, dt=self.dt,
                                               to_sigma=self._to_sigma)                            # TVP:48-54
+        self.mechanics = None
+        if self._mech_opts:
+            from .mechanics import MechanicalEquilibrium
+            self.mechanics = MechanicalEquilibrium(self._ctx, self.mesh, self.functionSpaces["sigma"].scalar,
+                                                   self.material_model.plan, self._device, self._mech_opts)
         self._thermal_op = None
         self.output_dir = None
         self.host_mirror = None           # output.HostMirror: per-step pinned host copies of T/phi/Tf/xi/sigma
@@ -153,6 +158,12 @@ class ThermoViscoProblem:
             "sigma": FunctionSpace(self.mesh, sS, (d, d)),
             "sigma_partial": FunctionSpace(self.mesh, sS, (N, d, d)),
         }
+        self._mech_opts = self._params.get("mechanics", False)
+        if self._mech_opts:
+            # extension: vector-P1 displacement on the mesh vertices, see mechanics.py
+            sU = sT if (cT["element"], cT["degree"]) == ("CG", 1) else fe.ScalarSpace(self.mesh, "CG", 1)
+            self.finiteElements["u"] = FiniteElementInfo("CG", cell, 1, (d,))
+            self.functionSpaces["u"] = FunctionSpace(self.mesh, sU, (d,))
         self._gather = None
         if not same:
             import torch
@@ -210,6 +221,10 @@ class ThermoViscoProblem:
         self.functions_next["sigma_partial"] = F("sigma_partial", allocate=full,
                                                  alias=self.functions_current["sigma_partial"])
         self.functions_next["sigma"] = F("sigma", "Stress_tensor")                                # TVP:171
+        if self._mech_opts:
+            self.functions["displacement"] = F("u", "Displacement")
+            self.functions["displacement_increment"] = F("u", "Displacement_increment")
+            self.functions["mechanical_strain"] = F("sigma", "Mechanical_strain")
 
     def _scatter(self, array, block_size):
         if self._thermal_op is not None and self._same_space:
@@ -293,6 +308,8 @@ class ThermoViscoProblem:
             print(f"t={self.t}")
         self._solve_T()
         self._solve_viscoelastic()          # == _solve_Tf + _solve_strains + _solve_shifted_time + _solve_stress
+        if self.mechanics is not None:
+            self._solve_mechanics()
         self._write_output()
         self._update_values(current=self.functions_current["T"], previous=self.functions_previous["T"])  # TVP:378
 
@@ -332,6 +349,19 @@ class ThermoViscoProblem:
 
     def _solve_stress(self) -> None:
         self._run_phases(_lib.PHASE_STRESS)                                                       # TVP:438-452
+
+    def _solve_mechanics(self) -> None:
+        """Extension, not in the reference (VM:135-139 assumes total_strain = -thermal_strain): equilibrate the stress the
+        phases above left in functions_next["sigma"] (mechanics.py).  Must follow _solve_stress of the same step."""
+        t = self._visco_tensors()
+        fields = {k: t[k] for k in ("sigma", "total_strain", "deviatoric_strain", "ds_partial", "dsigma_partial",
+                                    "s_partial", "sigma_partial")}
+        fields["mech_strain"] = self.functions["mechanical_strain"]._array
+        if self.material_model.physics == "corrected":
+            fields["s_tilde"], fields["sigma_tilde"] = t["s_tilde"], t["sigma_tilde"]
+        xi_sigma = self._to_sigma(self.functions["xi"]._array)
+        self.mechanics.step(xi_sigma, fields, self.functions["displacement_increment"]._array,
+                            self.functions["displacement"]._array)
 
     def solve(self) -> None:
         import torch

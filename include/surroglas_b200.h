@@ -281,6 +281,61 @@ int sg_pcg_solve(sg_thermal_solver *s, const double *T_lin, const double *b, dou
 int sg_thermal_timestep(sg_thermal_solver *s, double *T, const double *T_prev, const sg_newton_opts *opts,
                         sg_newton_stats *stats, void *stream);
 
+/* ------------------------------------------ (C) mechanical equilibrium (extension)
+ *
+ * The reference has no equilibrium solve: VM:135-139 sets total_strain = -thermal_strain (a fully restrained body).
+ * Behind model_parameters["mechanics"] the framework solves, once per time step, for the displacement increment du in
+ * the vector-P1 space on the mesh vertices for which the stresses of the reference's own Prony chain (VM:176-228),
+ * evaluated with total_strain = eps(du) - thermal_strain, are in weak equilibrium.  The chain is linear in the strain:
+ *     sigma = sigma0 + 2 G_eff dev(eps(du)) + K_eff tr(eps(du)) I        at every sigma node,
+ * sigma0 = what sg_visco_update wrote (the reference's stress), G_eff/K_eff = the chain's own per-node factors summed over
+ * the Prony terms.  Matrix-free Jacobi-PCG on the GPU (csrc/mech.cu); eps(du) is constant per cell and a sigma node takes
+ * the strain of winner_cell[node] (the last cell touching it: the rule dolfinx's interpolate applies to cell-wise
+ * discontinuous expressions, TVP:456-591).  Single GPU. */
+typedef struct {
+    int32_t dim;
+    int64_t n_vertices, n_cells;
+    const double *coords;         /* device [n_vertices, dim]   mesh.geometry.x */
+    const int32_t *cells;         /* device [n_cells, dim+1]    vertex ids */
+    const uint8_t *fixed;         /* device [n_vertices*dim]    1 = this displacement component is held at zero */
+    int32_t n_ld_sigma;           /* nodes per cell of the sigma space */
+    int64_t n_sigma_nodes;
+    const int32_t *sigma_dofmap;  /* device [n_cells, n_ld_sigma] */
+    const double *sigma_weights;  /* HOST   [n_ld_sigma]: int phi_l / |K| of the sigma element */
+    const int32_t *winner_cell;   /* device [n_sigma_nodes] */
+} sg_mech_desc;
+
+/* what sg_mech_correct adds eps(du) to; sigma and mech_strain are required, the rest may be NULL */
+typedef struct {
+    double *sigma;                /* bs d*d, in/out: sigma0 on entry */
+    double *mech_strain;          /* bs d*d, out: eps(du) at the sigma nodes */
+    double *total_strain, *deviatoric_strain;                   /* bs d*d, in/out (VM:135-146) */
+    double *ds_partial, *dsigma_partial;                        /* bs N*d*d, in/out (VM:176-191) */
+    double *s_partial, *sigma_partial;                          /* bs N*d*d, in/out (VM:212-221) */
+    double *s_tilde, *sigma_tilde;  /* bs N*d*d, in/out; SG_VISCO_CORRECTED only (there the history IS the partial stress) */
+} sg_mech_fields;
+
+typedef struct sg_mech_op sg_mech_op;
+int sg_mech_op_create(sg_ctx *ctx, const sg_mech_desc *desc, sg_mech_op **out);
+int sg_mech_op_destroy(sg_mech_op *op);
+/* G_eff, K_eff [n_nodes] from xi at the sigma nodes, with the factors of VM:176-191 (or of the corrected scheme) */
+int sg_mech_coefficients(sg_visco_plan *plan, int64_t n_nodes, const double *xi_sigma, double *G_eff, double *K_eff,
+                         void *stream);
+/* cell means of the nodal moduli; must precede sg_mech_apply / sg_mech_solve whenever G_eff/K_eff changed */
+int sg_mech_set_moduli(sg_mech_op *op, const double *G_eff, const double *K_eff, void *stream);
+/* y = (P A P + I - P) x: the tangent stiffness with the held components replaced by the identity */
+int sg_mech_apply(sg_mech_op *op, const double *x, double *y, void *stream);
+/* b = -P B^T sigma0 (the out-of-balance force of the restrained stress state) */
+int sg_mech_rhs(sg_mech_op *op, const double *sigma0, double *b, void *stream);
+/* Jacobi-PCG for A du = b(sigma0) starting from the du passed in (e.g. the previous step's increment); blocks until
+ * |r| <= max(rtol |b|, atol) or max_it (-> SG_E_NOCONV) */
+int sg_mech_solve(sg_mech_op *op, const double *sigma0, double *du, double rtol, double atol, int32_t max_it,
+                  int32_t *iters, double *rel_res, void *stream);
+int sg_mech_correct(sg_mech_op *op, sg_visco_plan *plan, const double *du, const double *xi_sigma, const double *G_eff,
+                    const double *K_eff, const sg_mech_fields *f, void *stream);
+/* algorithmic bytes of one sg_mech_apply (cell ids, gradients, moduli, gathers and scatters counted once per cell) */
+int64_t sg_mech_apply_bytes(const sg_mech_op *op);
+
 #ifdef __cplusplus
 }
 #endif
