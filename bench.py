@@ -616,6 +616,64 @@ def run_gpu(args):
         sys.exit(1)
 
 
+def mechanics_config(ctx, local: int, n=(160, 160, 8), steps: int = 3) -> dict:  # noqa: C901
+    """The equilibrium extension (model_parameters["mechanics"]; the reference has no such solve,
+    VM:135-139) on a 160x160x8 DG1 plate: time per step with and without it, PCG iterations, the tangent apply against the
+    HBM roofline, and the size-independent check that the equilibrated DG stress is in discrete equilibrium."""
+    import numpy as np
+    import torch
+    from fem_glass_tempering_b200 import ThermoViscoProblem
+    from fem_glass_tempering_b200 import mesh as msh
+    dev = torch.device("cuda", local)
+    mesh = msh.plate_mesh(3, n, tuple(float(k) for k in n))
+    params = dict(MAIN_PARAMS, sip_penalty=6.0, mechanics={"rtol": 1e-8})
+    prob = ThermoViscoProblem(mesh_path="", time=(0.0, 50.0), dt=DT, config=DG1, model_parameters=params, mesh=mesh, ctx=ctx,
+                              materialize="minimal", verbose=False)
+    prob.setup(dirichlet_bc=False)
+    me = prob.mechanics
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ms_rest, ms_mech, its, resid = [], [], [], []
+    nv3 = mesh.n_vertices * 3
+    b = torch.empty(nv3, dtype=torch.float64, device=dev)
+    for _ in range(steps + 1):                                  # the first step (cold start of du) is not reported
+        prob.t += prob.dt
+        ev[0].record()
+        prob._solve_T()
+        prob._solve_viscoelastic()
+        ev[1].record()
+        prob._solve_mechanics()
+        ev[2].record()
+        prob._update_values(current=prob.functions_current["T"], previous=prob.functions_previous["T"])
+        torch.cuda.synchronize(dev)
+        ms_rest.append(ev[0].elapsed_time(ev[1]))
+        ms_mech.append(ev[1].elapsed_time(ev[2]))
+        its.append(me.last_iters)
+        sig = prob.functions_next["sigma"].x.array
+        me.rhs(sig, b)                                          # out-of-balance force of the equilibrated stress
+        resid.append(float(b.abs().max() / (sig.abs().max() * float(max(n)))))
+    x, y = torch.randn(nv3, dtype=torch.float64, device=dev), torch.empty(nv3, dtype=torch.float64, device=dev)
+    for _ in range(3):
+        me.apply(x, y)
+    ev[0].record()
+    for _ in range(20):
+        me.apply(x, y)
+    ev[1].record()
+    torch.cuda.synchronize(dev)
+    t_apply = ev[0].elapsed_time(ev[1]) / 20
+    peak, _src = measured_peak()
+    gbs = me.apply_bytes() / t_apply / 1e6
+    qp = mesh.n_cells * 4
+    ms = float(np.mean(ms_rest[1:]) + np.mean(ms_mech[1:]))
+    return {"workload": "plate3d_DG1 + mechanical equilibrium (extension; vector-P1 displacement, Jacobi-PCG to rtol 1e-8)",
+            "cells": list(n), "qp_total": qp, "displacement_dofs": nv3, "ms_per_step": ms, "value": qp / ms * 1e3, "unit": UNIT,
+            "ms_thermal_and_visco": float(np.mean(ms_rest[1:])), "ms_mechanics": float(np.mean(ms_mech[1:])),
+            "mech_pcg_its_per_step": float(np.mean(its[1:])), "steps": steps,
+            "equilibrium_residual_rel": max(resid), "equilibrium_ok": bool(max(resid) < 1e-6),
+            "dominant_kernel": {"kernel": "k_mech_apply<3> (tangent apply: gather 4x3 displacements, constant strain, RED.ADD.F64 scatter)",
+                                "avg_launch_ms": t_apply, "achieved_GBs": gbs, "frac": gbs / peak, "bound": "hbm",
+                                "algorithmic_bytes_per_launch": me.apply_bytes()}}
+
+
 def other_configs(ctx, local: int, args) -> dict:
     """The other BASELINE configs on one GPU, each a short timed run (3 warm-up + a few steps) — parity for these shapes is
     in tests/; here they are put next to the headline so that every named config has a driver-run number."""
@@ -638,6 +696,10 @@ def other_configs(ctx, local: int, args) -> dict:
     run("C3_with_reference_penalty_5.0", DEFAULT_WORKLOAD, 5)          # diverges after ~15 steps: 3 + 5 stay below
     REFERENCE_PENALTY = False
     run("perturbed_plate3d_DG1_general_mesh_kernels", "perturbed_plate3d_DG1", 3)
+    try:
+        out["mechanics_plate3d_DG1_160x160x8"] = mechanics_config(ctx, local)
+    except Exception as e:  # noqa: BLE001
+        out["mechanics_plate3d_DG1_160x160x8"] = {"error": repr(e)[:300]}
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_visco
