@@ -1,10 +1,6 @@
 mkdir -p gpurun_out
-B="python bench.py --steps 6 --warmup 3 --no-other-configs --no-cpu-baseline --no-parity"
-for m in ce ce2 sm:8 sm:16 sm:32 sm:64; do
-  SG_MIRROR_MODE=$m $B > gpurun_out/r2w_e2e_$m.json 2> gpurun_out/r2w_e2e_$m.err; echo "$m rc=$?"
-  python - <<PY
-import json
-d=json.loads(open('gpurun_out/r2w_e2e_$m.json').read().strip().splitlines()[-1])
-print('$m', 'ms/step', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), 'agg', round(d['e2e']['aggregate_d2h_GBs'],1), 'raw', round(d['e2e']['raw_concurrent_d2h_GBs'],1))
-PY
+CMD="python bench.py --workload C4_plate3d_CG2 --steps 1 --warmup 1 --no-other-configs --no-cpu-baseline --no-parity"
+for t in 1 0; do
+SG_STENCIL_TILED=$t ncu --set full --clock-control none --import-source on -k "regex:k_stencil_apply" -s 20 -c 2 -o gpurun_out/r2y_stencil_tiled$t -f $CMD > gpurun_out/r2y_ncu$t.log 2>&1; echo "ncu $t rc=$?"
 done
+ls -la gpurun_out/*.ncu-rep
