@@ -385,7 +385,9 @@ struct PersistArgs {
     int *ctrl_done, *ctrl_iters;
     double *ctrl_rr, *rr0_out;
     long long *dbg;           // SG_PERSIST_TIMING=1: clock cycles per phase of block 0 (measurement only)
+    int bcap;                 // boundary rows per block whose assembled entries are staged in shared memory for the solve
 };
+constexpr int PERSIST_BS = 10;    // ... with at most this many entries each (2-D P2 boundary vertex: 5); others read global memory
 
 // Grid-wide barrier of the persistent kernel (all blocks co-resident: cooperative launch).  Arrival is a RELEASE reduction
 // (the block's earlier stores are visible at GPU scope before the count is), the poll is a RELAXED load: an acquire load
@@ -430,7 +432,30 @@ __device__ __forceinline__ double stencil_row(const StDev &sd, const Entry *ent,
     return acc;
 }
 
-template <int R, bool WIN>
+// Boundary part of a row whose index j into the boundary-row arrays is already known (persistent kernel: looked up once
+// per solve), gathering from the block's shared-memory window: one level of (L1-resident) global loads per iteration
+// instead of the chain brow_of -> bncol -> bcols/bvals.
+__device__ __forceinline__ double stencil_boundary_row_window(const StDev &sd, const int j, const double *s_win, const int win_lo) {
+    const int n = sd.bncol[j];
+    const long nb = sd.n_brows;
+    double acc = 0.0;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        const int m = n - i0 < 8 ? n - i0 : 8;
+        int32_t c[8];
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            c[u] = u < m ? sd.bcols[(long)(i0 + u) * nb + j] : win_lo;
+            v[u] = u < m ? sd.bvals[(long)(i0 + u) * nb + j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (u < m) acc = fma(v[u], s_win[c[u] - win_lo], acc);
+    }
+    return acc;
+}
+
+template <int R, bool WIN, bool BST>
 __global__ void __launch_bounds__(PTB, 1) k_cg_persistent(const __grid_constant__ PersistArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ double scratch[3][32];
@@ -448,24 +473,58 @@ __global__ void __launch_bounds__(PTB, 1) k_cg_persistent(const __grid_constant_
     double *s_win = reinterpret_cast<double *>(s_raw + ((sizeof(Entry) * (size_t)sd.n_entries + sizeof(int32_t) * (size_t)(sd.n_classes + 1) + 15) & ~(size_t)15));
     const long blk_lo = (long)blockIdx.x * R * PTB, win_lo = blk_lo - a.win, win_n = (long)R * PTB + 2 * a.win;
     unsigned gen = 0;
-    double x[R], r[R], p[R], s[R], di[R];
+    // per-row state of the whole solve: r, p, s in registers; WIN: x, 1/diag and the boundary-row index in shared memory
+    // ([k][thread], conflict-free) — with all seven vectors in registers the kernel spilled (R = 5: 112 bytes per thread,
+    // reloaded from local memory every iteration)
+    double *s_x = s_win + (WIN ? win_n : 0);
+    double *s_di = s_x + (WIN ? (long)R * PTB : 0);
+    double *s_bv = s_di + (WIN ? (long)R * PTB : 0);                          // [PERSIST_BS][bcap] boundary entries: values
+    int32_t *s_bc = reinterpret_cast<int32_t *>(s_bv + (WIN ? (long)PERSIST_BS * a.bcap : 0));   // ... window-local columns
+    int32_t *s_bn = s_bc + (WIN ? (long)PERSIST_BS * a.bcap : 0);             // [bcap] entries per staged row
+    int32_t *s_bj = s_bn + (WIN ? a.bcap : 0);                                // [R][PTB]: >= 0 global boundary row, <= -2 staged slot, -1 none
+    __shared__ int s_bcount;
+    if (threadIdx.x == 0) s_bcount = 0;
+    __syncthreads();
+    double xr_[WIN ? 1 : R], dir_[WIN ? 1 : R];
+    double r[R], p[R], s[R];
     int cw[R];                                          // class word of each row: read once, not once per iteration
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         const long row = t0 + k * T;
         const bool in = row < n;
         cw[k] = in ? (int)sd.rcls[row] : 0;
-        x[k] = 0.0;
         p[k] = 0.0;
         s[k] = 0.0;
         r[k] = in ? a.b[row] : 0.0;
-        di[k] = in ? a.dinv[row] : 0.0;
-        if (in) a.u[row] = di[k] * r[k];
+        const double dk = in ? a.dinv[row] : 0.0;
+        if constexpr (WIN) {
+            s_x[k * PTB + threadIdx.x] = 0.0;
+            s_di[k * PTB + threadIdx.x] = dk;
+            int bj = (in && (cw[k] & ROW_BND) && sd.bmat) ? sd.brow_of[row] : -1;
+            if (BST && bj >= 0) {
+                // the row's assembled exterior-facet entries are constant during the solve: keep them on chip
+                const int nb = sd.bncol[bj];
+                const int slot = nb <= PERSIST_BS ? atomicAdd(&s_bcount, 1) : a.bcap;
+                if (slot < a.bcap) {
+                    for (int i = 0; i < nb; ++i) {
+                        s_bc[i * a.bcap + slot] = (int32_t)(sd.bcols[(long)i * sd.n_brows + bj] - win_lo);
+                        s_bv[i * a.bcap + slot] = sd.bvals[(long)i * sd.n_brows + bj];
+                    }
+                    s_bn[slot] = nb;
+                    bj = -2 - slot;
+                }
+            }
+            s_bj[k * PTB + threadIdx.x] = bj;
+        } else {
+            xr_[k] = 0.0;
+            dir_[k] = dk;
+        }
+        if (in) a.u[row] = dk * r[k];
     }
     double gamma_old = 1.0, alpha = 1.0, tol2 = 0.0, rr = 0.0;
     int it = 0, done = 0;
     const bool timing = a.dbg && blockIdx.x == 0 && threadIdx.x == 0;
-    long long tph[7] = {0, 0, 0, 0, 0, 0, 0}, tc = timing ? clock64() : 0;
+    long long tph[7] = {0, 0, 0, 0, 0, 0, 0}, tc = timing ? clock64() : 0, t_row_acc = 0;
 #define SG_PHASE(i)                                 \
     if (timing) {                                   \
         const long long tn = clock64();             \
@@ -484,22 +543,67 @@ __global__ void __launch_bounds__(PTB, 1) k_cg_persistent(const __grid_constant_
         }
         SG_PHASE(1)
         double acc[3] = {0.0, 0.0, 0.0}, tot[3];
-        double w[R], u[R];
+        double w[R];
+        const long long t_rows = a.dbg ? clock64() : 0;
+        if constexpr (WIN) {
+            // The R rows of a thread advance TOGETHER through their class lists: R independent FMA chains hide the
+            // LDS -> LDS -> DFMA latency that a row-after-row loop exposes with only four warps per scheduler (each row's sum
+            // still runs in entry order).  Rows past the end of the vector have an empty list.
+            int k0[R], len[R], loc[R];
+            int maxlen = 0;
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const long row = t0 + k * T;
-            w[k] = 0.0;
-            u[k] = 0.0;
-            if (row < n) {
-                u[k] = di[k] * r[k];
-                w[k] = WIN ? stencil_row<true>(sd, s_ent, s_ptr, row, cw[k], s_win - win_lo, a.u)
-                           : stencil_row<false>(sd, s_ent, s_ptr, row, cw[k], a.u, a.u);
-                acc[0] += r[k] * u[k];
-                acc[1] += w[k] * u[k];
-                acc[2] += r[k] * r[k];
+            for (int k = 0; k < R; ++k) {
+                const long row = t0 + k * T;
+                const int c = cw[k] & (ROW_BND - 1);
+                k0[k] = s_ptr[c];
+                len[k] = row < n ? s_ptr[c + 1] - k0[k] : 0;
+                loc[k] = (int)(row - win_lo);
+                maxlen = len[k] > maxlen ? len[k] : maxlen;
+                w[k] = 0.0;
+            }
+            for (int i = 0; i < maxlen; ++i) {
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    if (i < len[k]) {
+                        const Entry e = s_ent[k0[k] + i];
+                        w[k] = fma(e.coef, s_win[loc[k] + (int)e.off], w[k]);
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const long row = t0 + k * T;
+                if (row < n) {
+                    const double uk = s_di[k * PTB + threadIdx.x] * r[k];
+                    const int bj = (cw[k] & ROW_BND) ? s_bj[k * PTB + threadIdx.x] : -1;
+                    if (BST && bj <= -2) {
+                        const int slot = -2 - bj, nb = s_bn[slot];
+                        double bacc = 0.0;
+                        for (int i = 0; i < nb; ++i) bacc = fma(s_bv[i * a.bcap + slot], s_win[s_bc[i * a.bcap + slot]], bacc);
+                        w[k] += bacc;
+                    } else if (bj >= 0) {
+                        w[k] += stencil_boundary_row_window(sd, bj, s_win, (int)win_lo);
+                    }
+                    acc[0] += r[k] * uk;
+                    acc[1] += w[k] * uk;
+                    acc[2] += r[k] * r[k];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const long row = t0 + k * T;
+                w[k] = 0.0;
+                if (row < n) {
+                    const double uk = dir_[k] * r[k];
+                    w[k] = stencil_row<false>(sd, s_ent, s_ptr, row, cw[k], a.u, a.u);
+                    acc[0] += r[k] * uk;
+                    acc[1] += w[k] * uk;
+                    acc[2] += r[k] * r[k];
+                }
             }
         }
         SG_PHASE(2)
+        if (a.dbg) t_row_acc += clock64() - t_rows;
         block_sum3(acc, scratch, tot);
         double *part = a.partials + ((size_t)(it & 1) * gridDim.x + blockIdx.x) * 4;
         if (threadIdx.x < 3) part[threadIdx.x] = tot[threadIdx.x == 0 ? 0 : (threadIdx.x == 1 ? 1 : 2)];
@@ -534,21 +638,27 @@ __global__ void __launch_bounds__(PTB, 1) k_cg_persistent(const __grid_constant_
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const long row = t0 + k * T;
-            p[k] = u[k] + beta * p[k];
+            const double dk = WIN ? s_di[k * PTB + threadIdx.x] : dir_[k];
+            p[k] = dk * r[k] + beta * p[k];             // u = D^-1 r of this iteration (r is updated two lines below)
             s[k] = w[k] + beta * s[k];
-            x[k] += alpha * p[k];
+            if constexpr (WIN) s_x[k * PTB + threadIdx.x] += alpha * p[k];
+            else xr_[k] += alpha * p[k];
             r[k] -= alpha * s[k];
-            if (row < n) a.u[row] = di[k] * r[k];
+            if (row < n) a.u[row] = dk * r[k];
         }
         SG_PHASE(6)
     }
 #undef SG_PHASE
-    if (timing)
+    if (timing) {
         for (int i = 0; i < 7; ++i) a.dbg[i] += tph[i];
+        a.dbg[7] += it;
+    }
+    if (a.dbg && (threadIdx.x == 0 || threadIdx.x == PTB - 32))       // row phase of the first and last warp of every block
+        a.dbg[8 + 2 * blockIdx.x + (threadIdx.x ? 1 : 0)] += t_row_acc;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         const long row = t0 + k * T;
-        if (row < n) a.x[row] = x[k];
+        if (row < n) a.x[row] = WIN ? s_x[k * PTB + threadIdx.x] : xr_[k];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *a.ctrl_done = done;
@@ -818,9 +928,16 @@ static int launch_persistent(SgStencil *s, int sm_count, PersistArgs &pa, cudaSt
     if ((long)sm_count * PTB * R < pa.sd.n_rows) return 0;            // more rows than R per thread with one block per SM
     // window variant when the block's rows + the stencil's reach on both sides fit next to the class lists in shared memory
     const size_t tab = (s->smem + 15) & ~(size_t)15;
-    const size_t win_bytes = sizeof(double) * ((size_t)R * PTB + 2 * (size_t)s->max_off);
-    const bool use_win = tab + win_bytes <= 160 * 1024;
-    auto k = use_win ? k_cg_persistent<R, true> : k_cg_persistent<R, false>;
+    // window + the per-row state kept in shared memory (x, 1/diag, boundary-row index)
+    size_t win_bytes = sizeof(double) * ((size_t)R * PTB + 2 * (size_t)s->max_off) + (size_t)R * PTB * (8 + 8 + 4);
+    const bool use_win = tab + win_bytes <= 200 * 1024;
+    // what is left (up to 512 rows) holds the assembled boundary entries of the block's rows on exterior facets
+    const size_t per_brow = (size_t)PERSIST_BS * 12 + 4;
+    long bcap = use_win ? (long)((200 * 1024 - tab - win_bytes) / per_brow) : 0;
+    bcap = bcap > 512 ? 512 : (bcap & ~1L);
+    if (use_win) win_bytes += (size_t)bcap * per_brow;
+    pa.bcap = (int)bcap;
+    auto k = use_win ? (bcap > 0 ? k_cg_persistent<R, true, true> : k_cg_persistent<R, true, false>) : k_cg_persistent<R, false, false>;
     const size_t smem = use_win ? tab + win_bytes : s->smem;
     pa.win = use_win ? s->max_off : 0;
     SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -840,14 +957,23 @@ static int launch_persistent(SgStencil *s, int sm_count, PersistArgs &pa, cudaSt
     }();
     static long long *dbg = nullptr;
     if (timing && !dbg) {
-        cudaMallocManaged(&dbg, 8 * sizeof(long long));
-        memset(dbg, 0, 8 * sizeof(long long));
+        cudaMallocManaged(&dbg, (8 + 2 * 160) * sizeof(long long));
+        memset(dbg, 0, (8 + 2 * 160) * sizeof(long long));
     }
     pa.dbg = timing ? dbg : nullptr;
     if (timing) {
         cudaStreamSynchronize(st);
+        fprintf(stderr, "iterations so far %lld; ", dbg[7]);
         fprintf(stderr, "persistent PCG phases so far (cycles of block 0): barrierA %lld window %lld rows %lld blocksum %lld barrierB %lld totals %lld update %lld\n",
                 dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[5], dbg[6]);
+        long long lo = dbg[8], hi = dbg[8], sum = 0;
+        for (int i = 0; i < 2 * sm_count; ++i) {
+            lo = dbg[8 + i] < lo ? dbg[8 + i] : lo;
+            hi = dbg[8 + i] > hi ? dbg[8 + i] : hi;
+            sum += dbg[8 + i];
+        }
+        fprintf(stderr, "  row phase over blocks x {first, last warp}: min %lld mean %lld max %lld; block 0: %lld %lld, block 1: %lld %lld, block 74: %lld %lld\n",
+                lo, sum / (2 * sm_count), hi, dbg[8], dbg[9], dbg[10], dbg[11], dbg[8 + 148], dbg[8 + 149]);
     }
     void *args[] = {&pa};
     SG_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)grid), dim3(PTB), args, smem, st));

@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-CMD="python bench.py --workload C4_plate3d_CG2 --steps 1 --warmup 1 --no-other-configs --no-cpu-baseline --no-parity"
-for t in 1 0; do
-SG_STENCIL_TILED=$t ncu --set full --clock-control none --import-source on -k "regex:k_stencil_apply" -s 20 -c 2 -o gpurun_out/r2y_stencil_tiled$t -f $CMD > gpurun_out/r2y_ncu$t.log 2>&1; echo "ncu $t rc=$?"
+L=fem_glass_tempering_b200/lib/libsurroglas_b200.so
+for v in head new head new; do
+cp tools/_ab/lib_$v.so $L
+echo "== $v"
+python bench.py --workload C2_plate2d_CG2_1M_qp --steps 20 --warmup 5 --no-other-configs --no-cpu-baseline --no-parity 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C2 ms/step', round(d['ms_per_step'],3), 'its', d['config'].get('pcg_its_per_step'))"
 done
-ls -la gpurun_out/*.ncu-rep
