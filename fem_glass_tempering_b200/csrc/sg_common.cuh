@@ -238,6 +238,19 @@ __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, u
                  "r"(smem_u32(smem_src)), "r"(bytes)
                  : "memory");
 }
+// 2-D tensor-map TMA (SASS: UTMALDG / UTMASTG): box of the map at element coordinates (c0 = inner, c1 = row).
+// smem 128-B aligned; elements outside the tensor are zero-filled on load and skipped on store.
+__device__ __forceinline__ void tensor_g2s_2d(void *smem_dst, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tensor_s2g_2d(const void *tmap, int c0, int c1, const void *smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(smem_u32(smem_src))
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the shared-memory SOURCE of all committed bulk stores has been read
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -366,21 +366,23 @@ visco_kernel(const VKParams P, const sg_visco_fields f, const VGather G, const l
 constexpr int WT = 32;  // nodes per warp tile
 
 #ifndef SG_VISCO_CHUNK
-#define SG_VISCO_CHUNK 4
+#define SG_VISCO_CHUNK 6
 #endif
-// Terms per shared-memory chunk.  Up to 6 Prony terms the whole history row of a node is staged at once; beyond that
-// (the 12-term end of the sweep of BASELINE config 5) a row of 12 x 9 doubles would cost 60 KB of shared memory per warp
-// and leave 3 warps per SM, so the terms are staged SG_VISCO_CHUNK = 4 at a time (every lane bulk-copies its own row segment): the
-// shared-memory footprint — and with it the number of resident warps — stays below that of the 6-term kernel.
+// Terms per shared-memory chunk.  While a node's two history rows fit in 32 KB per warp tile (N d^2 <= 64 doubles) they are
+// staged whole (three 1-D bulk copies per tile); beyond that — 8, 10, 12 Prony terms in 3-D, BASELINE config 5 — a row of
+// 12 x 9 doubles would cost 60 KB of shared memory per warp and leave 3 warps per SM, so the terms are staged
+// SG_VISCO_CHUNK = 6 at a time as a [32 nodes][6 terms] BOX of a 2-D tensor map of the history array (one
+// cp.async.bulk.tensor per array and chunk, SASS UTMALDG/UTMASTG; a box that ends past the last term is zero-filled on
+// load and clipped on store).  Measured on B200, d = 3, fraction of the measured HBM peak for N = 8 / 10 / 12:
+//   whole rows 0.81 / 0.78 / 0.58;  per-lane 1-D copies of 4-term segments (round 1) 0.76 / 0.76 / 0.81;
+//   tensor boxes of 2 terms 0.71 / 0.65 / 0.66, of 4 terms 0.82 / 0.77 / 0.76, of 6 terms **0.90 / 0.87 / 0.85**:
+// every chunk is a serial load -> compute -> store round trip of the warp, so few large chunks win as long as seven warps
+// still fit on an SM (the 6-term footprint).
 __host__ __device__ constexpr int fast_chunk_terms(int D, int N) {
-    // measured on B200 (d = 3): 8 and 10 terms are as fast or faster unchunked (80 % / 77 % of the HBM peak against
-    // 71-76 %: the per-lane segment copies cost what the occupancy gains), 12 terms are faster chunked: 58 % unchunked,
-    // 74 % in chunks of 6, 81 % in chunks of 4
-    if (N < 12) return N;
     const int DD = D * D;
-    // segments must be multiples of 16 bytes and start 16-byte aligned: even number of doubles per segment
-    if ((DD % 2) == 0) return SG_VISCO_CHUNK;
-    return (N % 2 == 0 && SG_VISCO_CHUNK % 2 == 0) ? SG_VISCO_CHUNK : N;
+    if (N * DD <= 64) return N;
+    // a chunk of a row must be a multiple of 16 bytes (TMA box width): an even number of doubles
+    return ((SG_VISCO_CHUNK * DD) % 2 == 0 && SG_VISCO_CHUNK < N) ? SG_VISCO_CHUNK : N;
 }
 
 template <int D, int N>
@@ -398,7 +400,8 @@ struct FastCfg {
 };
 
 template <int D, int N, bool CORR = false>
-__global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const sg_visco_fields f, const long n_tiles) {
+__global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const sg_visco_fields f, const long n_tiles,
+                                                        const __grid_constant__ ViscoTmaps tm) {
     using C = FastCfg<D, N>;
     constexpr int DD = C::DD, ROW = C::ROW, G = C::G, CH = C::CH, CROW = C::CROW;
     constexpr bool CHUNKED = CH < N;
@@ -427,14 +430,13 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
                 sgptx::bulk_g2s(buf_k, f.sigma_tilde + node0 * ROW, C::S_BYTES, bar);
                 sgptx::bulk_g2s(buf_t, f.Tf_partial + node0 * N, C::TFP_BYTES, bar);
             }
-        } else {   // first chunk of terms: every lane copies the segment of its own row
+        } else {   // first chunk of terms: one [32 nodes][CH terms] box per history array
             if (lane == 0) {
                 sgptx::mbar_expect_tx(bar, 2u * C::S_BYTES + C::TFP_BYTES);
                 sgptx::bulk_g2s(buf_t, f.Tf_partial + node0 * N, C::TFP_BYTES, bar);
+                sgptx::tensor_g2s_2d(buf_s, &tm.s, 0, (int)node0, bar);
+                sgptx::tensor_g2s_2d(buf_k, &tm.k, 0, (int)node0, bar);
             }
-            __syncwarp();
-            sgptx::bulk_g2s(buf_s + lane * CROW, f.s_tilde + node * ROW, CROW * 8u, bar);
-            sgptx::bulk_g2s(buf_k + lane * CROW, f.sigma_tilde + node * ROW, CROW * 8u, bar);
         }
         const double Tc = f.T_cur[node], Tp = f.T_prev[node];
         double phi, xi, Tf_old = 0.0, phi_old = 0.0;
@@ -489,10 +491,11 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
             (void)dummy;
             const int len = (N - c0 < CH) ? N - c0 : CH;      // compile-time after unrolling
             if (CHUNKED && c0 > 0) {                          // stage the next chunk (the previous one has been written back)
-                if (lane == 0) sgptx::mbar_expect_tx(bar, 2u * (uint32_t)(WT * len * DD * 8));
-                __syncwarp();
-                sgptx::bulk_g2s(buf_s + lane * CROW, f.s_tilde + node * ROW + c0 * DD, (uint32_t)(len * DD * 8), bar);
-                sgptx::bulk_g2s(buf_k + lane * CROW, f.sigma_tilde + node * ROW + c0 * DD, (uint32_t)(len * DD * 8), bar);
+                if (lane == 0) {                              // a box that ends past the last term is zero-filled there; the
+                    sgptx::mbar_expect_tx(bar, 2u * C::S_BYTES);   // transaction still counts the whole box
+                    sgptx::tensor_g2s_2d(buf_s, &tm.s, c0 * DD, (int)node0, bar);
+                    sgptx::tensor_g2s_2d(buf_k, &tm.k, c0 * DD, (int)node0, bar);
+                }
                 sgptx::mbar_wait(bar, parity);
                 parity ^= 1u;
             }
@@ -555,10 +558,13 @@ __global__ void __launch_bounds__(32) visco_fast_kernel(const VKParams P, const 
             }
             if constexpr (CHUNKED) {                          // write this chunk back before its buffer is reused
                 sgptx::fence_async_smem();
-                sgptx::bulk_s2g(f.s_tilde + node * ROW + c0 * DD, buf_s + lane * CROW, (uint32_t)(len * DD * 8));
-                sgptx::bulk_s2g(f.sigma_tilde + node * ROW + c0 * DD, buf_k + lane * CROW, (uint32_t)(len * DD * 8));
-                sgptx::bulk_commit();
-                sgptx::bulk_wait_read0();
+                __syncwarp();
+                if (lane == 0) {                              // columns past the last term are not stored
+                    sgptx::tensor_s2g_2d(&tm.s, c0 * DD, (int)node0, buf_s);
+                    sgptx::tensor_s2g_2d(&tm.k, c0 * DD, (int)node0, buf_k);
+                    sgptx::bulk_commit();
+                    sgptx::bulk_wait_read0();
+                }
                 __syncwarp();
             }
         }
@@ -631,6 +637,7 @@ int setup_fast(sg_visco_plan *pl) {
     pl->fast = kern;
     pl->fast_smem = smem;
     pl->fast_grid = per_sm * pl->ctx->sm_count;
+    pl->fast_chunk = FastCfg<D, N>::CH;
     return SG_OK;
 }
 
@@ -644,6 +651,41 @@ int setup_fast_d(sg_visco_plan *pl) {
         case 10: return setup_fast<D, 10>(pl);
         case 12: return setup_fast<D, 12>(pl);
     }
+    return SG_OK;
+}
+
+// Tensor maps of s_tilde / sigma_tilde as [rows][N*d*d] float64 with a [32][chunk*d*d] box (see ViscoTmaps); cached in the
+// plan for the buffers of the last call (the problem passes the same arrays every step).
+int ensure_tmaps(sg_visco_plan *pl, const sg_visco_fields *f, int64_t rows) {
+    if (pl->tm_s == f->s_tilde && pl->tm_k == f->sigma_tilde && pl->tm_rows == rows) return SG_OK;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        SG_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "sg_visco_update: cuTensorMapEncodeTiled is not available in this driver");
+        encode = (encode_fn)fn;
+    }
+    const int dd = pl->p.dim * pl->p.dim;
+    const cuuint64_t row = (cuuint64_t)pl->k.N * dd;
+    const cuuint64_t gdim[2] = {row, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {row * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)(pl->fast_chunk * dd), (cuuint32_t)WT};
+    const cuuint32_t estr[2] = {1, 1};
+    double *bases[2] = {f->s_tilde, f->sigma_tilde};
+    CUtensorMap *maps[2] = {&pl->tmaps.s, &pl->tmaps.k};
+    for (int i = 0; i < 2; ++i) {
+        const CUresult r = encode(maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, bases[i], gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SG_REQUIRE(r == CUDA_SUCCESS, "sg_visco_update: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+    pl->tm_s = f->s_tilde;
+    pl->tm_k = f->sigma_tilde;
+    pl->tm_rows = rows;
     return SG_OK;
 }
 
@@ -699,6 +741,10 @@ int sg_visco_plan_create(sg_ctx *ctx, const sg_visco_params *p, sg_visco_plan **
     pl->fast = nullptr;
     pl->fast_smem = 0;
     pl->fast_grid = 0;
+    pl->fast_chunk = 0;
+    memset(&pl->tmaps, 0, sizeof(pl->tmaps));
+    pl->tm_s = pl->tm_k = nullptr;
+    pl->tm_rows = 0;
     int rc = SG_OK;
     if (p->dim == 1) rc = setup_fast_d<1>(pl);
     if (p->dim == 2) rc = setup_fast_d<2>(pl);
@@ -734,7 +780,11 @@ int sg_visco_update(sg_visco_plan *plan, int64_t n_nodes, const sg_visco_fields 
     if (plan->fast && phases == SG_PHASE_ALL && no_optional && (align_or % 16) == 0 && n_nodes >= WT) {
         const int64_t n_tiles = n_nodes / WT;
         const int grid = (int)(n_tiles < plan->fast_grid ? n_tiles : plan->fast_grid);
-        plan->fast<<<grid, 32, plan->fast_smem, st>>>(plan->k, *f, (long)n_tiles);
+        if (plan->fast_chunk < plan->k.N) {
+            rc = ensure_tmaps(plan, f, n_tiles * WT);
+            if (rc) return rc;
+        }
+        plan->fast<<<grid, 32, plan->fast_smem, st>>>(plan->k, *f, (long)n_tiles, plan->tmaps);
         SG_CHECK_CUDA(cudaGetLastError());
         sg_count_launch();
         done = n_tiles * WT;

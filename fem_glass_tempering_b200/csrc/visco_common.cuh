@@ -3,6 +3,8 @@
 // Translation units including this are compiled with -fmad=false.
 #pragma once
 
+#include <cuda.h>
+
 #include "sg_common.cuh"
 
 struct VKParams {
@@ -34,7 +36,12 @@ __device__ __forceinline__ void decay_fac(double xi, double lambda, double &deca
     fac = (x != 0.0) ? (-em1) / x : 1.0;
 }
 
-typedef void (*visco_fast_fn)(const VKParams, const sg_visco_fields, const long);
+// Tensor maps (2-D TMA) of the two history arrays viewed as [n_nodes rows][N*d*d doubles]: the chunked fast kernel
+// fetches a [32 nodes][chunk of terms] box with ONE cp.async.bulk.tensor per array (SASS UTMALDG / UTMASTG).
+struct ViscoTmaps {
+    CUtensorMap s, k;
+};
+typedef void (*visco_fast_fn)(const VKParams, const sg_visco_fields, const long, const ViscoTmaps);
 
 struct sg_visco_plan {
     sg_ctx *ctx;
@@ -43,5 +50,9 @@ struct sg_visco_plan {
     visco_fast_fn fast;   // nullptr when (dim, n_terms) has no compiled fast path
     uint32_t fast_smem;
     int fast_grid;        // resident one-warp CTAs on the whole GPU
+    int fast_chunk;       // terms per staged chunk (< n_terms: the kernel needs tensor maps of the history arrays)
+    ViscoTmaps tmaps;     // for the arrays below (rebuilt when the caller passes other buffers)
+    const void *tm_s, *tm_k;
+    int64_t tm_rows;
 };
 

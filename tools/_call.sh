@@ -1,9 +1,10 @@
 mkdir -p gpurun_out
-L=fem_glass_tempering_b200/lib/libsurroglas_b200.so
-for v in head new head new; do
-cp tools/_ab/lib_$v.so $L
-echo "== $v"
-python bench.py --workload C2_plate2d_CG2_1M_qp --steps 20 --warmup 5 --no-other-configs --no-cpu-baseline --no-parity 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C2 ms/step', round(d['ms_per_step'],3), 'its', d['config'].get('pcg_its_per_step'))"
-done
+python -m pytest tests/test_visco_gpu.py tests/test_problem_gpu.py -x -q > gpurun_out/r2z_pytest_visco.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2z_pytest_visco.log
+python tools/bench_visco.py --sweep > gpurun_out/r2z_visco_sweep.jsonl 2> gpurun_out/r2z_visco_sweep.err; echo "sweep rc=$?"
+python - <<PY
+import json
+for l in open('gpurun_out/r2z_visco_sweep.jsonl'):
+    try: d=json.loads(l)
+    except Exception: continue
+    print('d',d['dim'],'N',d['terms'],'corr' if d.get('corrected') else 'ref','ms',d['ms_median'],'frac',d['frac_of_peak'])
+PY
