@@ -86,6 +86,7 @@ class MechanicalEquilibrium:
         z = lambda n: torch.zeros(n, dtype=torch.float64, device=device)
         self.G_eff, self.K_eff = z(self.n_sigma), z(self.n_sigma)
         self.last_iters, self.last_rel_res = 0, 0.0
+        self._du_prev = None
 
     # -- single operations (tests, benchmarks) --------------------------------------------------------------
     def coefficients(self, xi_sigma):
@@ -133,6 +134,13 @@ class MechanicalEquilibrium:
         self.set_moduli()
         if not self.warm_start:
             du.zero_()
+        elif self._du_prev is not None:
+            # the increments change slowly from step to step: start from 2 du_n - du_{n-1}
+            guess = 2.0 * du - self._du_prev
+            self._du_prev.copy_(du)
+            du.copy_(guess)
+        else:
+            self._du_prev = du.clone()
         self.solve(tensors["sigma"], du)
         self.correct(du, xi_sigma, tensors)
         u.add_(du)
