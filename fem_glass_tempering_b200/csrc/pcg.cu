@@ -1048,9 +1048,13 @@ static int pcg_run(sg_thermal_solver *s, const double *T_lin, const double *b, d
     const unsigned g = vgrid(n);
     double *S = s->S;
     int rc;
-    if (!s->blk_nld && s->ctx->nranks == 1 && !sg_thermal_profiling(s->op)) {
-        // small CG problem in gather form: the whole solve is ONE persistent cooperative kernel (stencil.cu k_cg_persistent)
-        rc = sg_thermal_pcg_persistent(s->op, T_lin, b, s->dinv, x, s->r, tp, max_it, S + 1, &s->ctrl->done, &s->ctrl->iters, &s->ctrl->rr, st);
+    if (s->ctx->nranks == 1 && !sg_thermal_profiling(s->op)) {
+        // small CG problem in gather form: the whole solve is ONE persistent cooperative kernel (stencil.cu k_cg_persistent);
+        // tiny DG problem: ONE block (thermal.cu k_dg_pcg_small)
+        if (s->blk_nld)
+            rc = sg_thermal_pcg_small_dg(s->op, T_lin, b, x, tp, max_it, S + 1, &s->ctrl->done, &s->ctrl->iters, &s->ctrl->rr, st);
+        else
+            rc = sg_thermal_pcg_persistent(s->op, T_lin, b, s->dinv, x, s->r, tp, max_it, S + 1, &s->ctrl->done, &s->ctrl->iters, &s->ctrl->rr, st);
         if (rc < 0) return rc;
         if (rc == 1) {
             if ((rc = read_scalars(s, 0, 8, st))) return rc;

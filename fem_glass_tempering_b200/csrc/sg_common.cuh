@@ -126,6 +126,10 @@ struct SgPcgPolicy {
 struct SgStencil;
 int sg_stencil_pcg(SgStencil *s, int sm_count, const double *b, const double *dinv, double *x, double *work, const SgPcgPolicy &pol, int max_it,
                    double *rr0_out, int *ctrl_done, int *ctrl_iters, double *ctrl_rr, cudaStream_t st);
+// thermal.cu: the whole block-Jacobi PCG solve of a tiny DG problem (<= 256 cells, class tables) in ONE block; same
+// return convention as sg_thermal_pcg_persistent
+int sg_thermal_pcg_small_dg(sg_thermal_op *op, const double *T_lin, const double *b, double *x, const SgPcgPolicy &pol, int max_it,
+                            double *rr0_out, int *ctrl_done, int *ctrl_iters, double *ctrl_rr, cudaStream_t st);
 int sg_thermal_pcg_persistent(sg_thermal_op *op, const double *T_lin, const double *b, const double *dinv, double *x, double *work,
                               const SgPcgPolicy &pol, int max_it, double *rr0_out, int *ctrl_done, int *ctrl_iters, double *ctrl_rr,
                               cudaStream_t st);

@@ -1064,6 +1064,8 @@ struct sg_thermal_op {
     double *diag_cells;    // CG: the cell part of diag J (M + dt alpha K does not depend on T), computed once at creation
     int (*linearize)(const sg_thermal_op *, const double *T_lin, cudaStream_t st);
     int (*cheb_step)(const sg_thermal_op *, const SgChebStep &, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
+    int (*small_pcg)(sg_thermal_op *, const double *b, double *x, const SgPcgPolicy &pol, int max_it, double *rr0_out, int *ctrl_done,
+                     int *ctrl_iters, double *ctrl_rr, cudaStream_t st);
     // optional profiling of the Jacobian-apply cell kernel (bench.py roofline): event pairs on the launch stream
     int prof_on, prof_n, prof_cap;
     cudaEvent_t *prof_ev;
@@ -1280,6 +1282,163 @@ int cheb_step_t(const sg_thermal_op *op, const SgChebStep &cs, SgRed red, double
     } else {
         sg_set_error("Chebyshev step is only available for DG spaces");
         return SG_E_UNSUPPORTED;
+    }
+}
+
+// ---- tiny DG problems (config 1: the 48-cell line of main.py): the WHOLE block-Jacobi PCG solve in one block ----------------
+// With a few hundred cells every kernel of the multi-launch iteration is pure launch latency (354 launches per time step on
+// main.py's mesh even as CUDA-graph batches).  One thread per cell keeps x, r, p of its cell in registers; p travels
+// through shared memory so that dg_cell_apply (the class-table apply, unchanged) reads the neighbours' rows from there;
+// the three reductions of an iteration are block-wide sums in a fixed order.  Same arithmetic per cell as k_pcg_init_blk /
+// k_update_xr_blk / k_update_p_blk (csrc/pcg.cu); the tolerance policy of the inexact Newton iteration runs on the device.
+constexpr int SMALL_DG_MAX_CELLS = 256;
+
+template <int NLD>
+struct SmallPcgArgs {
+    const double *b, *detJ;
+    double *x;
+    double minv[NLD * NLD];
+    SgPcgPolicy pol;
+    int max_it;
+    double *rr0_out;
+    int *ctrl_done, *ctrl_iters;
+    double *ctrl_rr;
+};
+
+// sum of v over the block, identical in every thread (fixed order: warp shuffles, then the warps' partials)
+__device__ __forceinline__ double small_block_sum(double v, double *scratch) {
+    v = sg_warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();                       // the previous sum's readers are done with scratch
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double w = lane < nw ? scratch[lane] : 0.0;
+    return sg_warp_sum(w);
+}
+
+template <int NLD, int NNB, int P, bool BND>
+__global__ void __launch_bounds__(SMALL_DG_MAX_CELLS) k_dg_pcg_small(const ClsDev cd, const __grid_constant__ SmallPcgArgs<NLD> a) {
+    extern __shared__ __align__(16) double s_tab[];
+    const int ntab = (cd.n_self + cd.n_nb) * cd.S;
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) s_tab[i] = cd.tab[i];
+    const double *s_nb = s_tab + cd.n_self * cd.S;
+    double *s_p = s_tab + ((ntab + 1) & ~1);                 // [n_cells][NLD], 16-byte aligned rows
+    double *scratch = s_p + (size_t)cd.n_cells * NLD;
+    const int c = threadIdx.x;
+    const bool in = c < (int)cd.n_cells;
+    double x[NLD], r[NLD], p[NLD], z[NLD];
+    const double inv_det = in ? 1.0 / a.detJ[c] : 0.0;
+    auto mass_solve = [&](const double (&rv)[NLD], double (&zv)[NLD]) {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) s += a.minv[i * NLD + j] * rv[j];
+            zv[i] = s * inv_det;
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        x[i] = 0.0;
+        r[i] = in ? a.b[(size_t)c * NLD + i] : 0.0;
+    }
+    mass_solve(r, z);
+    double lrz = 0.0, lrr = 0.0;
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        p[i] = z[i];
+        lrz += r[i] * z[i];
+        lrr += r[i] * r[i];
+    }
+    double rz = small_block_sum(lrz, scratch), rr = small_block_sum(lrr, scratch);
+    const double rr0 = rr, tol2 = a.pol.tol2(rr0);
+    int it = 0, done = 0;
+    for (;;) {
+        if (!(rr > tol2) || !isfinite(rr)) {
+            done = isfinite(rr) ? 1 : 2;
+            break;
+        }
+        if (it >= a.max_it) break;
+        __syncthreads();                                     // everyone has read the previous p rows
+        if (in) {
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) s_p[(size_t)c * NLD + i] = p[i];
+        }
+        __syncthreads();
+        double xk[NLD], Ap[NLD];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) Ap[i] = 0.0;
+        if (in) dg_cell_apply<NLD, NNB, P, false, BND>(cd, s_tab, s_nb, c, s_p, xk, Ap);
+        double lpAp = 0.0;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) lpAp += p[i] * Ap[i];
+        const double pAp = small_block_sum(lpAp, scratch);   // may be negative: the reference's penalty is not coercive for every
+        const double alpha = rz / pAp;                       // element; like the multi-kernel path, CG just carries on
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            x[i] += alpha * p[i];
+            r[i] -= alpha * Ap[i];
+        }
+        mass_solve(r, z);
+        lrz = 0.0;
+        lrr = 0.0;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            lrz += r[i] * z[i];
+            lrr += r[i] * r[i];
+        }
+        const double rz_new = small_block_sum(lrz, scratch);
+        rr = small_block_sum(lrr, scratch);
+        const double beta = rz_new / rz;
+        rz = rz_new;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) p[i] = z[i] + beta * p[i];
+        ++it;
+    }
+    if (in) {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) a.x[(size_t)c * NLD + i] = x[i];
+    }
+    if (threadIdx.x == 0) {
+        *a.rr0_out = rr0;
+        *a.ctrl_done = done;
+        *a.ctrl_iters = it;
+        *a.ctrl_rr = rr;
+    }
+}
+
+template <int D, int P, bool DG>
+int small_pcg_t(sg_thermal_op *op, const double *b, double *x, const SgPcgPolicy &pol, int max_it, double *rr0_out, int *ctrl_done,
+                int *ctrl_iters, double *ctrl_rr, cudaStream_t st) {
+    if constexpr (DG) {
+        constexpr int NLD = nld_of(D, P), NNB = D + 1;
+        const long nc = op->d.n_cells;
+        if (!op->cls.tab || nc > SMALL_DG_MAX_CELLS || op->cls.cell_lo != 0 || op->cls.cell_hi != nc) return 0;
+        const int ntab = (op->cls.n_self + op->cls.n_nb) * op->cls.S;
+        const size_t smem = sizeof(double) * (((size_t)ntab + 1) / 2 * 2 + (size_t)nc * NLD + 32);
+        if (smem > 200 * 1024) return 0;
+        SmallPcgArgs<NLD> a;
+        a.b = b;
+        a.detJ = op->d.geom + (int64_t)D * D * op->d.n_cells;
+        a.x = x;
+        for (int i = 0; i < NLD * NLD; ++i) a.minv[i] = op->mass_inv[i];
+        a.pol = pol;
+        a.max_it = max_it;
+        a.rr0_out = rr0_out;
+        a.ctrl_done = ctrl_done;
+        a.ctrl_iters = ctrl_iters;
+        a.ctrl_rr = ctrl_rr;
+        auto k = op->bmat ? k_dg_pcg_small<NLD, NNB, P, true> : k_dg_pcg_small<NLD, NNB, P, false>;
+        SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int threads = (int)((nc + 31) / 32 * 32);
+        ClsDev cdv = op->cls;
+        cdv.rev = 0;
+        k<<<1, threads, smem, st>>>(cdv, a);
+        SG_CHECK_CUDA(cudaGetLastError());
+        sg_count_launch();
+        return 1;
+    } else {
+        return 0;
     }
 }
 
@@ -1547,6 +1706,7 @@ int build_tab(sg_thermal_op *op) {
     op->build_classes = &build_classes_t<D, P, DG>;
     op->linearize = &linearize_t<D, P, DG>;
     op->cheb_step = &cheb_step_t<D, P, DG>;
+    op->small_pcg = &small_pcg_t<D, P, DG>;
     return SG_OK;
 }
 
@@ -1603,6 +1763,20 @@ int sg_thermal_pcg_persistent(sg_thermal_op *op, const double *T_lin, const doub
     const int rc = sg_thermal_linearize(op, T_lin, st);
     if (rc) return rc;
     return sg_stencil_pcg(op->stencil, op->ctx->sm_count, b, dinv, x, work, pol, max_it, rr0_out, ctrl_done, ctrl_iters, ctrl_rr, st);
+}
+
+int sg_thermal_pcg_small_dg(sg_thermal_op *op, const double *T_lin, const double *b, double *x, const SgPcgPolicy &pol, int max_it,
+                            double *rr0_out, int *ctrl_done, int *ctrl_iters, double *ctrl_rr, cudaStream_t st) {
+    if (op->d.family != 1 || op->ctx->nranks != 1 || !op->cls.tab || op->d.n_cells > SMALL_DG_MAX_CELLS) return 0;
+    if (op->dev.n_bf > 0 && !op->bmat) return 0;        // exterior facets must be inside the class kernel
+    static const bool off = [] {
+        const char *e = getenv("SG_NO_PERSISTENT");
+        return e && e[0] == '1';
+    }();
+    if (off) return 0;
+    const int rc = sg_thermal_linearize(op, T_lin, st);
+    if (rc) return rc;
+    return op->small_pcg(op, b, x, pol, max_it, rr0_out, ctrl_done, ctrl_iters, ctrl_rr, st);
 }
 
 int sg_thermal_apply_dot(sg_thermal_op *op, const double *T_lin, const double *x, double *y, SgRed red, double *dot2,

@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_mechanics_gpu.py -x -q 2>&1 | tail -12
-python tools/mech_probe.py 48 48 8 160 160 8 2>&1 | python -c "
-import json,sys
-for l in sys.stdin:
-    try: d=json.loads(l)
-    except Exception: print(l.strip()[:300]); continue
-    print(d['cells'], d['physics'], 'its', d['pcg_its'], 'ms_mech', d['ms_mechanics'], 'ms_step', d['ms_per_step'])"
+python -m pytest tests -m gpu -x -q > gpurun_out/r2C_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2C_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
