@@ -589,12 +589,21 @@ def run_gpu(args):
             if world > 1:
                 raise
 
+    pcheck = None
+    if world > 1 and not args.no_parity and args.workload == DEFAULT_WORKLOAD:
+        try:
+            pcheck = partition_check(ctx, rank, world, local, cheb_deg, eta)
+        except Exception as e:  # noqa: BLE001
+            pcheck = {"error": repr(e)[:300], "ok": False}
     if rank != 0:
         if world > 1:
             dist.barrier()
         return
 
     failed = False
+    if pcheck is not None:
+        head["partition_check"] = pcheck
+        failed = not pcheck.get("ok", False)
     if world == 1:
         # ---- parity of the timed path, then the CPU baseline on the same sample ----
         port = None
@@ -612,8 +621,71 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     if failed:
-        sys.stderr.write("bench.py: parity_check FAILED: " + json.dumps(head["parity_check"]) + "\n")
+        sys.stderr.write("bench.py: parity check FAILED: " + json.dumps(head.get("parity_check") or head.get("partition_check")) + "\n")
         sys.exit(1)
+
+
+def partition_check(ctx, rank: int, world: int, local: int, cheb_degree: int, eta, steps: int = 3):
+    """N > 1: the parity plate (48x48x8 hexahedra) split into N x-slabs — direct halo puts, in-kernel waits and all-reduces —
+    against the CPU port of the WHOLE plate on rank 0, with the rule of parity_check.  Collective: every rank calls it;
+    returns the object on rank 0, None elsewhere."""
+    import numpy as np
+    import torch.distributed as dist
+    from fem_glass_tempering_b200 import ThermoViscoProblem, distributed
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import stress_rounding_floor
+    wl = PARITY_WORKLOAD
+    dim, n, a, cfg = WORKLOADS[wl]
+    lengths = tuple(k * a for k in n)
+    mesh, part, info = distributed.slab_partition(dim, n, lengths, "DG", 1, rank, world)
+    prob = ThermoViscoProblem(mesh_path="", time=(0.0, 50.0), dt=DT, config=cfg, model_parameters=params_of(wl), mesh=mesh, ctx=ctx,
+                              partition=part, materialize="minimal", verbose=False)
+    prob.setup(dirichlet_bc=False)
+    prob._thermal_op.set_chebyshev(cheb_degree)
+    prob.solver.forcing_eta = eta
+    port = make_cpu_port(wl)[0] if rank == 0 else None
+    own = slice(part["own_lo"], part["own_hi"])
+    worst = {"T": 0.0, "Tf": 0.0, "sigma": 0.0, "sigma_over_floor": 0.0}
+    tiles = True
+    for _ in range(steps):
+        prob.t += prob.dt
+        prob._solve_T()
+        prob._solve_viscoelastic()
+        loc = {"T": prob.functions_current["T"].x.array[own].cpu().numpy(), "Tf": prob.functions_current["Tf"].x.array[own].cpu().numpy(),
+               "sigma": prob.functions_next["sigma"].x.array.view(-1, dim * dim)[own].cpu().numpy()}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, loc)
+        if rank == 0:
+            port.step(fused=True)
+            f = port.fields(True)
+            T = np.concatenate([g["T"] for g in gathered])           # x-slabs in rank order = the unpartitioned DG numbering
+            Tf = np.concatenate([g["Tf"] for g in gathered])
+            S = np.concatenate([g["sigma"] for g in gathered])
+            tiles = tiles and T.size == f["T"].size
+            if tiles:
+                rel = lambda x, y: float(np.max(np.abs(x - y)) / np.max(np.abs(y)))
+                worst["T"] = max(worst["T"], rel(T, f["T"]))
+                worst["Tf"] = max(worst["Tf"], rel(Tf, f["Tf"]))
+                dT = np.abs(f["T"] - f["T_prev"])
+                good = dT > 1e-6
+                sg, so = S[good], f["sigma"].reshape(-1, dim * dim)[good]
+                scale = float(np.max(np.abs(so)))
+                err = np.max(np.abs(sg - so), axis=1)
+                floor = stress_rounding_floor(port.vp, dT[good], np.abs(f["xi"])[good])
+                worst["sigma"] = max(worst["sigma"], float(np.max(err) / scale))
+                worst["sigma_over_floor"] = max(worst["sigma_over_floor"], float(np.max(err - 2.0 * floor) / scale))
+            port.end_step()
+        prob._update_values(current=prob.functions_current["T"], previous=prob.functions_previous["T"])
+    peer = bool(prob._thermal_op.peer_memory)
+    prob._thermal_op.close()
+    dist.barrier()
+    if rank != 0:
+        return None
+    ok = tiles and worst["T"] <= PARITY_TOL and worst["Tf"] <= PARITY_TOL and worst["sigma_over_floor"] <= PARITY_TOL
+    return {"workload": f"{wl}: {'x'.join(map(str, n))} hexahedra split into {world} x-slabs, {steps} steps, headline solver settings",
+            "checker": "oracle/cpu_port.py on the whole plate (rank 0)", "owned_ranges_tile_the_plate": bool(tiles),
+            "transport": "NVLink peer memory" if peer else "NCCL", "T": worst["T"], "Tf": worst["Tf"], "sigma": worst["sigma"],
+            "sigma_excess_over_rounding_floor": max(worst["sigma_over_floor"], 0.0), "tol": PARITY_TOL, "ok": bool(ok)}
 
 
 def mechanics_config(ctx, local: int, n=(160, 160, 8), steps: int = 3) -> dict:  # noqa: C901
