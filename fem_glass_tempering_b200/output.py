@@ -32,6 +32,10 @@ class HostMirror:
         p = problem
         self.functions = {"T": p.functions_current["T"], "phi": p.functions["phi"], "Tf": p.functions_current["Tf"],
                           "xi": p.functions["xi"], "sigma": p.functions_next["sigma"]}
+        self.FIELDS = HostMirror.FIELDS
+        if getattr(p, "mechanics", None) is not None:       # extension: the accumulated displacement travels with the stress
+            self.functions["displacement"] = p.functions["displacement"]
+            self.FIELDS = HostMirror.FIELDS + ("displacement",)
         self._device = p._device
         self._stream = torch.cuda.Stream(device=self._device)
         self._staging = {k: torch.empty_like(f.x.array) for k, f in self.functions.items()}
@@ -139,7 +143,7 @@ class FieldWriter:
         fields = {k: {"block_size": f.function_space.block_size, "name": f.name, "n_nodes": f.function_space.n_nodes}
                   for k, f in fn.items()}
         self._files = RankFiles(directory, comm.rank, comm.size, fields, owned, offset, total)
-        for key in ("T", "sigma"):
+        for key in ("T", "sigma") + (("displacement",) if "displacement" in fn else ()):
             self._files.save_coordinates(key, fn[key].function_space.tabulate_dof_coordinates())
         self._q: queue.Queue = queue.Queue()
         self._err = None

@@ -268,6 +268,27 @@ def test_dg_stress_is_in_discrete_equilibrium_after_every_step(sg_ctx):
     assert prob.functions["displacement"].x.array.abs().max().item() > 0.0
 
 
+def test_field_writer_records_the_displacement(sg_ctx, tmp_path):
+    """With mechanics on, the per-step output (TVP:357-364 schedule, output.FieldWriter) carries the displacement too."""
+    from fem_glass_tempering_b200.output import read_series
+    mesh = M.box_mesh(4, 4, 2, 4.0, 4.0, 2.0)
+    config = {"T": {"element": "DG", "degree": 1}, "sigma": {"element": "DG", "degree": 1}}
+    prob = ThermoViscoProblem(mesh_path="", time=(0.0, 50.0), dt=0.1, config=config, mesh=mesh, ctx=sg_ctx, verbose=False,
+                              model_parameters=dict(vo.MAIN_PARAMS, mechanics=True, sip_penalty=8.0))
+    prob.output_dir = str(tmp_path)
+    prob.setup(dirichlet_bc=False)
+    for _ in range(3):
+        prob.t += prob.dt
+        prob.solve_timestep(prob.t)
+    prob._finalize()
+    times, u = read_series(str(tmp_path), "displacement")
+    assert len(times) == 4 and u.shape == (4, mesh.n_vertices * 3)      # initial state + three steps
+    assert np.abs(u[0]).max() == 0.0
+    np.testing.assert_array_equal(u[-1], prob.functions["displacement"].x.array.cpu().numpy())
+    _, sig = read_series(str(tmp_path), "sigma")
+    np.testing.assert_array_equal(np.nan_to_num(sig[-1]), np.nan_to_num(prob.functions_next["sigma"].x.array.cpu().numpy()))
+
+
 def test_mechanics_off_is_the_reference_behaviour(sg_ctx):
     mesh = M.graded_line_mesh()
     config = {"T": {"element": "DG", "degree": 1}, "sigma": {"element": "CG", "degree": 1}}
