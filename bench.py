@@ -74,8 +74,14 @@ METRIC, UNIT = "quadrature-point updates/s (full timestep: heat solve + viscoela
 PARITY_TOL = 1e-10
 
 
+NEWTON_GUESS = None          # --newton-guess: model_parameters["newton_initial_guess"] of every GPU problem of this run
+
+
 def params_of(workload: str) -> dict:
-    return dict(MAIN_PARAMS, **({} if REFERENCE_PENALTY else PARAM_OVERRIDES.get(workload, {})))
+    p = dict(MAIN_PARAMS, **({} if REFERENCE_PENALTY else PARAM_OVERRIDES.get(workload, {})))
+    if NEWTON_GUESS:
+        p["newton_initial_guess"] = NEWTON_GUESS
+    return p
 
 
 def measured_peak():
@@ -823,10 +829,13 @@ def main():
     ap.add_argument("--cheb", type=int, default=None, help="Chebyshev preconditioner degree of the DG solver (0 = off)")
     ap.add_argument("--reference-penalty", action="store_true",
                     help="3-D DG plates with the reference's SIP penalty 5.0 instead of the coercive 6.0 (keep the run under 15 steps)")
+    ap.add_argument("--newton-guess", default=None, choices=["previous", "extrapolate"],
+                    help='start of the Newton iteration: "previous" = T_n like the reference (TVP:389), "extrapolate" = 2 T_n - T_{n-1}')
     ap.add_argument("--eta", type=float, default=None, help="first forcing term of the inexact Newton iteration (0 = fixed tolerance)")
     args = ap.parse_args()
-    global REFERENCE_PENALTY
+    global REFERENCE_PENALTY, NEWTON_GUESS
     REFERENCE_PENALTY = args.reference_penalty
+    NEWTON_GUESS = args.newton_guess
     with StdoutToStderr() as OUT:
         if args.impl == "reference":
             run_reference(args)

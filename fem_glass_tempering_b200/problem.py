@@ -53,6 +53,7 @@ class NewtonSolverGPU:
         self.report = False
         self.krylov_solver = _KrylovStub()
         self.linear_rtol = 1e-12   # final linear-residual target of a step, relative to the first Newton residual
+        self.linear_atol = 0.0     # absolute floor of that target
         self.forcing_eta = 1e-3    # inexact Newton: first forcing term (0 = every PCG solve runs to the target)
         self.last_stats = None
 
@@ -60,6 +61,7 @@ class NewtonSolverGPU:
         op = self._p._thermal_op
         op.opts.newton_rtol, op.opts.newton_atol, op.opts.newton_max_it = self.rtol, self.atol, self.max_it
         op.opts.lin_rtol = self.linear_rtol
+        op.opts.lin_atol = self.linear_atol
         op.opts.forcing_eta = self.forcing_eta
         try:
             st = op.timestep(u.x.array, self._p.functions_previous["T"].x.array)
@@ -107,6 +109,10 @@ class ThermoViscoProblem:
                                               functions_previous=self.functions_previous,
                                               functions_next=self.functions_next, dt=self.dt,
                                               to_sigma=self._to_sigma)                            # TVP:48-54
+        guess = model_parameters.get("newton_initial_guess", "previous")
+        if guess not in ("previous", "extrapolate"):
+            raise ValueError('model_parameters["newton_initial_guess"] must be "previous" (TVP:389) or "extrapolate"')
+        self._extrapolate, self._T_pp = guess == "extrapolate", None
         self.mechanics = None
         if self._mech_opts:
             from .mechanics import MechanicalEquilibrium
@@ -313,7 +319,32 @@ class ThermoViscoProblem:
         self._write_output()
         self._update_values(current=self.functions_current["T"], previous=self.functions_previous["T"])  # TVP:378
 
+    def _extrapolated_start(self) -> None:
+        """model_parameters["newton_initial_guess"] = "extrapolate": start Newton from 2 T_n - T_{n-1} instead of T_n (what the
+        reference's NewtonSolver starts from, TVP:389).  The discrete solution is the same to solver tolerance — the final
+        linear-solve target stays anchored at |F(T_n)| through lin_atol — but the first correction is 5-20x smaller, which
+        usually saves a Newton iteration per step."""
+        import torch
+        T, Tp, op = self.functions_current["T"]._array, self.functions_previous["T"]._array, self._thermal_op
+        if self._T_pp is None:
+            self._T_pp = Tp.clone()                       # first step: nothing to extrapolate from yet
+            self._F_scratch = torch.empty_like(Tp)
+            return
+        # |F| at the reference's starting point T_n: keeps the absolute accuracy target of the step unchanged
+        own = slice(op.own_lo, op.own_hi)
+        F = op.residual(T, Tp, self._F_scratch)
+        f2 = (F[own] * F[own]).sum()
+        if self._ctx.nranks > 1:
+            import torch.distributed as dist
+            dist.all_reduce(f2)
+        self.solver.linear_atol = self.solver.linear_rtol * float(f2.sqrt())
+        guess = 2.0 * T - self._T_pp
+        self._T_pp.copy_(T)
+        T.copy_(guess)
+
     def _solve_T(self) -> None:
+        if self._extrapolate:
+            self._extrapolated_start()
         _, converged = self.solver.solve(self.functions_current["T"])                             # TVP:389
         assert (converged), "Newton solver did not converge: " + _lib.lib().sg_last_error().decode()   # TVP:390
 

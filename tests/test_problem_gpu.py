@@ -335,3 +335,27 @@ def test_default_run_against_the_hand_evaluated_history(sg_ctx):
         moved = np.abs(st["T"] - st["T_prev"])[g["winner_dof"]] > 1e-6
         sig = cpu(prob.functions_next["sigma"])
         assert np.max(np.abs(sig[moved] - st["sigma"][moved])) <= 1e-9 * np.max(np.abs(st["sigma"][moved]))
+
+
+def test_extrapolated_newton_start_reaches_the_same_solution(sg_ctx):
+    """model_parameters["newton_initial_guess"] = "extrapolate" starts Newton from 2 T_n - T_{n-1} instead of T_n (TVP:389):
+    a different path to the same discrete solution — histories must agree to the solver tolerance."""
+    mesh = msh.box_mesh(6, 6, 3, 6.0, 6.0, 3.0)
+    cfg = {"T": {"element": "DG", "degree": 1}, "sigma": {"element": "DG", "degree": 1}}
+    runs = {}
+    for guess in ("previous", "extrapolate"):
+        prob = ThermoViscoProblem(mesh_path="", time=(0.0, 50.0), dt=0.1, config=cfg, mesh=mesh, ctx=sg_ctx, verbose=False,
+                                  model_parameters=dict(MAIN_PARAMS, newton_initial_guess=guess))
+        prob.setup(dirichlet_bc=False)
+        its = 0
+        for _ in range(6):
+            prob.t += prob.dt
+            prob.solve_timestep(prob.t)
+            its += prob.solver.last_stats.lin_its
+        runs[guess] = (cpu(prob.functions_current["T"]), cpu(prob.functions_current["Tf"]), its)
+    assert rel_err(runs["extrapolate"][0], runs["previous"][0]) <= 1e-12
+    assert rel_err(runs["extrapolate"][1], runs["previous"][1]) <= 1e-12
+    assert runs["extrapolate"][2] <= runs["previous"][2]
+    with pytest.raises(ValueError):
+        ThermoViscoProblem(mesh_path="", time=(0.0, 1.0), dt=0.1, config=cfg, mesh=mesh, ctx=sg_ctx, verbose=False,
+                           model_parameters=dict(MAIN_PARAMS, newton_initial_guess="secant"))
