@@ -297,7 +297,7 @@ __device__ __forceinline__ void cell_compute(const Tab<D, P, DG> &tab, const OpD
 }
 
 template <int D, int P, bool DG, int MODE>
-__global__ void __launch_bounds__(TB) cell_kernel(const __grid_constant__ Tab<D, P, DG> tab, const __grid_constant__ OpDev op, const double *__restrict__ x,
+__global__ void __launch_bounds__(TB, (P == 1) ? 6 : 1) cell_kernel(const __grid_constant__ Tab<D, P, DG> tab, const __grid_constant__ OpDev op, const double *__restrict__ x,
                                                   const double *__restrict__ xprev, double *__restrict__ y) {
     constexpr int NLD = nld_of(D, P);
     const long c = op.cell_lo + (long)blockIdx.x * TB + threadIdx.x;
