@@ -43,12 +43,14 @@ def test_ctypes_structures_match_the_header_layout(tmp_path):
     sizeof and every offsetof (field names must exist in the header for this to compile), ctypes must agree."""
     import shutil
     import subprocess
+    from fem_glass_tempering_b200 import _lib_mech as lm
     from fem_glass_tempering_b200 import _lib_thermal as lt
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
     pairs = [("sg_visco_params", _lib.ViscoParamsC), ("sg_visco_fields", _lib.ViscoFieldsC),
              ("sg_visco_gather", _lib.ViscoGatherC), ("sg_thermal_desc", lt.ThermalDescC),
-             ("sg_halo_segment", lt.HaloSegmentC), ("sg_newton_opts", lt.NewtonOptsC), ("sg_newton_stats", lt.NewtonStatsC)]
+             ("sg_halo_segment", lt.HaloSegmentC), ("sg_newton_opts", lt.NewtonOptsC), ("sg_newton_stats", lt.NewtonStatsC),
+             ("sg_mech_desc", lm.MechDescC), ("sg_mech_fields", lm.MechFieldsC)]
     header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "surroglas_b200.h")
     lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{header}"', "int main(void) {"]
     for cname, cls in pairs:
@@ -64,3 +66,11 @@ def test_ctypes_structures_match_the_header_layout(tmp_path):
         assert int(out[cname]) == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_mech_entry_points_validate_their_arguments_without_a_gpu():
+    """The equilibrium extension's entry points reject NULL handles before any CUDA call (error code + message)."""
+    L = _lib.lib()
+    assert L.sg_mech_op_create(None, None, None) == _lib.SG_E_INVALID and b"NULL" in L.sg_last_error()
+    assert L.sg_mech_solve(None, None, None, 1e-8, 0.0, 10, None, None, None) == _lib.SG_E_INVALID
+    assert L.sg_mech_apply_bytes(None) == -1
