@@ -168,6 +168,7 @@ int sg_stencil_build(sg_ctx *ctx, const int32_t *dofmap, int64_t n_cells, int n_
                      const uint16_t *cls16, const double *tab, int S, int64_t n_rows, SgStencil **out);
 int sg_stencil_apply(const SgStencil *s, const double *x, double *y, int64_t own_lo, int64_t own_hi, SgRed red, double *dot2,
                      const int *skip, cudaStream_t st, const SgHaloWait *wait = nullptr);
+int sg_stencil_apply_cells(const SgStencil *s, const double *x, double *y, int subtract, SgRed red, double *dot2, cudaStream_t st);
 int sg_stencil_attach_boundary(SgStencil *s, const int32_t *dofmap, int64_t n_cells, int64_t cell_lo, int64_t cell_hi, int64_t n_bf,
                                const int32_t *bf_cell, const int32_t *bf_facet, int nfd, const int *facet_dofs, const double *bmat,
                                int *attached);

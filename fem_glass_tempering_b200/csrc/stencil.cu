@@ -57,6 +57,7 @@ struct StDev {
     long nc;
     int nfd, maxf;
     const int32_t *fd;    // [4][6] local dofs of the facets (thermal.cu facet_dof), device memory
+    int sub;              // 1: y -= (stencil row) instead of y = (stencil row)  (residual in gather form, sg_stencil_apply_cells)
 };
 
 constexpr int ROW_BND = 0x8000;
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(STB, MINB) k_stencil_apply(const StDev sd, con
             acc = fma(e.coef, __ldg(xr + e.off), acc);
         }
         if ((cw & ROW_BND) && sd.bmat) acc += stencil_boundary_row(sd, row, x);
-        y[row] = acc;
+        y[row] = sd.sub ? y[row] - acc : acc;
         if (row >= sd.own_lo && row < sd.own_hi) dsum[0] += __ldg(xr) * acc;
     }
     sg_grid_reduce<2>(dsum, red, dot_out);
@@ -834,6 +835,23 @@ int sg_stencil_apply(const SgStencil *s, const double *x, double *y, int64_t own
         if (own_hi < sd.n_rows) sd.safe_hi = std::max<long>(sd.safe_lo, own_hi - s->max_off);
     }
     s->kernel<<<s->grid, STB, s->smem, st>>>(sd, x, y, red, dot2, skip, hw);
+    SG_CHECK_CUDA(cudaGetLastError());
+    sg_count_launch();
+    return SG_OK;
+}
+
+// Cell part only (the attached exterior facets, if any, are left out), y = S x or - subtract - y -= S x: the two halves of
+// the residual in gather form,  F_cells = S_J T - S_M T_prev  (thermal.cu).
+int sg_stencil_apply_cells(const SgStencil *s, const double *x, double *y, int subtract, SgRed red, double *dot2, cudaStream_t st) {
+    StDev sd = s->dev;
+    sd.own_lo = 0;
+    sd.own_hi = 0;                 // no dot product wanted
+    sd.safe_lo = 0;
+    sd.safe_hi = sd.n_rows;
+    sd.bmat = nullptr;
+    sd.sub = subtract ? 1 : 0;
+    SgHaloWait hw{};
+    s->kernel<<<s->grid, STB, s->smem, st>>>(sd, x, y, red, dot2, nullptr, hw);
     SG_CHECK_CUDA(cudaGetLastError());
     sg_count_launch();
     return SG_OK;

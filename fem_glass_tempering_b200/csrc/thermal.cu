@@ -1061,6 +1061,8 @@ struct sg_thermal_op {
     double *bmat;
     SgStencil *stencil;    // CG: row-stencil classes (stencil.cu); nullptr: cell-centric cg_class_apply
     int stencil_bnd;       // the stencil kernel also applies the exterior facets (gather form; no cg_bfacet_apply launch)
+    SgStencil *stencil_mass;   // CG: the same row classes for |detJ| Mhat: residual in gather form, F_cells = S_J T - S_M T_prev
+    double *mass_tab;          // its class tables (device)
     double *diag_cells;    // CG: the cell part of diag J (M + dt alpha K does not depend on T), computed once at creation
     int (*linearize)(const sg_thermal_op *, const double *T_lin, cudaStream_t st);
     int (*cheb_step)(const sg_thermal_op *, const SgChebStep &, SgRed red, double *dot_out, const int *skip, cudaStream_t st);
@@ -1083,6 +1085,16 @@ inline bool inkernel_wait() {
         return !(e && e[0] == '1');
     }();
     return on;
+}
+
+// rows from which the CG residual runs in gather form (SG_GATHER_RESID_MIN_ROWS overrides: the tests set it to 0)
+static const long GATHER_RESID_MIN_ROWS = getenv("SG_GATHER_RESID_MIN_ROWS") ? atol(getenv("SG_GATHER_RESID_MIN_ROWS")) : 1000000;
+inline bool gather_resid_off() {      // SG_NO_GATHER_RESID=1: keep cg_class_resid (measurement / test switch)
+    static const bool off = [] {
+        const char *e = getenv("SG_NO_GATHER_RESID");
+        return e && e[0] == '1';
+    }();
+    return off;
 }
 
 inline unsigned capped_grid(long n, int tb) {
@@ -1122,7 +1134,10 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
     const unsigned gc = (unsigned)((ncell + TB - 1) / TB), gb = capped_grid(dv.n_bf, TB);
     const bool fast = mode == MODE_APPLY && op->cls.tab != nullptr;
     const bool cached_diag = !DG && mode == MODE_DIAG && op->diag_cells != nullptr && y != op->diag_cells;
-    if (!DG && !cached_diag && !(mode == MODE_APPLY && (op->y_is_zero || (fast && op->stencil))))
+    const bool gather_resid = !DG && mode == MODE_RESID && op->cls.tab != nullptr && !(op->d.flags & SG_THERMAL_GENERAL_RESIDUAL) &&
+                              op->stencil && op->stencil_mass && dv.dt_f == 0.0 && !gather_resid_off() &&
+                              dv.n_dofs >= GATHER_RESID_MIN_ROWS;   // two ~row-kernel launches: below, the one scatter launch wins
+    if (!DG && !cached_diag && !gather_resid && !(mode == MODE_APPLY && (op->y_is_zero || (fast && op->stencil))))
         SG_CHECK_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)dv.n_dofs, st));
     if (cached_diag) {
         // point Jacobi asks for diag J(T) in every Newton iteration; only the exterior facets (below) depend on T
@@ -1184,12 +1199,19 @@ int launch_op(const sg_thermal_op *op, int mode, const double *Tlin, const doubl
             auto k = wide ? dg_class_resid<NLD, D + 1, P, true> : dg_class_resid<NLD, D + 1, P, false>;
             SG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
             k<<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, rd, x, y);
+        } else if (gather_resid) {
+            // gather form: F_cells = S_J T - S_M T_prev, plain stores, no atomics (f = 0: no load vector)
+            double *scr = op->own_red.partials + 2 * SG_MAX_BLOCKS;
+            int rcg = sg_stencil_apply_cells(op->stencil, x, y, 0, op->own_red, scr, st);
+            if (!rcg) rcg = sg_stencil_apply_cells(op->stencil_mass, xprev, y, 1, op->own_red, scr, st);
+            if (rcg) return rcg;
         } else {
             SG_CHECK_CUDA(cudaFuncSetAttribute(cg_class_resid<NLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->cls_smem));
             cg_class_resid<NLD><<<op->cls_grid, CB, op->cls_smem, st>>>(op->cls, rd, x, y);
+            sg_count_launch();
         }
         SG_CHECK_CUDA(cudaGetLastError());
-        sg_count_launch();
+        if (DG) sg_count_launch();
     } else if (ncell > 0) {
         if (mode == MODE_APPLY && op->wait && op->wait->n) {
             const int rcw = sg_peer_wait(nullptr, *op->wait, st);
@@ -1462,6 +1484,24 @@ int ensure_own_red(sg_thermal_op *op) {
 
 // CG: try the row-stencil form of the apply (stencil.cu) and keep it only if it reproduces the cell part of
 // cg_class_apply on a pseudo-random vector (guards the 64-bit row hash and the table construction).
+// one representative cell per geometry class (any member: the class mass matrix only needs its |detJ|)
+__global__ void k_class_rep(long nc, const uint16_t *__restrict__ cls16, int32_t *rep) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nc) rep[cls16[c]] = (int32_t)c;
+}
+template <int NLD>
+struct MassTabArgs {
+    double mass[NLD * NLD];
+};
+template <int NLD>
+__global__ void k_mass_tables(const __grid_constant__ MassTabArgs<NLD> ma, int n_cls, int S, const int32_t *__restrict__ rep,
+                              const double *__restrict__ detJ, double *__restrict__ tab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_cls) return;
+    const double dj = detJ[rep[k]];
+    for (int e = 0; e < S; ++e) tab[(long)k * S + e] = e < NLD * NLD ? dj * ma.mass[e] : 0.0;
+}
+
 template <int D, int P>
 int build_stencil_t(sg_thermal_op *op) {
     constexpr int NLD = nld_of(D, P);
@@ -1529,6 +1569,41 @@ int build_stencil_t(sg_thermal_op *op) {
         op->stencil_bnd = attached;
     }
     op->stencil = st;
+    // The residual's cell part in the same form (no RED scatter in the time loop): a second set of row classes from the
+    // class MASS matrices |detJ| Mhat.  Verified like the first against a cell-centric scatter; any failure just keeps
+    // cg_class_resid.
+    {
+        const int NS = op->cls.n_self, S = op->cls.S;
+        DevBuf rep;
+        if (cudaMalloc(&rep.p, sizeof(int32_t) * (size_t)NS) == cudaSuccess && cudaMalloc(&op->mass_tab, sizeof(double) * (size_t)NS * S) == cudaSuccess) {
+            MassTabArgs<NLD> ma;
+            memcpy(ma.mass, op->mass, sizeof(double) * NLD * NLD);
+            k_class_rep<<<(unsigned)((dv.n_cells + 255) / 256), 256>>>(dv.n_cells, op->cls.cls16, rep.as<int32_t>());
+            k_mass_tables<NLD><<<(NS + 63) / 64, 64>>>(ma, NS, S, rep.as<int32_t>(), op->d.geom + (int64_t)D * D * op->d.n_cells, op->mass_tab);
+            SgStencil *sm = nullptr;
+            if (cudaGetLastError() == cudaSuccess &&
+                sg_stencil_build(op->ctx, dv.dofmap, dv.n_cells, NLD, dv.cell_lo, dv.cell_hi, op->cls.cls16, op->mass_tab, S, dv.n_dofs, &sm) == SG_OK && sm) {
+                // check: S_M x against the scatter of the class mass matrices
+                ClsDev mass_cells = op->cls;
+                mass_cells.bmat = nullptr;
+                mass_cells.tab = op->mass_tab;
+                cudaMemset(ya.p, 0, sizeof(double) * (size_t)n);
+                cudaMemset(mx.p, 0, 2 * sizeof(unsigned long long));
+                cg_class_apply<D, P><<<op->cls_grid, CB, op->cls_smem>>>(mass_cells, xb.as<double>(), ya.as<double>(), op->own_red, scratch, nullptr);
+                int rcm = sg_stencil_apply_cells(sm, xb.as<double>(), yb.as<double>(), 0, op->own_red, scratch, 0);
+                k_max_diff<<<g, 256>>>(n, ya.as<double>(), yb.as<double>(), mx.as<unsigned long long>());
+                unsigned long long mb[2] = {0, 0};
+                if (!rcm && cudaMemcpy(mb, mx.p, sizeof(mb), cudaMemcpyDeviceToHost) == cudaSuccess) {
+                    double ym, dm;
+                    memcpy(&ym, &mb[0], 8);
+                    memcpy(&dm, &mb[1], 8);
+                    if (dm <= 1e-12 * ym) op->stencil_mass = sm;
+                }
+                if (!op->stencil_mass) sg_stencil_destroy(sm);
+            }
+        }
+        cudaGetLastError();
+    }
     return SG_OK;
 }
 
@@ -1938,6 +2013,8 @@ int sg_thermal_op_destroy(sg_thermal_op *op) {
     if (op->nbr_ext) cudaFree(op->nbr_ext);
     if (op->bmat) cudaFree(op->bmat);
     sg_stencil_destroy(op->stencil);
+    sg_stencil_destroy(op->stencil_mass);
+    cudaFree(op->mass_tab);
     if (op->diag_cells) cudaFree(op->diag_cells);
     if (op->own_red.partials) cudaFree(op->own_red.partials);
     if (op->own_red.counter) cudaFree(op->own_red.counter);

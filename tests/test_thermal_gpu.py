@@ -333,3 +333,44 @@ def test_nonconvergence_is_reported(sg_ctx):
     with pytest.raises(_lib.SgError) as e:
         op.timestep(T, T.clone())
     assert e.value.code == _lib.SG_E_NOCONV          # TVP:390 assert(converged)
+
+
+def test_cg_residual_in_gather_form(sg_ctx):
+    """Large CG meshes evaluate the residual's cell part as S_J T - S_M T_prev with two row-stencil launches (no RED
+    scatter in the time loop).  Forced on small meshes here (subprocess: the threshold is read once per process) and
+    compared with the cell-centric scatter kernel and, through the existing tests, the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from fem_glass_tempering_b200 import _lib, fe
+from fem_glass_tempering_b200 import mesh as msh
+from fem_glass_tempering_b200.thermal_op import ThermalOperator
+from oracle import thermal_oracle as to
+from oracle.visco_oracle import MAIN_PARAMS
+ctx = _lib.Context(0)
+for dim, degree, dims in ((2, 2, (9, 5)), (3, 1, (5, 4, 3)), (3, 2, (5, 4, 3)), (3, 2, (21, 18, 4))):
+    m = msh.plate_mesh(dim, dims, tuple(float(k) for k in dims))
+    space = fe.ScalarSpace(m, "CG", degree)
+    op = ThermalOperator(ctx, space, MAIN_PARAMS, 0.1, cheb_degree=0)
+    assert op.stencil_info()["active"]
+    n = space.n_nodes
+    rng = np.random.default_rng(5)
+    T, Tp = 700 + 100 * rng.random(n), 700 + 100 * rng.random(n)
+    F = op.residual(torch.from_numpy(T).cuda(), torch.from_numpy(Tp).cuda(), torch.full((n,), 3.0, dtype=torch.float64, device="cuda")).cpu().numpy()
+    if m.n_cells < 5000:
+        orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "CG", degree, MAIN_PARAMS, 0.1)
+        Fo = orc.residual(T, Tp)
+        assert np.max(np.abs(F - Fo)) <= 1e-12 * np.max(np.abs(Fo)), (dim, degree, np.max(np.abs(F - Fo)))
+    print("ok", dim, degree, dims)
+print("GATHER_RESID_OK")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for rows in ("0", "1000000000"):
+        env = dict(os.environ, SG_GATHER_RESID_MIN_ROWS=rows)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert res.returncode == 0 and "GATHER_RESID_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
+        outs[rows] = res.stdout
+    assert outs["0"].count("ok") == outs["1000000000"].count("ok") == 4
