@@ -307,6 +307,34 @@ def test_row_stencil_form_of_the_cg_apply(dim, n, degree):
     assert R_scrambled > space.n_nodes // 2
 
 
+@pytest.mark.parametrize("dim,n,degree", [(2, (10, 6), 2), (3, (4, 7, 3), 1), (3, (4, 7, 3), 2)])
+def test_row_stencil_form_of_the_cg_residual(dim, n, degree):
+    """Large CG meshes evaluate the cell part of the residual as S_J T - S_M T_prev: the row classes of the Jacobian tables
+    applied to T minus the row classes of the class MASS matrices |detJ| Mhat applied to T_prev (csrc/thermal.cu
+    build_stencil_t, numpy emulation).  Must equal the cell-by-cell residual (f = 0, exterior facets apart)."""
+    import kernel_mirror
+    from fem_glass_tempering_b200 import mesh as msh
+    m = msh.plate_mesh(dim, n, tuple(float(k) for k in n))
+    space = fe.ScalarSpace(m, "CG", degree)
+    tabs, geo = fe.operator_tables(dim, degree), fe.cell_geometry(m)
+    A = kernel_mirror.cell_matrices(space, tabs, geo, MAIN_PARAMS, 0.1)
+    Mc = geo.detJ[:, None, None] * tabs.mass[None]
+    gkey = np.round(np.concatenate([geo.Jinv.reshape(m.n_cells, -1), geo.detJ[:, None]], axis=1), 9)
+    _, first, ccls = np.unique(gkey, axis=0, return_index=True, return_inverse=True)
+    rcls, R = kernel_mirror.row_stencil_classes(space.dofmap, ccls, space.n_nodes)
+    rng = np.random.default_rng(2)
+    T, Tp = 700 + 100 * rng.random(space.n_nodes), 700 + 100 * rng.random(space.n_nodes)
+    yJ, _ = kernel_mirror.row_stencil_apply(space.dofmap, ccls, A[first], rcls, R, T)
+    yM, _ = kernel_mirror.row_stencil_apply(space.dofmap, ccls, Mc[first], rcls, R, Tp)
+    F = np.zeros(space.n_nodes)
+    np.add.at(F, space.dofmap.ravel(), (np.einsum("cij,cj->ci", A, T[space.dofmap]) - np.einsum("cij,cj->ci", Mc, Tp[space.dofmap])).ravel())
+    assert np.max(np.abs((yJ - yM) - F)) <= 1e-12 * np.max(np.abs(F))
+    # ... which is the cell part of the oracle's residual: M (T - T_prev) + dt alpha K T
+    orc = to.ThermalOracle(m.x, m.cells, space.dofmap, space.element.nodes, "CG", degree, MAIN_PARAMS, 0.1)
+    Fo = orc.M @ (T - Tp) + 0.1 * float(MAIN_PARAMS["alpha"]) * (orc.K @ T)
+    assert np.max(np.abs(F - Fo)) <= 1e-12 * np.max(np.abs(Fo))
+
+
 def test_p2_lattice_numbering_keeps_planes_and_runs():
     """The P2 numbering of the plate meshes: x half-planes are contiguous id ranges (distributed.slab_partition relies on
     it) and inside a plane consecutive ids run along the longest in-plane axis with even half-steps before odd ones, so
